@@ -1,0 +1,665 @@
+// libcfear_b200.so -- C ABI (include/cfear_b200.h) over the sm_100a kernels of the CFEAR per-scan hot path.
+// No CPU fallback: every entry point either runs the CUDA kernels or fails with CFEAR_ERR_CUDA /
+// CFEAR_ERR_NO_DEVICE.  Nothing here touches oracle/.
+#include "../../include/cfear_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "k1_kstrongest.cuh"
+#include "k3_surface.cuh"
+#include "k5_register.cuh"
+
+using namespace cfear;
+
+static thread_local std::string g_err;
+
+#define CK(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                \
+      return CFEAR_ERR_CUDA;                                                                      \
+    }                                                                                             \
+  } while (0)
+
+static_assert(sizeof(cfear_reg_stats) == sizeof(RegStatsDev), "stats layout");
+static_assert(sizeof(cfear_point) == sizeof(float4), "point layout");
+
+namespace cfear {
+
+// Row-padded points [nscans][A][k] -> dense cloud [nscans][cap] in row order (radar_filters.cpp:316-336 push_back order).
+__global__ void __launch_bounds__(512) k2_compact_rows(const float4* rowpts, const int32_t* rowcnt, int A, int k, int cap,
+                                                       float4* out, int32_t* nout) {
+  __shared__ int s_warp[33];
+  extern __shared__ int s_off[];
+  const int scan = blockIdx.x;
+  const int32_t* rc = rowcnt + (size_t)scan * A;
+  for (int a = threadIdx.x; a < A; a += blockDim.x) s_off[a] = rc[a];
+  __syncthreads();
+  const int n = block_array_excl_scan(s_off, A, s_warp);
+  const float4* src = rowpts + (size_t)scan * A * k;
+  float4* dst = out + (size_t)scan * cap;
+  for (int s = threadIdx.x; s < A * k; s += blockDim.x) {
+    const int a = s / k, j = s - a * k;
+    const int start = s_off[a];
+    const int cnt = ((a + 1 < A) ? s_off[a + 1] : n) - start;
+    if (j < cnt) dst[start + j] = src[s];
+  }
+  if (threadIdx.x == 0) nout[scan] = n;
+}
+
+// Compensate (utils.cpp:96-113) on a dense cloud.
+__global__ void k2b_compensate(float4* cloud, int n, double m0, double m1, double m2, int ccw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 pt = cloud[i];
+  const double x = (double)pt.x, y = (double)pt.y;
+  const double d = rel_time_stamp(x, y, ccw != 0);
+  double s1, c1; sincos(d * m2, &s1, &c1);
+  const double tx = c1 * x + (-s1) * y + d * m0;
+  const double ty = s1 * x + c1 * y + d * m1;
+  pt.x = (float)tx; pt.y = (float)ty;
+  cloud[i] = pt;
+}
+
+__global__ void k4b_nearest(CellPool pool, int slot, const double* q, int nq, double radius, int32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const NNGrid G = pool.grid[slot];
+  out[i] = nn_query(pool, slot, G, q[2 * i], q[2 * i + 1], radius);
+}
+
+// AoS cfear_cell <-> pool SoA
+struct CellAoS { double mean[2], normal[2], cov[4], planarity, avg_intensity; int32_t nsamples, pad; };
+__global__ void k_cells_gather(CellPool pool, int slot, CellAoS* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = (size_t)slot * pool.max_cells + i;
+  CellAoS c;
+  c.mean[0] = pool.mean[b].x; c.mean[1] = pool.mean[b].y;
+  c.normal[0] = pool.normal[b].x; c.normal[1] = pool.normal[b].y;
+  const double4 v = pool.cov[b];
+  c.cov[0] = v.x; c.cov[1] = v.y; c.cov[2] = v.z; c.cov[3] = v.w;
+  c.planarity = pool.planarity[b]; c.avg_intensity = pool.avg_intensity[b];
+  c.nsamples = pool.nsamples[b]; c.pad = 0;
+  out[i] = c;
+}
+__global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) pool.ncells[slot] = n;
+  if (i >= n) return;
+  const size_t b = (size_t)slot * pool.max_cells + i;
+  const CellAoS c = in[i];
+  pool.mean[b] = make_double2(c.mean[0], c.mean[1]);
+  pool.normal[b] = make_double2(c.normal[0], c.normal[1]);
+  pool.cov[b] = make_double4(c.cov[0], c.cov[1], c.cov[2], c.cov[3]);
+  pool.planarity[b] = c.planarity; pool.avg_intensity[b] = c.avg_intensity;
+  pool.nsamples[b] = c.nsamples;
+}
+
+}  // namespace cfear
+
+static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
+
+struct cfear_ctx {
+  cfear_config cfg;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_ev;
+  int64_t launches = 0;
+  int timing = 0;
+  float stage_ms[3] = {0, 0, 0};
+  int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0;
+  int g_hist_cap = 0;
+  std::vector<void*> allocs;
+  // device buffers
+  uint8_t* d_polar = nullptr; double2* d_cs = nullptr;
+  int32_t *d_kidx = nullptr, *d_kcnt = nullptr, *d_rowcnt = nullptr, *d_rowpeakcnt = nullptr, *d_npts = nullptr, *d_npeaks = nullptr;
+  float4 *d_rowcloud = nullptr, *d_rowpeaks = nullptr, *d_cloud = nullptr, *d_peaks = nullptr, *d_bufA = nullptr, *d_bufB = nullptr;
+  int* d_ghist = nullptr; int32_t* d_status = nullptr;
+  double* d_mot = nullptr; int32_t *d_slots = nullptr, *d_curslots = nullptr, *d_kfslots = nullptr;
+  double *d_poses = nullptr, *d_cov36 = nullptr; cfear_reg_stats* d_stats = nullptr; int32_t* d_assoc = nullptr;
+  double4* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
+  CellPool pool;
+  std::vector<double2> h_cs;
+
+  template <typename T> int alloc(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) { g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CFEAR_ERR_CUDA; }
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return CFEAR_OK;
+  }
+};
+
+#define AL(p, n)                                    \
+  do {                                              \
+    int rc__ = c->alloc(&(p), (size_t)(n));         \
+    if (rc__ != CFEAR_OK) { cfear_destroy(c); return rc__; } \
+  } while (0)
+
+extern "C" {
+
+const char* cfear_last_error(void) { return g_err.c_str(); }
+const char* cfear_version(void) { return "cfear_b200 0.1 (sm_100a)"; }
+
+void cfear_default_config(cfear_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0; cfg->max_batch = 1; cfg->azimuths = 400; cfg->range_bins = 3360; cfg->k_strongest = 12;
+  cfg->z_min = 60.f; cfg->range_res = 0.0438f; cfg->min_distance = 2.5f; cfg->radius = 3.5f;   // radar_driver.h:40-48
+  cfg->downsample_factor = 1.0; cfg->weight_intensity = 1; cfg->compensate = 1; cfg->radar_ccw = 0;
+  cfg->cost = CFEAR_COST_P2L; cfg->loss = CFEAR_LOSS_HUBER; cfg->weight_opt = CFEAR_WEIGHT_UNIFORM;
+  cfg->solver_mode = CFEAR_SOLVER_CERES_LM; cfg->loss_limit = 0.1; cfg->cov_scale = 1.0; cfg->regularization = 1.0;
+  cfg->reg_radius = 2.0; cfg->max_outer = 8; cfg->min_outer = 3; cfg->max_inner = 20; cfg->gn_iters = 10;
+  cfg->max_keyframes = 4; cfg->max_cellsets = 8; cfg->max_cells = 0;
+}
+
+void cfear_destroy(cfear_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* p : c->allocs) cudaFree(p);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->chunk_ev) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
+  if (!cfg || !out) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->azimuths < 1 || cfg->range_bins < 1 || cfg->k_strongest < 1 || cfg->k_strongest > K1_MAXK ||
+      cfg->max_batch < 1 || cfg->max_keyframes < 1 || cfg->max_keyframes + 1 > K5_MAXSCANS || cfg->max_cellsets < 1 ||
+      cfg->range_bins > 65535 || !(cfg->radius > 0.f) || !(cfg->downsample_factor > 0.0)) {
+    g_err = "invalid configuration (need 1<=k<=64, range_bins<=65535, max_keyframes<=64, radius>0)";
+    return CFEAR_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) {
+    g_err = "no CUDA device: the cfear_b200 path has no CPU fallback";
+    return CFEAR_ERR_NO_DEVICE;
+  }
+  cfear_ctx* c = new (std::nothrow) cfear_ctx();
+  if (!c) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
+  c->cfg = *cfg;
+  CK(cudaSetDevice(cfg->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) CK(cudaEventCreate(&e));
+  const int A = cfg->azimuths, R = cfg->range_bins, k = cfg->k_strongest, B = cfg->max_batch;
+  c->cap_pts = A * k;
+  c->max_cells = cfg->max_cells > 0 ? cfg->max_cells : A * k;
+  c->grid_cap = K3_HIST_CAP;
+  c->res_cap = cfg->max_keyframes * c->max_cells;
+  c->g_hist_cap = 1 << 18;
+  // shared-memory plan of K3
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+  const size_t hist_bytes = (size_t)(K3_HIST_CAP + 1) * sizeof(int);
+  const size_t full = (size_t)c->cap_pts * 32 + hist_bytes;
+  c->pts_in_smem = (full + 2048 <= (size_t)max_optin) ? 1 : 0;
+  c->k3_smem = c->pts_in_smem ? full : hist_bytes;
+  CK(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+  CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+
+  const size_t rows = (size_t)B * A;
+  AL(c->d_polar, rows * R);
+  AL(c->d_cs, A);
+  AL(c->d_kidx, rows * k); AL(c->d_kcnt, rows); AL(c->d_rowcnt, rows); AL(c->d_rowpeakcnt, rows);
+  AL(c->d_rowcloud, rows * k); AL(c->d_rowpeaks, rows * k);
+  AL(c->d_cloud, (size_t)B * c->cap_pts); AL(c->d_peaks, (size_t)B * c->cap_pts);
+  AL(c->d_npts, B); AL(c->d_npeaks, B); AL(c->d_status, B);
+  if (!c->pts_in_smem) { AL(c->d_bufA, (size_t)B * c->cap_pts); AL(c->d_bufB, (size_t)B * c->cap_pts); }
+  AL(c->d_ghist, (size_t)B * (c->g_hist_cap + 1));
+  AL(c->d_mot, (size_t)B * 3);
+  const int ns = cfg->max_keyframes + 1;
+  AL(c->d_slots, (size_t)B * ns); AL(c->d_curslots, B); AL(c->d_kfslots, (size_t)B * ns);
+  AL(c->d_poses, (size_t)B * ns * 3); AL(c->d_cov36, (size_t)B * 36); AL(c->d_stats, B);
+  AL(c->d_res, (size_t)B * c->res_cap * 4);
+  AL(c->d_cellaos, c->max_cells);
+  // cell pool
+  CellPool& P = c->pool;
+  const size_t S = (size_t)cfg->max_cellsets, M = (size_t)c->max_cells;
+  P.max_cells = c->max_cells; P.grid_cap = c->grid_cap;
+  AL(P.ncells, S); AL(P.mean, S * M); AL(P.normal, S * M); AL(P.cov, S * M); AL(P.planarity, S * M);
+  AL(P.avg_intensity, S * M); AL(P.nsamples, S * M); AL(P.grid, S); AL(P.gstart, S * (P.grid_cap + 1));
+  AL(P.gxy, S * M); AL(P.gidx, S * M); AL(P.fm_scratch, S * M);
+  CK(cudaMemsetAsync(P.ncells, 0, S * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(P.gstart, 0, S * (P.grid_cap + 1) * sizeof(int), c->stream));
+  {
+    std::vector<NNGrid> g(S);
+    for (auto& x : g) { x.ox = x.oy = 0.f; x.g = 4.f; x.inv_g = 0.25f; x.nx = x.ny = 1; }
+    CK(cudaMemcpyAsync(P.grid, g.data(), S * sizeof(NNGrid), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  // theta = 2 pi (a+1)/A  (radar_filters.cpp:317), host libm like the reference
+  c->h_cs.resize(A);
+  for (int a = 0; a < A; ++a) {
+    const double theta = ((double)(a + 1) / A) * 2. * M_PI;
+    c->h_cs[a] = make_double2(cos(theta), sin(theta));
+  }
+  CK(cudaMemcpyAsync(c->d_cs, c->h_cs.data(), A * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return CFEAR_OK;
+}
+
+int64_t cfear_launch_count(const cfear_ctx* c) { return c ? c->launches : 0; }
+void* cfear_stream(cfear_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int cfear_sync(cfear_ctx* c) {
+  if (!c) return CFEAR_ERR_ARG;
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+void* cfear_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  return p;
+}
+void cfear_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+void* cfear_alloc_device(cfear_ctx* c, size_t bytes) {
+  if (!c) return nullptr;
+  cudaSetDevice(c->cfg.device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { g_err = "cudaMalloc failed"; return nullptr; }
+  return p;
+}
+void cfear_free_device(cfear_ctx* c, void* p) { if (c && p) { cudaSetDevice(c->cfg.device); cudaFree(p); } }
+int cfear_memcpy_h2d(cfear_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c) return CFEAR_ERR_ARG;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+int cfear_memcpy_d2h(cfear_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c) return CFEAR_ERR_ARG;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+}  // extern "C"
+
+// ---- launch helpers (device-resident arguments) ----------------------------------------------------
+static int launch_k1(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
+  K1Params p;
+  p.polar = d_polar; p.nrows = nscans * c->cfg.azimuths; p.A = c->cfg.azimuths; p.R = c->cfg.range_bins;
+  p.polar_end = d_polar + (size_t)p.nrows * p.R;
+  p.zmin = (int)(uint8_t)(int)c->cfg.z_min;                                  // radar_driver.cpp:58, radar_filters.cpp:198,212
+  p.k = c->cfg.k_strongest;
+  const double range_res = (double)c->cfg.range_res, min_distance = (double)c->cfg.min_distance;
+  p.min_range_bin = (int)ceil(min_distance / range_res);                      // radar_filters.cpp:315
+  p.range_res = range_res; p.cs = c->d_cs;
+  p.kidx = c->d_kidx; p.kcnt = c->d_kcnt; p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
+  const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
+  k1_kstrongest<<<grid, K1_WARPS * 32, 0, c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return CFEAR_OK;
+}
+
+static int launch_peaks(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
+  PeaksParams p;
+  p.polar = d_polar; p.nrows = nscans * c->cfg.azimuths; p.A = c->cfg.azimuths; p.R = c->cfg.range_bins;
+  p.total = (long)p.nrows * p.R; p.k = c->cfg.k_strongest;
+  const double range_res = (double)c->cfg.range_res, min_distance = (double)c->cfg.min_distance;
+  p.min_range_bin = (int)ceil(min_distance / range_res);
+  p.range_res = range_res; p.cs = c->d_cs; p.kidx = c->d_kidx; p.kcnt = c->d_kcnt;
+  p.rowpeaks = c->d_rowpeaks; p.rowpeakcnt = c->d_rowpeakcnt;
+  k1b_peaks<<<(p.nrows + 7) / 8, 256, 0, c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return CFEAR_OK;
+}
+
+static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud) {
+  K3Params p;
+  p.mode = mode; p.A = c->cfg.azimuths; p.k = c->cfg.k_strongest;
+  p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
+  p.mot = (c->cfg.compensate && mode == 0) ? d_mot : nullptr; p.ccw = c->cfg.radar_ccw;
+  p.cloud = (mode == 1 || write_cloud) ? c->d_cloud : nullptr; p.npts = c->d_npts; p.cap_pts = c->cap_pts;
+  p.slots = d_slots; p.radius = c->cfg.radius;
+  p.leaf = (float)((double)c->cfg.radius / c->cfg.downsample_factor);        // pointnormal.cpp:279
+  p.weight_intensity = c->cfg.weight_intensity; p.origin_x = 0.0; p.origin_y = 0.0;   // odometrykeyframefuser.cpp:161
+  p.nn_cell = 4.0f;
+  p.pts_in_smem = c->pts_in_smem; p.g_bufA = c->d_bufA; p.g_bufB = c->d_bufB;
+  p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.pool = c->pool;
+  k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return CFEAR_OK;
+}
+
+static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
+                     cfear_reg_stats* d_stats, int32_t* d_assoc) {
+  RegParams p;
+  p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
+  p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res; p.res_cap = c->res_cap;
+  p.cost = c->cfg.cost; p.loss = c->cfg.loss; p.weight_opt = c->cfg.weight_opt; p.solver_mode = c->cfg.solver_mode;
+  p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
+  p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
+  p.radius = c->cfg.reg_radius;
+  k5_register<<<nprob, K5_THREADS, 0, c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return CFEAR_OK;
+}
+
+static int check_slot(cfear_ctx* c, int slot) {
+  if (slot < 0 || slot >= c->cfg.max_cellsets) { g_err = "cell-set slot out of range"; return CFEAR_ERR_ARG; }
+  return CFEAR_OK;
+}
+#define RC(expr) do { int rc__ = (expr); if (rc__ != CFEAR_OK) return rc__; } while (0)
+#define ENTER(c) do { if (!(c)) { g_err = "null context"; return CFEAR_ERR_ARG; } CK(cudaSetDevice((c)->cfg.device)); } while (0)
+
+extern "C" {
+
+int cfear_filter(cfear_ctx* c, const uint8_t* polar, int nscans, int32_t* idx_out, int32_t* cnt_out,
+                 cfear_point* cloud_out, int32_t* npts_out, cfear_point* peaks_out, int32_t* npeaks_out) {
+  ENTER(c);
+  if (!polar || nscans < 0) { g_err = "null image"; return CFEAR_ERR_ARG; }     // radar_driver.cpp:75-78
+  if (nscans > c->cfg.max_batch) { g_err = "nscans exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nscans == 0) return CFEAR_OK;
+  const int A = c->cfg.azimuths, R = c->cfg.range_bins, k = c->cfg.k_strongest;
+  const size_t rows = (size_t)nscans * A;
+  CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
+  RC(launch_k1(c, c->d_polar, nscans));
+  if (idx_out) CK(cudaMemcpyAsync(idx_out, c->d_kidx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (cnt_out) CK(cudaMemcpyAsync(cnt_out, c->d_kcnt, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (cloud_out || npts_out) {
+    k2_compact_rows<<<nscans, 512, A * sizeof(int), c->stream>>>(c->d_rowcloud, c->d_rowcnt, A, k, c->cap_pts, c->d_cloud, c->d_npts);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (cloud_out) CK(cudaMemcpyAsync(cloud_out, c->d_cloud, (size_t)nscans * c->cap_pts * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (npts_out) CK(cudaMemcpyAsync(npts_out, c->d_npts, nscans * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (peaks_out || npeaks_out) {
+    RC(launch_peaks(c, c->d_polar, nscans));
+    k2_compact_rows<<<nscans, 512, A * sizeof(int), c->stream>>>(c->d_rowpeaks, c->d_rowpeakcnt, A, k, c->cap_pts, c->d_peaks, c->d_npeaks);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (peaks_out) CK(cudaMemcpyAsync(peaks_out, c->d_peaks, (size_t)nscans * c->cap_pts * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (npeaks_out) CK(cudaMemcpyAsync(npeaks_out, c->d_npeaks, nscans * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_kstrongest(cfear_ctx* c, const uint8_t* polar, int nscans, int32_t* idx_out, int32_t* cnt_out) {
+  return cfear_filter(c, polar, nscans, idx_out, cnt_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+int cfear_compensate(cfear_ctx* c, cfear_point* cloud, int n, const double mot[3], int ccw) {
+  ENTER(c);
+  if (n < 0 || (n > 0 && !cloud) || !mot) { g_err = "bad cloud"; return CFEAR_ERR_ARG; }
+  if (n > c->cfg.max_batch * c->cap_pts) { g_err = "cloud exceeds capacity"; return CFEAR_ERR_CAPACITY; }
+  if (n == 0) return CFEAR_OK;
+  CK(cudaMemcpyAsync(c->d_cloud, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  k2b_compensate<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cloud, n, mot[0], mot[1], mot[2], ccw);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cloud, c->d_cloud, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_surface_points(cfear_ctx* c, const cfear_point* cloud, int n, int slot, int32_t* ncells) {
+  ENTER(c);
+  RC(check_slot(c, slot));
+  if (n < 0 || (n > 0 && !cloud)) { g_err = "bad cloud"; return CFEAR_ERR_ARG; }
+  if (n > c->cap_pts) { g_err = "cloud exceeds azimuths*k_strongest points"; return CFEAR_ERR_CAPACITY; }
+  if (n > 0) CK(cudaMemcpyAsync(c->d_cloud, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  const int32_t n32 = n, s32 = slot;
+  CK(cudaMemcpyAsync(c->d_npts, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  RC(launch_k3(c, 1, 1, nullptr, c->d_curslots, false));
+  int32_t st = 0, nc = 0;
+  CK(cudaMemcpyAsync(&st, c->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&nc, c->pool.ncells + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (st != 0) { g_err = "voxel grid exceeds capacity (extent / leaf too large)"; return CFEAR_ERR_CAPACITY; }
+  if (ncells) *ncells = nc;
+  return CFEAR_OK;
+}
+
+int cfear_cells_count(cfear_ctx* c, int slot, int32_t* ncells) {
+  ENTER(c);
+  RC(check_slot(c, slot));
+  if (!ncells) { g_err = "null output"; return CFEAR_ERR_ARG; }
+  CK(cudaMemcpyAsync(ncells, c->pool.ncells + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_cells_download(cfear_ctx* c, int slot, cfear_cell* out, int capacity, int32_t* ncells) {
+  ENTER(c);
+  RC(check_slot(c, slot));
+  int32_t n = 0;
+  CK(cudaMemcpyAsync(&n, c->pool.ncells + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (ncells) *ncells = n;
+  if (!out) return CFEAR_OK;
+  if (capacity < n) { g_err = "output capacity too small"; return CFEAR_ERR_CAPACITY; }
+  if (n == 0) return CFEAR_OK;
+  k_cells_gather<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pool, slot, c->d_cellaos, n);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, c->d_cellaos, (size_t)n * sizeof(CellAoS), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_cells_upload(cfear_ctx* c, int slot, const cfear_cell* cells, int n) {
+  ENTER(c);
+  RC(check_slot(c, slot));
+  if (n < 0 || (n > 0 && !cells)) { g_err = "bad cells"; return CFEAR_ERR_ARG; }
+  if (n > c->max_cells) { g_err = "cell set exceeds max_cells"; return CFEAR_ERR_CAPACITY; }
+  if (n > 0) CK(cudaMemcpyAsync(c->d_cellaos, cells, (size_t)n * sizeof(CellAoS), cudaMemcpyHostToDevice, c->stream));
+  k_cells_scatter<<<(std::max(n, 1) + 255) / 256, 256, 0, c->stream>>>(c->pool, slot, c->d_cellaos, n);
+  c->launches++;
+  CK(cudaGetLastError());
+  const int32_t s32 = slot;
+  CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = 4.0f;
+  k4_build_index<<<1, K3_THREADS, (K3_HIST_CAP + 1) * sizeof(int), c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_nearest(cfear_ctx* c, int slot, const double* queries_xy, int nq, double radius, int32_t* out_idx) {
+  ENTER(c);
+  RC(check_slot(c, slot));
+  if (nq < 0 || (nq > 0 && (!queries_xy || !out_idx))) { g_err = "bad queries"; return CFEAR_ERR_ARG; }
+  if (nq == 0) return CFEAR_OK;
+  double* dq = nullptr; int32_t* dout = nullptr;
+  CK(cudaMallocAsync(&dq, (size_t)nq * 2 * sizeof(double), c->stream));
+  CK(cudaMallocAsync(&dout, (size_t)nq * sizeof(int32_t), c->stream));
+  CK(cudaMemcpyAsync(dq, queries_xy, (size_t)nq * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k4b_nearest<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->pool, slot, dq, nq, radius, dout);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_idx, dout, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaFreeAsync(dq, c->stream));
+  CK(cudaFreeAsync(dout, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_register_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nscans, double* poses, double* cov36,
+                         cfear_reg_stats* stats, int32_t* assoc_out) {
+  ENTER(c);
+  if (nprob < 0 || !slots || !poses) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (nscans < 2 || nscans > c->cfg.max_keyframes + 1) { g_err = "nscans must be in [2, max_keyframes+1]"; return CFEAR_ERR_ARG; }   // n_scan_normal.cpp:190
+  if (nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nprob == 0) return CFEAR_OK;
+  for (size_t i = 0; i < (size_t)nprob * nscans; ++i) RC(check_slot(c, slots[i]));
+  CK(cudaMemcpyAsync(c->d_slots, slots, (size_t)nprob * nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const size_t assoc_n = (size_t)nprob * (nscans - 1) * c->max_cells;
+  if (assoc_out) {
+    if (!c->d_assoc) {
+      int rc = c->alloc(&c->d_assoc, (size_t)c->cfg.max_batch * c->cfg.max_keyframes * c->max_cells);
+      if (rc != CFEAR_OK) return rc;
+    }
+    CK(cudaMemsetAsync(c->d_assoc, 0xff, assoc_n * sizeof(int32_t), c->stream));
+  }
+  RC(launch_k5(c, nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, assoc_out ? c->d_assoc : nullptr));
+  CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
+  if (assoc_out) CK(cudaMemcpyAsync(assoc_out, c->d_assoc, assoc_n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_register(cfear_ctx* c, const int32_t* slots, int nscans, double* poses, double* cov36, cfear_reg_stats* stats) {
+  return cfear_register_batch(c, 1, slots, nscans, poses, cov36, stats, nullptr);
+}
+
+// d_kf_slots [nprob][K], d_cur_slots [nprob] -> d_slots [nprob][K+1]
+__global__ void k_merge_slots(const int32_t* kf, const int32_t* cur, int K, int nprob, int32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nprob * (K + 1)) return;
+  const int b = i / (K + 1), j = i - b * (K + 1);
+  out[i] = (j < K) ? kf[b * K + j] : cur[b];
+}
+
+static int step_dev(cfear_ctx* c, int nprob, const uint8_t* d_polar, const double* d_mot, const int32_t* d_kf_slots, int K,
+                    const int32_t* d_cur_slots, double* d_poses, double* d_cov36, cfear_reg_stats* d_stats, bool k1_done) {
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  if (!k1_done) RC(launch_k1(c, d_polar, nprob));
+  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  RC(launch_k3(c, 0, nprob, d_mot, d_cur_slots, false));
+  if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf_slots, d_cur_slots, K, nprob, c->d_slots);
+  c->launches++;
+  CK(cudaGetLastError());
+  RC(launch_k5(c, nprob, K + 1, c->d_slots, d_poses, d_cov36, d_stats, nullptr));
+  if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_odometry_step_batch_dev(cfear_ctx* c, int nprob, const uint8_t* d_polar, const double* d_mot,
+                                  const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
+                                  double* d_poses, double* d_cov36, cfear_reg_stats* d_stats) {
+  ENTER(c);
+  if (!d_polar || !d_kf_slots || !d_cur_slots || !d_poses || !d_cov36 || !d_stats) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (K < 1 || K > c->cfg.max_keyframes) { g_err = "K must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
+  if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nprob == 0) return CFEAR_OK;
+  return step_dev(c, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats, false);
+}
+
+int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, const double* mot,
+                              const int32_t* kf_slots, int K, const int32_t* cur_slots,
+                              double* poses, double* cov36, cfear_reg_stats* stats,
+                              int32_t* npts_out, int32_t* ncells_out) {
+  ENTER(c);
+  if (!polar || !kf_slots || !cur_slots || !poses) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (K < 1 || K > c->cfg.max_keyframes) { g_err = "K must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
+  if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nprob == 0) return CFEAR_OK;
+  for (int i = 0; i < nprob * K; ++i) RC(check_slot(c, kf_slots[i]));
+  for (int i = 0; i < nprob; ++i) RC(check_slot(c, cur_slots[i]));
+  const int A = c->cfg.azimuths, R = c->cfg.range_bins;
+  const size_t img = (size_t)A * R;
+  // small arguments first, then the images in chunks on the copy stream so K1 of chunk i overlaps the
+  // host->device copy of chunk i+1
+  int32_t* d_kf = c->d_kfslots;
+  CK(cudaMemcpyAsync(d_kf, kf_slots, (size_t)nprob * K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_curslots, cur_slots, (size_t)nprob * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * (K + 1) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const bool have_mot = mot != nullptr && c->cfg.compensate;
+  if (have_mot) CK(cudaMemcpyAsync(c->d_mot, mot, (size_t)nprob * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int chunk = 16;
+  const int nchunks = (nprob + chunk - 1) / chunk;
+  while ((int)c->chunk_ev.size() < nchunks + 1) {
+    cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->chunk_ev.push_back(e);
+  }
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  CK(cudaEventRecord(c->chunk_ev[nchunks], c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nchunks], 0));          // d_polar free (previous work done)
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int b0 = ch * chunk, nb = std::min(chunk, nprob - b0);
+    CK(cudaMemcpyAsync(c->d_polar + b0 * img, polar + b0 * img, nb * img, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->chunk_ev[ch], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->chunk_ev[ch], 0));
+    // K1 on this chunk (row-indexed outputs are offset by the chunk)
+    K1Params p;
+    p.polar = c->d_polar + b0 * img; p.nrows = nb * A; p.A = A; p.R = R;
+    p.polar_end = c->d_polar + (size_t)nprob * img;
+    p.zmin = (int)(uint8_t)(int)c->cfg.z_min; p.k = c->cfg.k_strongest;
+    const double range_res = (double)c->cfg.range_res, min_distance = (double)c->cfg.min_distance;
+    p.min_range_bin = (int)ceil(min_distance / range_res); p.range_res = range_res; p.cs = c->d_cs;
+    const size_t r0 = (size_t)b0 * A;
+    p.kidx = c->d_kidx + r0 * p.k; p.kcnt = c->d_kcnt + r0; p.rowcloud = c->d_rowcloud + r0 * p.k; p.rowcnt = c->d_rowcnt + r0;
+    k1_kstrongest<<<(p.nrows + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, c->stream>>>(p);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  const int timing = c->timing;
+  c->timing = 0;                       // ev[0] already recorded; record the rest here
+  if (timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  RC(launch_k3(c, 0, nprob, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
+  if (timing) CK(cudaEventRecord(c->ev[2], c->stream));
+  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf, c->d_curslots, K, nprob, c->d_slots);
+  c->launches++;
+  CK(cudaGetLastError());
+  RC(launch_k5(c, nprob, K + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr));
+  if (timing) CK(cudaEventRecord(c->ev[3], c->stream));
+  c->timing = timing;
+  CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * (K + 1) * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
+  if (npts_out) CK(cudaMemcpyAsync(npts_out, c->d_npts, (size_t)nprob * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (ncells_out) RC(cfear_last_counts(c, nprob, cur_slots, nullptr, ncells_out));
+  return CFEAR_OK;
+}
+
+int cfear_stage_timing(cfear_ctx* c, int enable, float ms_out[3]) {
+  ENTER(c);
+  if (ms_out) {
+    ms_out[0] = ms_out[1] = ms_out[2] = 0.f;
+    if (c->timing) {
+      CK(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i < 3; ++i)
+        if (cudaEventElapsedTime(&ms_out[i], c->ev[i], c->ev[i + 1]) != cudaSuccess) { ms_out[i] = 0.f; (void)cudaGetLastError(); }
+    }
+  }
+  c->timing = enable;
+  return CFEAR_OK;
+}
+
+int cfear_last_counts(cfear_ctx* c, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out) {
+  ENTER(c);
+  if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (npts_out) CK(cudaMemcpyAsync(npts_out, c->d_npts, (size_t)nprob * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (ncells_out) {
+    if (!cur_slots) { g_err = "null slots"; return CFEAR_ERR_ARG; }
+    std::vector<int32_t> all(c->cfg.max_cellsets);
+    CK(cudaMemcpyAsync(all.data(), c->pool.ncells, all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nprob; ++i) { RC(check_slot(c, cur_slots[i])); ncells_out[i] = all[cur_slots[i]]; }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared device helpers and device-side data layout for the CFEAR hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfear {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident cell-set pool (SoA).  Slot s occupies [s*max_cells, (s+1)*max_cells) of each array.
+// This is what MapPointNormal holds for the pose path (pointnormal.h:66-73,196-199): cells + the
+// 2-D nearest-neighbour index over fp32 cell means (kd_cells), here a uniform bucket grid.
+// ------------------------------------------------------------------------------------------------
+struct NNGrid {            // per slot
+  float ox, oy, inv_g, g;  // origin, 1/cell, cell
+  int nx, ny;              // dims (nx*ny <= grid_cap)
+};
+
+struct CellPool {
+  int max_cells;
+  int grid_cap;            // max grid cells per slot
+  int* ncells;             // [slots]
+  double2* mean;           // u_
+  double2* normal;         // snormal_
+  double4* cov;            // cov_ row-major (xx, xy, yx, yy)
+  double* planarity;       // scale_
+  double* avg_intensity;
+  int* nsamples;
+  // NN index
+  NNGrid* grid;            // [slots]
+  int* gstart;             // [slots][grid_cap+1]
+  float2* gxy;             // [slots][max_cells]  fp32 means sorted by grid cell
+  int* gidx;               // [slots][max_cells]  original cell index
+  float2* fm_scratch;      // [slots][max_cells]  fp32 means staging for the index build of uploaded sets
+};
+
+// ------------------------------------------------------------------------------------------------
+// warp / block primitives
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(FULL, v, d);
+    if (lane_id() >= d) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread.  s_warp: >= 33 ints of shared memory.
+// Returns the exclusive prefix; *total gets the block sum.  Contains __syncthreads().
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
+  const int incl = warp_incl_scan(v);
+  const int nw = (blockDim.x + 31) >> 5;
+  __syncthreads();                         // protect s_warp reuse
+  if (lane_id() == 31) s_warp[warp_id()] = incl;
+  __syncthreads();
+  if (warp_id() == 0) {
+    int w = lane_id() < nw ? s_warp[lane_id()] : 0;
+    int wi = warp_incl_scan(w);
+    s_warp[lane_id()] = wi - w;            // exclusive warp offsets
+    if (lane_id() == 31) s_warp[32] = wi;  // total
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp_id()] + incl - v;
+}
+
+// In-place exclusive scan of an int array of length n (global or shared) by the whole block.
+// After the call a[i] = sum_{j<i} old a[j]; returns the total.  a must have room for n entries.
+__device__ inline int block_array_excl_scan(int* a, int n, int* s_warp) {
+  const int T = blockDim.x;
+  const int chunk = (n + T - 1) / T;
+  const int lo = min(threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += a[i];
+  int total;
+  int base = block_excl_scan(s, s_warp, &total);
+  for (int i = lo; i < hi; ++i) { int t = a[i]; a[i] = base; base += t; }
+  __syncthreads();
+  return total;
+}
+
+}  // namespace cfear

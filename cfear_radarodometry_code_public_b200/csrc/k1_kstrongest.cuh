@@ -1,0 +1,283 @@
+// K1: k-strongest filter + polar->Cartesian cloud rows.
+// Replaces StructuredKStrongest::FilterKstrongest (radar_filters.cpp:209-237) and
+// getPeaksFilteredPointCloud (radar_filters.cpp:309-337) of the reference.
+//
+// One warp per azimuth row.  The row (R uint8, 3360 B on Navtech data) is streamed once from HBM
+// with 16-byte non-allocating loads (8 in flight per lane), tested against z_min with SWAR byte
+// compares, the (sparse) candidates are packed as keys (intensity<<16 | range) into a per-warp
+// shared-memory list, and the k largest keys are selected exactly:
+//   lexicographic (intensity, range) order == integer order of the key, so ties go to the larger
+//   range bin exactly like the reference's sorted-insert / erase-front loop.
+// Algorithmic HBM bytes per row: R (read) + 4k+4 (indices) + 16k+4 (cloud row).
+#pragma once
+#include "common.cuh"
+
+namespace cfear {
+
+constexpr int K1_WARPS = 8;       // warps (rows) per CTA
+constexpr int K1_CAP = 256;       // candidate keys per warp kept in shared memory
+constexpr int K1_TILES = 8;       // uint4 per lane per super-tile (8*512 B = 4096 B of row in registers)
+constexpr int K1_MAXK = 64;       // k_strongest <= 64
+
+struct K1Params {
+  const uint8_t* polar;      // [nrows][R]
+  const uint8_t* polar_end;  // polar + nrows*R
+  int nrows;                 // nscans * A
+  int A, R;
+  int zmin;                  // already uchar(int(z_min))
+  int k;
+  int min_range_bin;         // ceil(min_distance / range_res)
+  double range_res;
+  const double2* cs;         // [A] (cos theta, sin theta), theta = 2 pi (a+1)/A, host libm
+  int32_t* kidx;             // [nrows][k]
+  int32_t* kcnt;             // [nrows]
+  float4* rowcloud;          // [nrows][k]  points passing the min-range cut, ascending (intensity, range)
+  int32_t* rowcnt;           // [nrows]
+};
+
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// 16 bytes at p (16-B aligned); bytes outside [lo, hi) read as 0 without touching memory.
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+  if (p >= lo && p + 16 <= hi) return ld_stream16(p);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint8_t* q = p + i;
+    if (q >= lo && q < hi) w[i >> 2] |= (uint32_t)(*q) << (8 * (i & 3));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// bit7 of each byte set iff byte >= z_min.  addc = (0x80 - (zmin&0x7f)) * 0x01010101.
+__device__ __forceinline__ uint32_t ge_flags(uint32_t x, uint32_t addc, bool zhi) {
+  const uint32_t a = (x & 0x7f7f7f7fu) + addc;     // bit7: low 7 bits >= low 7 bits of zmin; no cross-byte carry
+  return zhi ? (x & a & 0x80808080u) : ((x | a) & 0x80808080u);
+}
+
+// flags of a uint4 packed in one word: byte b of word w -> bit 8b + 7 - w
+__device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc, bool zhi) {
+  return ge_flags(d.x, addc, zhi) | (ge_flags(d.y, addc, zhi) >> 1) | (ge_flags(d.z, addc, zhi) >> 2) |
+         (ge_flags(d.w, addc, zhi) >> 3);
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params p) {
+  __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
+  __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
+  __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
+  const int grow = blockIdx.x * K1_WARPS + warp_id();
+  if (grow >= p.nrows) return;                 // no block-level sync in this kernel
+  const int lane = lane_id();
+  uint32_t* cand = s_cand[warp_id()];
+  uint32_t* sel = s_sel[warp_id()];
+  uint32_t* outk = s_out[warp_id()];
+
+  const int R = p.R, k = p.k;
+  const uint8_t* row = p.polar + (size_t)grow * R;
+  const int off = (int)((uintptr_t)row & 15);
+  const uint8_t* base = row - off;
+  const int nvec = (off + R + 15) >> 4;
+  const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
+  const bool zhi = p.zmin >= 128;
+
+  // ---- pass 1: stream the row, collect candidate keys ------------------------------------------
+  int C = 0;                                   // warp-uniform candidate count
+  for (int v0 = 0; v0 < nvec; v0 += 32 * K1_TILES) {
+    uint4 d[K1_TILES];
+#pragma unroll
+    for (int i = 0; i < K1_TILES; ++i) {
+      const int v = v0 + i * 32 + lane;
+      d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
+    }
+    uint32_t g[K1_TILES];
+    int nl = 0;
+#pragma unroll
+    for (int i = 0; i < K1_TILES; ++i) {
+      const int v = v0 + i * 32 + lane;
+      uint32_t m = ge_flags16(d[i], addc, zhi);
+      const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
+      if (v >= nvec) m = 0;
+      else if (b0 < 0 || b0 + 16 > R) {        // row head / tail: drop bytes of neighbouring rows
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = b0 + j;
+          if (r >= 0 && r < R) keep |= 1u << (8 * (j & 3) + 7 - (j >> 2));
+        }
+        m &= keep;
+      }
+      g[i] = m;
+      nl += __popc(m);
+    }
+    const int incl = warp_incl_scan(nl);
+    const int tot = __shfl_sync(FULL, incl, 31);
+    if (C + tot <= K1_CAP) {
+      int pos = C + incl - nl;
+#pragma unroll
+      for (int i = 0; i < K1_TILES; ++i) {
+        uint32_t m = g[i];
+        const int rb = (v0 + i * 32 + lane) * 16 - off;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int b = bit >> 3, w = 7 - (bit & 7);
+          const uint32_t word = (w == 0) ? d[i].x : (w == 1) ? d[i].y : (w == 2) ? d[i].z : d[i].w;
+          const uint32_t inten = (word >> (8 * b)) & 0xffu;
+          cand[pos++] = (inten << 16) | (uint32_t)(rb + 4 * w + b);
+        }
+      }
+    }
+    C += tot;
+  }
+  __syncwarp();
+
+  // ---- pass 2: exact top-k of the keys -----------------------------------------------------------
+  const int kk = min(k, C);
+  const uint32_t* work = cand;
+  int nwork = C;
+  if (C > K1_MAXK) {
+    // radix select: largest T with #(key >= T) >= k.  Keys are distinct, so #(key >= T) == k.
+    uint32_t T = 0;
+    const bool in_smem = (C <= K1_CAP);
+    for (int bit = 23; bit >= 0; --bit) {
+      const uint32_t Tt = T | (1u << bit);
+      int c = 0;
+      if (in_smem) {
+        for (int j = lane; j < C; j += 32) c += (cand[j] >= Tt);
+      } else {   // candidate list overflowed (saturated row): re-read the row (L1/L2 resident)
+        for (int r = lane; r < R; r += 32) c += ((((uint32_t)row[r]) << 16 | (uint32_t)r) >= Tt);
+      }
+      c = __reduce_add_sync(FULL, c);
+      if (c >= k) T = Tt;
+    }
+    int nb = 0;
+    const int n_iter = in_smem ? C : R;
+    for (int j0 = 0; j0 < n_iter; j0 += 32) {
+      const int j = j0 + lane;
+      uint32_t key = 0;
+      if (j < n_iter) key = in_smem ? cand[j] : (((uint32_t)row[j]) << 16 | (uint32_t)j);
+      const bool s = (j < n_iter) && key >= T;
+      const unsigned bal = __ballot_sync(FULL, s);
+      if (s) sel[nb + __popc(bal & ((1u << lane) - 1))] = key;
+      nb += __popc(bal);
+    }
+    __syncwarp();
+    work = sel;
+    nwork = k;
+  }
+  // rank by counting among <= 64 keys; ascending output position = kk-1-rank_desc
+  for (int j = lane; j < nwork; j += 32) {
+    const uint32_t key = work[j];
+    int rank = 0;
+    for (int m = 0; m < nwork; ++m) rank += (work[m] > key);
+    if (rank < kk) outk[kk - 1 - rank] = key;
+  }
+  __syncwarp();
+
+  // ---- outputs: index set (parity target) + cloud row ---------------------------------------------
+  const int a = grow % p.A;
+  const double2 cs = p.cs[a];
+  const double half = p.range_res / 2.0;
+  int ncloud = 0;
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    const int j = j0 + lane;
+    const bool have = j < kk;
+    const uint32_t key = have ? outk[j] : 0u;
+    const int r = (int)(key & 0xffffu);
+    if (j < k) p.kidx[(size_t)grow * k + j] = have ? r : -1;
+    const bool pass = have && r > p.min_range_bin;            // radar_filters.cpp:327
+    const unsigned bal = __ballot_sync(FULL, pass);
+    if (pass) {
+      // (range_res/2 + range_res*range) * cos/sin in double, rounded once to float (:329-330); no FMA contraction
+      const double rho = __dadd_rn(half, __dmul_rn(p.range_res, (double)r));
+      float4 pt;
+      pt.x = __double2float_rn(__dmul_rn(rho, cs.x));
+      pt.y = __double2float_rn(__dmul_rn(rho, cs.y));
+      pt.z = 0.f;
+      pt.w = (float)(key >> 16);
+      p.rowcloud[(size_t)grow * k + ncloud + __popc(bal & ((1u << lane) - 1))] = pt;
+    }
+    ncloud += __popc(bal);
+  }
+  if (lane == 0) { p.kcnt[grow] = kk; p.rowcnt[grow] = ncloud; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peaks cloud: StructuredKStrongest::AxialNonMaxSupress (radar_filters.cpp:238-298).  Off the pose
+// path (the reference stores the peaks cloud but never uses it for registration); one thread per
+// kept bin, scores recomputed from the image.  Reads outside the row index the flat image buffer
+// like the reference's unchecked cv::Mat::at, clamped to the buffer.
+// ------------------------------------------------------------------------------------------------
+struct PeaksParams {
+  const uint8_t* polar; long total;  // nscans*A*R bytes
+  int nrows, A, R, k, min_range_bin; double range_res; const double2* cs;
+  const int32_t* kidx; const int32_t* kcnt;
+  float4* rowpeaks; int32_t* rowpeakcnt;   // [nrows][k], [nrows]
+};
+
+__device__ __forceinline__ int peaks_score(const PeaksParams& p, long rowbase, int r_n) {
+  int s = 0;
+#pragma unroll
+  for (int d = -3; d <= 3; ++d) {
+    long f = rowbase + r_n + d;
+    f = f < 0 ? 0 : (f >= p.total ? p.total - 1 : f);
+    s += p.polar[f];
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k1b_peaks(const PeaksParams p) {
+  const int grow = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (grow >= p.nrows) return;
+  const int lane = lane_id();
+  const int W = 3, R = p.R, k = p.k;
+  const int cnt = p.kcnt[grow];
+  const long rowbase = (long)grow * R;
+  const int a = grow % p.A;
+  const double2 cs = p.cs[a];
+  const double half = p.range_res / 2.0;
+  int nout = 0;
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    const int j = j0 + lane;
+    bool keep = false;
+    int r = 0;
+    if (j < cnt) {
+      r = p.kidx[(size_t)grow * k + j];
+      // score[x] exists iff x is within +-W of an in-guard kept bin (:251-263); missing keys read as 0 (:271-276)
+      auto have = [&](int x) {
+        for (int m = 0; m < cnt; ++m) {
+          const int q = p.kidx[(size_t)grow * k + m];
+          if (q >= W && q < R - W && x >= q - W && x <= q + W) return true;
+        }
+        return false;
+      };
+      auto sc = [&](int x) { return have(x) ? peaks_score(p, rowbase, x) : 0; };
+      const int pthis = sc(r);
+      keep = true;
+      for (int i = 1; i <= W; ++i) {
+        const int pnext = sc(r + i), pprev = sc(r - i);
+        if (pprev > pthis || pthis < pnext) { keep = false; break; }   // :282
+      }
+    }
+    const bool pass = keep && r > p.min_range_bin;
+    const unsigned bal = __ballot_sync(FULL, pass);
+    if (pass) {
+      const double rho = __dadd_rn(half, __dmul_rn(p.range_res, (double)r));
+      float4 pt;
+      pt.x = __double2float_rn(__dmul_rn(rho, cs.x));
+      pt.y = __double2float_rn(__dmul_rn(rho, cs.y));
+      pt.z = 0.f;
+      pt.w = (float)p.polar[rowbase + r];
+      p.rowpeaks[(size_t)grow * k + nout + __popc(bal & ((1u << lane) - 1))] = pt;
+    }
+    nout += __popc(bal);
+  }
+  if (lane == 0) p.rowpeakcnt[grow] = nout;
+}
+
+}  // namespace cfear

@@ -1,0 +1,454 @@
+// K2/K3/K4: cloud assembly (+ motion compensation), voxel centroids, oriented surface points and the
+// nearest-neighbour index over the cell means -- one CTA per scan, everything between the row-cloud
+// read and the cell-set write stays in shared memory.
+//
+// Replaces, for one scan:
+//   Compensate(cloud, Tmot, ccw)                         utils.cpp:96-113, utils.h:28-32
+//   MapPointNormal::MapPointNormal / ComputeNormals      pointnormal.cpp:65-90, 265-297
+//     pcl::VoxelGrid (leaf = radius/downsample_factor)   pointnormal.cpp:277-280
+//     kd-tree radiusSearch(centroid, radius) >= 6        pointnormal.cpp:291
+//     cell::cell + cell::ComputeNormal                   pointnormal.cpp:7-63
+//   MapPointNormal::ComputeSearchTreeFromCells           pointnormal.cpp:151-162
+//
+// Data flow (smem unless the cloud is too large, then the same code runs on global scratch):
+//   bufA <- TMA bulk copy (cp.async.bulk + mbarrier) of the scan's padded row cloud [A][k] float4
+//   bufA: in-place left compaction (row order = the reference's push_back order) + Compensate
+//   hist: voxel histogram -> exclusive scan -> scatter bufA -> bufB (bucketed by voxel)
+//   per voxel: order by input index, fp32 centroid (sequential sum like VoxelGrid) -> cxy list (in bufA)
+//   per centroid: exact fp32 radius test over the 3x3 voxel neighbourhood in bufB, fp64 weighted
+//   mean / covariance / closed-form 2x2 eigen -> validity -> ordered compaction into the cell slot
+//   fp32 means -> bucket grid (counting sort through hist) -> gstart / gxy / gidx of the slot
+#pragma once
+#include "common.cuh"
+
+namespace cfear {
+
+constexpr int K3_THREADS = 512;
+constexpr int K3_HIST_CAP = 16384;        // voxel / NN-grid bins kept in shared memory
+
+struct K3Params {
+  // input mode 0: padded row clouds from K1;  mode 1: ready clouds (already compensated) in `cloud`
+  int mode;
+  int A, k;                    // rows per scan, slots per row (mode 0)
+  const float4* rowcloud;      // [nscans][A][k]
+  const int32_t* rowcnt;       // [nscans][A]
+  const double* mot;           // [nscans][3] previous motion (x, y, yaw) or nullptr = no compensation
+  int ccw;
+  float4* cloud;               // [nscans][cap_pts] out (mode 0, may be null) / in (mode 1)
+  int32_t* npts;               // [nscans] out (mode 0) / in (mode 1)
+  int cap_pts;                 // capacity of one cloud (A*k)
+  const int32_t* slots;        // [nscans] destination cell-set slot
+  float radius;                // "res"
+  float leaf;                  // float(radius / downsample_factor)
+  int weight_intensity;
+  double origin_x, origin_y;
+  float nn_cell;               // bucket size of the NN grid (metres)
+  int pts_in_smem;             // 1: bufA/bufB in shared memory
+  float4* g_bufA; float4* g_bufB;   // [nscans][cap_pts] global fallback
+  int* g_hist; int g_hist_cap;      // [nscans][g_hist_cap+1] global fallback for large grids
+  int32_t* status;             // [nscans] 0 ok, 1 voxel grid over capacity
+  CellPool pool;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (bytes % 16 == 0, 16-B aligned).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// utils.h:28-32 GetRelTimeStamp
+__device__ __forceinline__ double rel_time_stamp(double x, double y, bool ccw) {
+  const double a = atan2(y, x);
+  const double d = ((a > 0.00001 ? a : (2 * M_PI + a)) / (2 * M_PI));
+  return ccw ? -(d - 0.5) : (d - 0.5);
+}
+
+// closed-form symmetric 2x2 eigen decomposition: (a b; b d) -> ascending eigenvalues, unit eigenvectors
+struct Eig2 { double lmin, lmax, nx, ny; };
+__device__ __forceinline__ Eig2 eig2_sym(double a, double b, double d) {
+  Eig2 e;
+  const double t = 0.5 * (a - d), m = 0.5 * (a + d);
+  const double h = sqrt(t * t + b * b);
+  e.lmax = m + h; e.lmin = m - h;
+  double vx, vy;
+  if (h == 0.0) { vx = 1.0; vy = 0.0; }
+  else if (t >= 0.0) { vx = t + h; vy = b; }
+  else { vx = b; vy = h - t; }
+  const double nrm = sqrt(vx * vx + vy * vy);
+  if (nrm > 0.0) { vx /= nrm; vy /= nrm; } else { vx = 1.0; vy = 0.0; }
+  e.nx = -vy; e.ny = vx;
+  return e;
+}
+
+__device__ __forceinline__ float block_min_f(float v, float* s_red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, d));
+  __syncthreads();
+  if (lane_id() == 0) s_red[warp_id()] = v;
+  __syncthreads();
+  float r = s_red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fminf(r, s_red[w]);
+  return r;
+}
+__device__ __forceinline__ float block_max_f(float v, float* s_red) { return -block_min_f(-v, s_red); }
+
+// Build the bucket grid over n fp32 means (fm in shared or global memory) into slot arrays.
+// hist: >= hist_cap+1 ints of scratch.  Whole block participates.
+__device__ inline void build_nn_grid(const CellPool& pool, int slot, const float2* fm, int n, float nn_cell,
+                                     int* hist, int hist_cap, int* s_warp, float* s_red) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+  for (int i = tid; i < n; i += T) {
+    const float2 p = fm[i];
+    mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x); mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
+  }
+  mnx = block_min_f(mnx, s_red); mny = block_min_f(mny, s_red);
+  mxx = block_max_f(mxx, s_red); mxy = block_max_f(mxy, s_red);
+  if (n == 0) { mnx = mny = mxx = mxy = 0.f; }
+  float g = nn_cell;
+  int nx, ny;
+  for (;;) {
+    nx = (int)floorf((mxx - mnx) / g) + 1; ny = (int)floorf((mxy - mny) / g) + 1;
+    if ((long long)nx * ny <= hist_cap) break;
+    g *= 2.f;
+  }
+  const float inv = 1.0f / g;
+  const int nb = nx * ny;
+  for (int b = tid; b <= nb; b += T) hist[b] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const float2 p = fm[i];
+    int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
+    bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
+    atomicAdd(&hist[bx + by * nx], 1);
+  }
+  __syncthreads();
+  block_array_excl_scan(hist, nb + 1, s_warp);      // hist[b] = start of bucket b, hist[nb] = n
+  int* gstart = pool.gstart + (size_t)slot * (pool.grid_cap + 1);
+  for (int b = tid; b <= nb; b += T) gstart[b] = hist[b];
+  __syncthreads();
+  float2* gxy = pool.gxy + (size_t)slot * pool.max_cells;
+  int* gidx = pool.gidx + (size_t)slot * pool.max_cells;
+  for (int i = tid; i < n; i += T) {
+    const float2 p = fm[i];
+    int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
+    bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
+    const int pos = atomicAdd(&hist[bx + by * nx], 1);
+    gxy[pos] = p; gidx[pos] = i;
+  }
+  if (tid == 0) {
+    NNGrid G; G.ox = mnx; G.oy = mny; G.inv_g = inv; G.g = g; G.nx = nx; G.ny = ny;
+    pool.grid[slot] = G;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Params p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ int s_warp[33];
+  __shared__ float s_red[32];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_misc[4];
+
+  const int scan = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int slot = p.slots[scan];
+  const int cap = p.cap_pts;
+
+  float4* bufA; float4* bufB; int* s_hist;
+  if (p.pts_in_smem) {
+    bufA = reinterpret_cast<float4*>(dyn_smem);
+    bufB = bufA + cap;
+    s_hist = reinterpret_cast<int*>(bufB + cap);
+  } else {
+    bufA = p.g_bufA + (size_t)scan * cap;
+    bufB = p.g_bufB + (size_t)scan * cap;
+    s_hist = reinterpret_cast<int*>(dyn_smem);
+  }
+
+  // ---- stage the input into bufA ------------------------------------------------------------------
+  int n = 0;
+  if (p.mode == 0) {
+    const int nslots = p.A * p.k;
+    const float4* src = p.rowcloud + (size_t)scan * nslots;
+    if (p.pts_in_smem) {
+      if (tid == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)nslots * 16u;
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(bufA, src, bytes, &s_bar);
+      }
+    }
+    // row offsets while the copy is in flight: s_hist[a] = exclusive prefix of rowcnt
+    const int32_t* rc = p.rowcnt + (size_t)scan * p.A;
+    for (int a = tid; a < p.A; a += T) s_hist[a] = rc[a];
+    __syncthreads();
+    n = block_array_excl_scan(s_hist, p.A, s_warp);
+    if (p.pts_in_smem) mbar_wait(&s_bar, 0);
+    // in-place left compaction, chunk by chunk (dest index <= source index), + Compensate
+    const double* mot = p.mot ? p.mot + 3 * (size_t)scan : nullptr;
+    const double m0 = mot ? mot[0] : 0.0, m1 = mot ? mot[1] : 0.0, m2 = mot ? mot[2] : 0.0;
+    float4* outc = p.cloud ? p.cloud + (size_t)scan * cap : nullptr;
+    for (int s0 = 0; s0 < nslots; s0 += T) {
+      const int s = s0 + tid;
+      bool have = false; float4 pt = make_float4(0, 0, 0, 0); int dst = 0;
+      if (s < nslots) {
+        const int a = s / p.k, j = s - a * p.k;
+        const int start = s_hist[a];
+        const int cnt = ((a + 1 < p.A) ? s_hist[a + 1] : n) - start;
+        if (j < cnt) {
+          have = true; dst = start + j;
+          pt = p.pts_in_smem ? bufA[s] : src[s];
+          if (mot) {                                       // utils.cpp:96-113
+            const double x = (double)pt.x, y = (double)pt.y;
+            const double d = rel_time_stamp(x, y, p.ccw != 0);
+            double s1, c1; sincos(d * m2, &s1, &c1);
+            const double tx = c1 * x + (-s1) * y + d * m0;
+            const double ty = s1 * x + c1 * y + d * m1;
+            pt.x = (float)tx; pt.y = (float)ty;
+          }
+        }
+      }
+      __syncthreads();
+      if (have) { bufA[dst] = pt; if (outc) outc[dst] = pt; }
+    }
+    __syncthreads();
+    if (tid == 0 && p.npts) p.npts[scan] = n;
+  } else {
+    n = p.npts[scan];
+    const float4* src = p.cloud + (size_t)scan * cap;
+    if (p.pts_in_smem) {
+      if (tid == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      if (n > 0) {
+        if (tid == 0) {
+          const uint32_t bytes = (uint32_t)n * 16u;
+          mbar_expect_tx(&s_bar, bytes);
+          tma_bulk_g2s(bufA, src, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+      }
+    } else {
+      for (int i = tid; i < n; i += T) bufA[i] = src[i];
+    }
+    __syncthreads();
+  }
+
+  if (tid == 0) p.status[scan] = 0;
+  if (n == 0) {                                            // reference exits on an empty cloud (pointnormal.cpp:72-75)
+    if (tid == 0) {
+      p.pool.ncells[slot] = 0;
+      NNGrid G; G.ox = G.oy = 0.f; G.g = p.nn_cell; G.inv_g = 1.f / p.nn_cell; G.nx = G.ny = 1;
+      p.pool.grid[slot] = G;
+      p.pool.gstart[(size_t)slot * (p.pool.grid_cap + 1)] = 0;
+      p.pool.gstart[(size_t)slot * (p.pool.grid_cap + 1) + 1] = 0;
+    }
+    return;
+  }
+
+  // ---- VoxelGrid: bounds, voxel ids (fp32, restating pcl voxel_grid.hpp applyFilter) ---------------
+  float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+  for (int i = tid; i < n; i += T) {
+    const float4 q = bufA[i];
+    mnx = fminf(mnx, q.x); mxx = fmaxf(mxx, q.x); mny = fminf(mny, q.y); mxy = fmaxf(mxy, q.y);
+  }
+  mnx = block_min_f(mnx, s_red); mny = block_min_f(mny, s_red);
+  mxx = block_max_f(mxx, s_red); mxy = block_max_f(mxy, s_red);
+  const float inv = 1.0f / p.leaf;
+  const int minbx = (int)floorf(mnx * inv), maxbx = (int)floorf(mxx * inv);
+  const int minby = (int)floorf(mny * inv), maxby = (int)floorf(mxy * inv);
+  const int divx = maxbx - minbx + 1, divy = maxby - minby + 1;
+  const long long nbins_ll = (long long)divx * divy;
+  int* hist = s_hist;
+  if (nbins_ll + 1 > K3_HIST_CAP) {
+    if (nbins_ll + 1 > p.g_hist_cap) {
+      if (tid == 0) { p.status[scan] = 1; p.pool.ncells[slot] = 0; }
+      return;
+    }
+    hist = p.g_hist + (size_t)scan * (p.g_hist_cap + 1);
+  }
+  const int nbins = (int)nbins_ll;
+  for (int b = tid; b <= nbins; b += T) hist[b] = 0;
+  __syncthreads();
+  const float fminbx = (float)minbx, fminby = (float)minby;
+  for (int i = tid; i < n; i += T) {
+    const float4 q = bufA[i];
+    const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
+    atomicAdd(&hist[i0 + i1 * divx], 1);
+  }
+  __syncthreads();
+  block_array_excl_scan(hist, nbins + 1, s_warp);          // hist[v] = start of voxel v
+  for (int i = tid; i < n; i += T) {
+    float4 q = bufA[i];
+    const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
+    const int pos = atomicAdd(&hist[i0 + i1 * divx], 1);   // afterwards hist[v] = end of voxel v
+    q.z = __int_as_float(i);                               // z is identically 0 on this path: carry the input index
+    bufB[pos] = q;
+  }
+  __syncthreads();
+
+  // ---- per voxel: restore input order, sequential fp32 centroid; ordered list of non-empty voxels ---
+  float2* cxy = reinterpret_cast<float2*>(bufA);           // bufA is free now: centroid list, later fp32 cell means
+  {
+    const int chunk = (nbins + T - 1) / T;
+    const int lo = min(tid * chunk, nbins), hi = min(lo + chunk, nbins);
+    int nonempty = 0;
+    for (int v = lo; v < hi; ++v) {
+      const int s = v ? hist[v - 1] : 0, e = hist[v];
+      if (e > s) {
+        ++nonempty;
+        for (int a = s + 1; a < e; ++a) {                   // insertion sort by input index
+          const float4 key = bufB[a];
+          const int ki = __float_as_int(key.z);
+          int b = a - 1;
+          while (b >= s && __float_as_int(bufB[b].z) > ki) { bufB[b + 1] = bufB[b]; --b; }
+          bufB[b + 1] = key;
+        }
+      }
+    }
+    int total;
+    int base = block_excl_scan(nonempty, s_warp, &total);
+    for (int v = lo; v < hi; ++v) {
+      const int s = v ? hist[v - 1] : 0, e = hist[v];
+      if (e > s) {
+        float sx = 0.f, sy = 0.f;
+        for (int a = s; a < e; ++a) { sx += bufB[a].x; sy += bufB[a].y; }
+        const float cnt = (float)(e - s);
+        cxy[base++] = make_float2(sx / cnt, sy / cnt);
+      }
+    }
+    if (tid == 0) s_misc[0] = total;
+    __syncthreads();
+  }
+  const int nvox = s_misc[0];
+
+  // ---- per centroid: radius neighbourhood -> cell ---------------------------------------------------
+  const float r = p.radius;
+  const float r2 = (float)((double)r * (double)r);
+  const float rq = r * 1.0001f + 1e-4f;                    // bin-range margin (the d2 test itself is exact)
+  const size_t cbase = (size_t)slot * p.pool.max_cells;
+  int ncells = 0;                                          // block-uniform running count
+  for (int c0 = 0; c0 < nvox; c0 += T) {
+    const int c = c0 + tid;
+    bool valid = false;
+    double ux = 0, uy = 0, cxx = 0, cxy_ = 0, cyx = 0, cyy = 0, scale = 0, nx_ = 0, ny_ = 0, avgI = 0;
+    int N = 0;
+    if (c < nvox) {
+      const float2 q = cxy[c];
+      int bx0 = (int)(floorf((q.x - rq) * inv) - fminbx), bx1 = (int)(floorf((q.x + rq) * inv) - fminbx);
+      int by0 = (int)(floorf((q.y - rq) * inv) - fminby), by1 = (int)(floorf((q.y + rq) * inv) - fminby);
+      bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, divx - 1); by1 = min(by1, divy - 1);
+      double wsum = 0.0;
+      for (int by = by0; by <= by1; ++by) {                 // pass 1: N, sum of weights
+        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+        for (int a = s; a < e; ++a) {
+          const float4 pt = bufB[a];
+          const float dx = q.x - pt.x, dy = q.y - pt.y;
+          float d2 = dx * dx; d2 += dy * dy;
+          if (d2 < r2) {
+            ++N;
+            wsum += p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0;    // pointnormal.cpp:15
+          }
+        }
+      }
+      if (N >= 6) {                                         // pointnormal.cpp:291
+        for (int by = by0; by <= by1; ++by) {               // pass 2: weighted mean (:21-24)
+          const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+          const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+          for (int a = s; a < e; ++a) {
+            const float4 pt = bufB[a];
+            const float dx = q.x - pt.x, dy = q.y - pt.y;
+            float d2 = dx * dx; d2 += dy * dy;
+            if (d2 < r2) {
+              const double w = (p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
+              ux += w * (double)pt.x; uy += w * (double)pt.y;
+            }
+          }
+        }
+        for (int by = by0; by <= by1; ++by) {               // pass 3: weighted scatter (:26-33)
+          const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+          const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+          for (int a = s; a < e; ++a) {
+            const float4 pt = bufB[a];
+            const float dx = q.x - pt.x, dy = q.y - pt.y;
+            float d2 = dx * dx; d2 += dy * dy;
+            if (d2 < r2) {
+              const double w = (p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
+              const double ex = (double)pt.x - ux, ey = (double)pt.y - uy;
+              const double wx = w * ex, wy = w * ey;
+              cxx += ex * wx; cxy_ += ex * wy; cyx += ey * wx; cyy += ey * wy;
+            }
+          }
+        }
+        const Eig2 eg = eig2_sym(cxx, cyx, cyy);            // ComputeNormal (:37-63)
+        const double cond = fabs(eg.lmax / eg.lmin);
+        const double det = eg.lmax * eg.lmin;
+        valid = (cond <= 10000) && (det > 0.00001) && eg.lmin > 0 && eg.lmax > 0;
+        scale = log(1.0 + cond / 2);
+        nx_ = eg.nx; ny_ = eg.ny;
+        if (nx_ * (p.origin_x - ux) + ny_ * (p.origin_y - uy) < 0) { nx_ = -nx_; ny_ = -ny_; }
+        avgI = wsum / (double)N;
+      }
+    }
+    int total;
+    const int pos = ncells + block_excl_scan(valid ? 1 : 0, s_warp, &total);
+    if (valid && pos < p.pool.max_cells) {
+      p.pool.mean[cbase + pos] = make_double2(ux, uy);
+      p.pool.normal[cbase + pos] = make_double2(nx_, ny_);
+      p.pool.cov[cbase + pos] = make_double4(cxx, cxy_, cyx, cyy);
+      p.pool.planarity[cbase + pos] = scale;
+      p.pool.avg_intensity[cbase + pos] = avgI;
+      p.pool.nsamples[cbase + pos] = N;
+      cxy[pos] = make_float2((float)ux, (float)uy);        // pointnormal.cpp:153-157 (pos <= c: safe in place)
+    }
+    ncells += total;
+    __syncthreads();
+  }
+  ncells = min(ncells, p.pool.max_cells);
+  if (tid == 0) p.pool.ncells[slot] = ncells;
+  __syncthreads();
+
+  // ---- NN index over the fp32 means --------------------------------------------------------------
+  build_nn_grid(p.pool, slot, cxy, ncells, p.nn_cell, s_hist, min(K3_HIST_CAP, p.pool.grid_cap) - 1, s_warp, s_red);
+}
+
+// NN index for an uploaded cell set (cfear_cells_upload): one CTA per slot.
+struct K4Params { CellPool pool; const int32_t* slots; float nn_cell; };
+
+__global__ void __launch_bounds__(K3_THREADS, 1) k4_build_index(const K4Params p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ int s_warp[33];
+  __shared__ float s_red[32];
+  const int slot = p.slots[blockIdx.x];
+  const int n = p.pool.ncells[slot];
+  int* s_hist = reinterpret_cast<int*>(dyn_smem);
+  float2* fm = p.pool.fm_scratch + (size_t)slot * p.pool.max_cells;
+  const double2* mean = p.pool.mean + (size_t)slot * p.pool.max_cells;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) fm[i] = make_float2((float)mean[i].x, (float)mean[i].y);
+  __syncthreads();
+  build_nn_grid(p.pool, slot, fm, n, p.nn_cell, s_hist, min(K3_HIST_CAP, p.pool.grid_cap) - 1, s_warp, s_red);
+}
+
+}  // namespace cfear

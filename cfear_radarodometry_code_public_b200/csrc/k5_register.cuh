@@ -1,0 +1,482 @@
+// K5/K6: scan-to-keyframes registration, one CTA per independent problem, no host round trips.
+//
+// Replaces n_scan_normal_reg::Register (n_scan_normal.cpp:82-187) with everything below it:
+//   BuildOptimizationProblem / AddScanPairCost       n_scan_normal.cpp:344-391, 215-326
+//     MapPointNormal::GetClosestIdx                  pointnormal.cpp:238-254  (exact fp32 1-NN, d2 < r*r)
+//     Weights::GetWeight                             registration.cpp:67-76
+//   cost functors P2L / P2D / P2P (autodiff == the analytic Jacobians used here)  n_scan_normal.h:180-255, 330-361
+//   Registration::GetLoss + ScaledLoss               registration.cpp:78-97, n_scan_normal.cpp:277
+//   SolveOptimizationProblem -> ceres::Solve         n_scan_normal.cpp:443-452 (trust-region LM, Ceres defaults)
+//   GetCovariance                                    n_scan_normal.cpp:392-433
+//
+// Per outer iteration the block (1) associates every (keyframe, source cell) pair through the keyframe's
+// bucket grid and compacts the accepted pairs, in (keyframe, cell) order, into a residual list, then
+// (2) runs the LM loop: every evaluation is a block-wide pass over the list with the 6 J^T J + 3 J^T r
+// + cost sums reduced by warp shuffles and a fixed-order cross-warp sum (bit-reproducible), while the
+// scalar trust-region logic is executed redundantly by every thread on identical inputs.
+#pragma once
+#include "common.cuh"
+
+namespace cfear {
+
+constexpr int K5_THREADS = 512;
+constexpr int K5_WARPS = K5_THREADS / 32;
+constexpr int K5_MAXSCANS = 65;     // K+1 <= 65
+
+struct RegParams {
+  CellPool pool;
+  int nprob, nscans;             // nscans = K+1 cell sets per problem, last = current scan
+  const int32_t* slots;          // [nprob][nscans]
+  double* poses;                 // [nprob][nscans][3] in/out
+  double* cov36;                 // [nprob][36]
+  void* stats;                   // [nprob] cfear_reg_stats
+  int32_t* assoc;                // [nprob][nscans-1][max_cells] or null
+  double4* res;                  // [nprob][res_cap][4]  residual scratch (64 B each)
+  int res_cap;
+  int cost, loss, weight_opt, solver_mode;
+  int max_outer, min_outer, max_inner, gn_iters;
+  double loss_limit, cov_scale, regularization, radius;
+};
+
+struct RegStatsDev {             // == cfear_reg_stats
+  int32_t success, outer_iterations, inner_iterations, num_residuals, num_blocks, usable;
+  double final_cost, score;
+};
+
+struct Resid { double px, py, qx, qy, a, b, c, w; };
+
+// ceres/loss_function.cc
+__device__ __forceinline__ void loss_eval(int loss, double a, double s, double rho[3]) {
+  switch (loss) {
+    case 1: {
+      const double b = a * a;
+      if (s > b) { const double r = sqrt(s); rho[0] = 2.0 * a * r - b; rho[1] = fmax(2.2250738585072014e-308, a / r); rho[2] = -rho[1] / (2.0 * s); }
+      else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+      return; }
+    case 2: {
+      const double b = a * a, c = 1.0 / b;
+      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = b * log(sum); rho[1] = fmax(2.2250738585072014e-308, inv); rho[2] = -c * (inv * inv);
+      return; }
+    case 3: {
+      const double b = a * a, c = 1.0 / b;
+      const double sum = 1.0 + s * c, tmp = sqrt(sum);
+      rho[0] = 2.0 * b * (tmp - 1.0); rho[1] = fmax(2.2250738585072014e-308, 1.0 / tmp); rho[2] = -(c * rho[1]) / (2.0 * sum);
+      return; }
+    case 4: {   // ComposedLoss(Huber(1), Cauchy(1))  registration.cpp:88-92
+      double g[3], f[3];
+      loss_eval(2, 1.0, s, g); loss_eval(1, 1.0, g[0], f);
+      rho[0] = f[0]; rho[1] = f[1] * g[1]; rho[2] = f[2] * g[1] * g[1] + f[1] * g[2];
+      return; }
+    case 5: {
+      const double a2 = a * a;
+      if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho[0] = a2 / 3.0 * (1.0 - v2 * v); rho[1] = v2; rho[2] = -2.0 / a2 * v; }
+      else { rho[0] = a2 / 3.0; rho[1] = 0.0; rho[2] = 0.0; }
+      return; }
+    default: rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return;
+  }
+}
+
+struct EvalOut { double cost, H[6], g[3]; };
+
+// Block-wide evaluation of cost (and normal equations) over the residual list at x.
+// s_part: [2][K5_WARPS][10] doubles; *parity toggles per call (one __syncthreads per evaluation).
+__device__ inline void block_evaluate(int cost_kind, int loss, double loss_limit, const double4* __restrict__ res,
+                                      int nres, const double x[3], bool with_jac, EvalOut& ev,
+                                      double* s_part, int& parity) {
+  double cs, sn; sincos(x[2], &sn, &cs);
+  double acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+  for (int r = threadIdx.x; r < nres; r += blockDim.x) {
+    const double4 v0 = res[4 * (size_t)r + 0], v1 = res[4 * (size_t)r + 1];   // px py qx qy | a b c w
+    const double2 pq = make_double2(v0.x, v0.y);
+    const double rx = cs * pq.x - sn * pq.y, ry = sn * pq.x + cs * pq.y;
+    const double ex = rx + x[0] - v0.z, ey = ry + x[1] - v0.w;
+    const double dpx = -ry, dpy = rx;
+    const double a = v1.x, b = v1.y, c = v1.z, w = v1.w;
+    double r0, r1 = 0.0, J0[3], J1[3] = {0, 0, 0};
+    bool two;
+    if (cost_kind == 1) {
+      r0 = ex * a + ey * b; two = false;
+      J0[0] = a; J0[1] = b; J0[2] = dpx * a + dpy * b;
+    } else if (cost_kind == 2) {
+      r0 = a * ex; r1 = b * ex + c * ey; two = true;
+      J0[0] = a; J0[1] = 0.0; J0[2] = a * dpx;
+      J1[0] = b; J1[1] = c; J1[2] = b * dpx + c * dpy;
+    } else {
+      r0 = -ex; r1 = -ey; two = true;
+      J0[0] = -1.0; J0[1] = 0.0; J0[2] = -dpx;
+      J1[0] = 0.0; J1[1] = -1.0; J1[2] = -dpy;
+    }
+    const double s = r0 * r0 + r1 * r1;
+    double rho[3];
+    loss_eval(loss, loss_limit, s, rho);
+    acc[0] += 0.5 * w * rho[0];
+    if (with_jac) {
+      const double wr = w * rho[1];
+      acc[1] += wr * J0[0] * J0[0]; acc[2] += wr * J0[0] * J0[1]; acc[3] += wr * J0[0] * J0[2];
+      acc[4] += wr * J0[1] * J0[1]; acc[5] += wr * J0[1] * J0[2]; acc[6] += wr * J0[2] * J0[2];
+      acc[7] += wr * J0[0] * r0; acc[8] += wr * J0[1] * r0; acc[9] += wr * J0[2] * r0;
+      if (two) {
+        acc[1] += wr * J1[0] * J1[0]; acc[2] += wr * J1[0] * J1[1]; acc[3] += wr * J1[0] * J1[2];
+        acc[4] += wr * J1[1] * J1[1]; acc[5] += wr * J1[1] * J1[2]; acc[6] += wr * J1[2] * J1[2];
+        acc[7] += wr * J1[0] * r1; acc[8] += wr * J1[1] * r1; acc[9] += wr * J1[2] * r1;
+      }
+    }
+  }
+  const int nv = with_jac ? 10 : 1;
+  double* part = s_part + parity * (K5_WARPS * 10);
+  parity ^= 1;
+  for (int i = 0; i < nv; ++i) {
+    const double v = warp_sum(acc[i]);
+    if (lane_id() == 0) part[warp_id() * 10 + i] = v;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  double tot[10];
+  for (int i = 0; i < nv; ++i) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += part[w * 10 + i];
+    tot[i] = t;
+  }
+  ev.cost = tot[0];
+  if (with_jac) {
+    for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
+    for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
+  }
+}
+
+__device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3], double y[3]) {
+  const double l00 = sqrt(A[0]);
+  if (!(l00 > 0.0) || !isfinite(l00)) return false;
+  const double l10 = A[1] / l00, l20 = A[2] / l00;
+  const double d1 = A[3] - l10 * l10;
+  if (!(d1 > 0.0)) return false;
+  const double l11 = sqrt(d1);
+  const double l21 = (A[4] - l20 * l10) / l11;
+  const double d2 = A[5] - l20 * l20 - l21 * l21;
+  if (!(d2 > 0.0)) return false;
+  const double l22 = sqrt(d2);
+  const double z0 = b[0] / l00;
+  const double z1 = (b[1] - l10 * z0) / l11;
+  const double z2 = (b[2] - l20 * z0 - l21 * z1) / l22;
+  y[2] = z2 / l22;
+  y[1] = (z1 - l21 * y[2]) / l11;
+  y[0] = (z0 - l10 * y[1] - l20 * y[2]) / l00;
+  return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
+}
+
+struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usable; };
+
+// Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc),
+// block-uniform control flow.
+__device__ inline void lm_solve(const RegParams& P, const double4* res, int nres, double x[3], SolveSum& sum,
+                                double* s_part, int& parity) {
+  const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
+  const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
+  const double kMaxRadius = 1e16, kMinRadius = 1e-32;
+  double radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int invalid_in_a_row = 0;
+  sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
+
+  EvalOut ev;
+  block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+  double x_cost = ev.cost;
+  double scale[3];
+  scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
+  scale[1] = 1.0 / (1.0 + sqrt(ev.H[3]));
+  scale[2] = 1.0 / (1.0 + sqrt(ev.H[5]));
+  double x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  double min_cost = x_cost;
+  double gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
+  sum.final_cost = min_cost;
+  if (gmax <= kGradientTol) return;
+  double diag[3] = {0, 0, 0};
+  for (int it = 1;; ++it) {
+    const double Hs[6] = {ev.H[0] * scale[0] * scale[0], ev.H[1] * scale[0] * scale[1], ev.H[2] * scale[0] * scale[2],
+                          ev.H[3] * scale[1] * scale[1], ev.H[4] * scale[1] * scale[2], ev.H[5] * scale[2] * scale[2]};
+    const double gs[3] = {ev.g[0] * scale[0], ev.g[1] * scale[1], ev.g[2] * scale[2]};
+    if (!reuse_diagonal) {
+      diag[0] = fmin(fmax(Hs[0], kMinDiag), kMaxDiag);
+      diag[1] = fmin(fmax(Hs[3], kMinDiag), kMaxDiag);
+      diag[2] = fmin(fmax(Hs[5], kMinDiag), kMaxDiag);
+    }
+    const double A[6] = {Hs[0] + diag[0] / radius, Hs[1], Hs[2], Hs[3] + diag[1] / radius, Hs[4], Hs[5] + diag[2] / radius};
+    double y[3];
+    const double nb[3] = {-gs[0], -gs[1], -gs[2]};
+    const bool ok = chol3_solve(A, nb, y);
+    reuse_diagonal = true;
+    double model_change = 0.0;
+    if (ok) {
+      const double Hy0 = Hs[0] * y[0] + Hs[1] * y[1] + Hs[2] * y[2];
+      const double Hy1 = Hs[1] * y[0] + Hs[3] * y[1] + Hs[4] * y[2];
+      const double Hy2 = Hs[2] * y[0] + Hs[4] * y[1] + Hs[5] * y[2];
+      model_change = -(y[0] * gs[0] + y[1] * gs[1] + y[2] * gs[2]) - 0.5 * (y[0] * Hy0 + y[1] * Hy1 + y[2] * Hy2);
+    }
+    if (!ok || !(model_change > 0.0)) {
+      if (++invalid_in_a_row >= 5) { sum.usable = false; return; }
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      sum.n_iterations++; sum.last_rel = 0.0;
+      min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
+      if (it >= P.max_inner) return;
+      if (radius <= kMinRadius) return;
+      continue;
+    }
+    invalid_in_a_row = 0;
+    const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
+    const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
+    EvalOut evc;
+    block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, xc, false, evc, s_part, parity);
+    const double cand_cost = evc.cost;
+    const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+    if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
+    const double cost_change = x_cost - cand_cost;
+    if (fabs(cost_change) <= kFunctionTol * x_cost) return;
+    const double rel = cost_change / model_change;
+    sum.n_iterations++; sum.last_rel = rel;
+    if (rel > kMinRelDecrease) {
+      x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
+      x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      x_cost = ev.cost;
+      gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
+      const double t = 2.0 * rel - 1.0;
+      radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+      radius = fmin(kMaxRadius, radius);
+      decrease_factor = 2.0; reuse_diagonal = false;
+      min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
+      if (it >= P.max_inner) return;
+      if (gmax <= kGradientTol) return;
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      min_cost = fmin(min_cost, cand_cost); sum.final_cost = min_cost;
+      if (it >= P.max_inner) return;
+      if (radius <= kMinRadius) return;
+    }
+  }
+}
+
+// GetClosestIdx: exact fp32 nearest neighbour through the slot's bucket grid; ties -> smallest cell index.
+__device__ __forceinline__ int nn_query(const CellPool& pool, int slot, const NNGrid& G, double pxd, double pyd,
+                                        double radius) {
+  const float qx = (float)pxd, qy = (float)pyd;             // pointnormal.cpp:241-242
+  const float rq = (float)radius * 1.0001f + 1e-3f;         // bucket-range margin only
+  int bx0 = (int)floorf((qx - rq - G.ox) * G.inv_g), bx1 = (int)floorf((qx + rq - G.ox) * G.inv_g);
+  int by0 = (int)floorf((qy - rq - G.oy) * G.inv_g), by1 = (int)floorf((qy + rq - G.oy) * G.inv_g);
+  bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, G.nx - 1); by1 = min(by1, G.ny - 1);
+  const int* gstart = pool.gstart + (size_t)slot * (pool.grid_cap + 1);
+  const float2* gxy = pool.gxy + (size_t)slot * pool.max_cells;
+  const int* gidx = pool.gidx + (size_t)slot * pool.max_cells;
+  float best = 3.4028234e38f; int besti = -1;
+  for (int by = by0; by <= by1; ++by) {
+    const int s = gstart[bx0 + by * G.nx], e = gstart[bx1 + by * G.nx + 1];
+    for (int a = s; a < e; ++a) {
+      const float2 m = gxy[a];
+      const float dx = qx - m.x, dy = qy - m.y;
+      float d2 = dx * dx; d2 += dy * dy;
+      if (d2 <= best) {
+        const int i = gidx[a];
+        if (d2 < best || i < besti) { best = d2; besti = i; }
+      }
+    }
+  }
+  if (besti >= 0 && (double)best < radius * radius) return besti;   // pointnormal.cpp:250
+  return -1;
+}
+
+__device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) / (x + y); }
+
+// One outer iteration's association pass.  Returns the number of residual blocks (block-uniform).
+__device__ inline int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
+                                    const NNGrid* s_grid, const double x[3], int itr, double4* res, int32_t* assoc,
+                                    int* s_warp) {
+  const int ns = P.nscans, K = ns - 1;
+  const int src_slot = slots[K];
+  const int n_src = P.pool.ncells[src_slot];
+  const size_t sbase = (size_t)src_slot * P.pool.max_cells;
+  double cs_s, sn_s; sincos(x[2], &sn_s, &cs_s);
+  const double angle_outlier = cos(M_PI / 6.0);
+  const double curr_radius = (itr == 1) ? 2 * P.radius : P.radius;       // n_scan_normal.cpp:222
+  const int npairs = K * n_src;
+  int nres = 0;
+  for (int t0 = 0; t0 < npairs; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    bool valid = false;
+    Resid R; int i = 0, j = 0, m = -1;
+    if (t < npairs) {
+      i = t / n_src; j = t - i * n_src;
+      const double* pt = s_pose + 5 * i;
+      const double ct = pt[3], st = pt[4];
+      const double rc = ct * cs_s + st * sn_s, rs = ct * sn_s - st * cs_s;     // Ttar^-1 * Tsrc   :224
+      const double dx = x[0] - pt[0], dy = x[1] - pt[1];
+      const double tx = ct * dx + st * dy, ty = -st * dx + ct * dy;
+      const double2 mu = P.pool.mean[sbase + j];
+      const double qx = rc * mu.x - rs * mu.y + tx, qy = rs * mu.x + rc * mu.y + ty;   // :240
+      const int tslot = slots[i];
+      m = nn_query(P.pool, tslot, s_grid[i], qx, qy, curr_radius);                    // :241
+      if (m >= 0) {
+        const size_t tb = (size_t)tslot * P.pool.max_cells + m;
+        const double2 nsrc = P.pool.normal[sbase + j];
+        const double2 ntar = P.pool.normal[tb];
+        const double ntx = rc * nsrc.x - rs * nsrc.y, nty = rs * nsrc.x + rc * nsrc.y;  // :244
+        const double sim = fmax(ntx * ntar.x + nty * ntar.y, 0.0);                      // :246
+        if (sim > angle_outlier) {                                                      // :247
+          valid = true;
+          double w = 1.0;                                                              // registration.cpp:67-76
+          if (P.weight_opt != 0) {
+            const double n1 = (double)P.pool.nsamples[sbase + j], n2 = (double)P.pool.nsamples[tb];
+            const double p1 = P.pool.planarity[sbase + j], p2 = P.pool.planarity[tb];
+            if (P.weight_opt == 1) w = sim_ratio(n1, n2);
+            else if (P.weight_opt == 2) w = sim;
+            else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
+            else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
+          }
+          R.w = w; R.px = mu.x; R.py = mu.y;
+          const double2 tm = P.pool.mean[tb];
+          R.qx = ct * tm.x - st * tm.y + pt[0]; R.qy = st * tm.x + ct * tm.y + pt[1];
+          R.a = R.b = R.c = 0.0;
+          if (P.cost == 1) {                                                           // :279-289
+            R.a = ct * ntar.x - st * ntar.y; R.b = st * ntar.x + ct * ntar.y;
+          } else if (P.cost == 2) {                                                    // :290-300
+            const double4 C = P.pool.cov[tb];
+            const double a00 = ct * C.x - st * C.z, a01 = ct * C.y - st * C.w;
+            const double a10 = st * C.x + ct * C.z, a11 = st * C.y + ct * C.w;
+            double s00 = a00 * ct - a01 * st, s01 = a00 * st + a01 * ct;
+            double s10 = a10 * ct - a11 * st, s11 = a10 * st + a11 * ct;
+            s00 = (P.regularization + s00) * P.cov_scale; s11 = (P.regularization + s11) * P.cov_scale;
+            s01 = s01 * P.cov_scale; s10 = s10 * P.cov_scale;
+            const double det = s00 * s11 - s01 * s10;
+            const double i00 = s11 / det, i10 = -s10 / det, i11 = s00 / det;
+            const double l00 = sqrt(i00);
+            const double l10 = i10 / l00;
+            const double l11 = sqrt(i11 - l10 * l10);
+            R.a = l00; R.b = l10; R.c = l11;
+          }
+        }
+      }
+      if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
+    }
+    int total;
+    const int pos = nres + block_excl_scan(valid ? 1 : 0, s_warp, &total);
+    if (valid && pos < P.res_cap) {
+      res[4 * (size_t)pos + 0] = make_double4(R.px, R.py, R.qx, R.qy);
+      res[4 * (size_t)pos + 1] = make_double4(R.a, R.b, R.c, R.w);
+    }
+    nres += total;
+  }
+  __syncthreads();                 // residual list visible to the whole block
+  return min(nres, P.res_cap);
+}
+
+__global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) {
+  __shared__ int s_warp[33];
+  __shared__ double s_part[2 * K5_WARPS * 10];
+  __shared__ double s_pose[K5_MAXSCANS * 5];
+  __shared__ NNGrid s_grid[K5_MAXSCANS];
+  __shared__ int32_t s_slots[K5_MAXSCANS];
+
+  const int prob = blockIdx.x;
+  const int ns = P.nscans, K = ns - 1;
+  const int tid = threadIdx.x;
+  double* poses = P.poses + (size_t)prob * ns * 3;
+  if (tid < ns) {
+    const int sl = P.slots[(size_t)prob * ns + tid];
+    s_slots[tid] = sl;
+    s_grid[tid] = P.pool.grid[sl];
+    const double yaw = poses[3 * tid + 2];
+    double s, c; sincos(yaw, &s, &c);
+    s_pose[5 * tid + 0] = poses[3 * tid + 0]; s_pose[5 * tid + 1] = poses[3 * tid + 1];
+    s_pose[5 * tid + 2] = yaw; s_pose[5 * tid + 3] = c; s_pose[5 * tid + 4] = s;
+  }
+  __syncthreads();
+  double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
+  double4* res = P.res + (size_t)prob * P.res_cap * 4;
+  int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * K * P.pool.max_cells : nullptr;
+  const int per_block = (P.cost == 1) ? 1 : 2;
+  int parity = 0;
+
+  SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
+  bool success = true;
+  int inner_total = 0, nres = 0, outer = 0;
+  if (P.solver_mode == 1) {
+    // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
+    int it;
+    for (it = 1; it <= P.gn_iters; ++it) {
+      nres = build_problem(P, s_slots, s_pose, s_grid, x, it, res, assoc, s_warp);
+      if (nres * per_block <= 1) { success = false; break; }
+      EvalOut ev;
+      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
+      if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
+      x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
+      sum.final_cost = ev.cost;
+      inner_total++;
+    }
+    outer = it;
+    if (success) {
+      EvalOut ev;
+      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, false, ev, s_part, parity);
+      sum.final_cost = ev.cost;
+    }
+  } else {
+    double prev_par[3] = {x[0], x[1], x[2]};
+    double prev_score = 1.7976931348623157e308;
+    int itr;
+    for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
+      nres = build_problem(P, s_slots, s_pose, s_grid, x, itr, res, assoc, s_warp);
+      if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
+      lm_solve(P, res, nres, x, sum, s_part, parity);                           // :117
+      success = sum.usable;
+      inner_total += sum.n_iterations - 1;
+      const double current_score = sum.final_cost;
+      const double rel_improvement = (prev_score - current_score) / prev_score;
+      if (itr > P.min_outer) {                                                  // :134-149
+        if (prev_score < current_score) { x[0] = prev_par[0]; x[1] = prev_par[1]; x[2] = prev_par[2]; break; }
+        else if (rel_improvement < 0.00001) break;
+        else if (sum.last_rel < 0.00001 || sum.n_iterations == 1) break;
+      }
+      prev_score = current_score;
+      prev_par[0] = x[0]; prev_par[1] = x[1]; prev_par[2] = x[2];
+    }
+    outer = itr;
+  }
+
+  RegStatsDev st;
+  st.outer_iterations = outer; st.inner_iterations = inner_total;
+  st.num_blocks = nres; st.num_residuals = nres * per_block;
+  st.usable = sum.usable ? 1 : 0; st.final_cost = sum.final_cost; st.score = 0.0; st.success = 0;
+  double cov[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+  if (success) {
+    st.score = sum.final_cost / st.num_residuals;                               // :166
+    cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
+    EvalOut ev;                                                                 // GetCovariance :392-433
+    block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+    double inv[9]; bool ok = true;
+    for (int c = 0; c < 3 && ok; ++c) {
+      double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
+      ok = chol3_solve(ev.H, e, y);
+      inv[0 + c] = y[0]; inv[3 + c] = y[1]; inv[6 + c] = y[2];
+    }
+    if (ok && st.num_residuals - 3 != 0) {
+      const double f = 30 * (sum.final_cost / (st.num_residuals - 3));          // :418
+#pragma unroll
+      for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+      for (int i = 0; i < 6; ++i) cov[i * 6 + i] = 1.0;
+      cov[0] = f * inv[0]; cov[1] = f * inv[1]; cov[6] = f * inv[3]; cov[7] = f * inv[4];
+      cov[35] = f * inv[8]; cov[5] = f * inv[2]; cov[30] = f * inv[6];
+      st.success = 1;
+    }
+  }
+  if (tid == 0) {
+    poses[3 * K + 0] = x[0]; poses[3 * K + 1] = x[1]; poses[3 * K + 2] = x[2];
+    reinterpret_cast<RegStatsDev*>(P.stats)[prob] = st;
+    double* c36 = P.cov36 + (size_t)prob * 36;
+    for (int i = 0; i < 36; ++i) c36[i] = cov[i];
+  }
+}
+
+}  // namespace cfear

@@ -1,0 +1,184 @@
+"""ctypes binding of the CPU oracle (oracle/cfear_oracle.cc).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(cfear_radarodometry_code_public_b200) must never import this module.
+
+Parity unpinned: see the header of cfear_oracle.cc.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcfear_oracle.so")
+_lib = None
+
+COST = {"P2P": 0, "P2L": 1, "P2D": 2}
+LOSS = {"None": 0, "Huber": 1, "Cauchy": 2, "SoftLOne": 3, "Combined": 4, "Tukey": 5}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "cfear_oracle.cc")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libcfear_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_eval_cost.restype = C.c_double
+    return _lib
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RegStats(C.Structure):
+    _fields_ = [("success", C.c_int32), ("outer_iterations", C.c_int32), ("inner_iterations", C.c_int32),
+                ("num_residuals", C.c_int32), ("num_blocks", C.c_int32), ("usable", C.c_int32),
+                ("final_cost", C.c_double), ("score", C.c_double)]
+
+
+def kstrongest(img: np.ndarray, z_min: int, k: int):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    A, R = img.shape
+    idx = np.full((A, k), -1, np.int32)
+    cnt = np.zeros(A, np.int32)
+    rc = lib().orc_kstrongest(_p(img), A, R, int(z_min), int(k), _p(idx), _p(cnt))
+    assert rc == 0
+    return idx, cnt
+
+
+def peaks(img, idx, cnt):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    A, R = img.shape
+    k = idx.shape[1]
+    pidx = np.full((A, k), -1, np.int32)
+    pcnt = np.zeros(A, np.int32)
+    lib().orc_peaks(_p(img), A, R, k, _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(cnt)), _p(pidx), _p(pcnt))
+    return pidx, pcnt
+
+
+def cloud(img, idx, cnt, min_distance=2.5, range_res=0.0438):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    A, R = img.shape
+    k = idx.shape[1]
+    out = np.zeros((A * k, 4), np.float32)
+    n = lib().orc_cloud(_p(img), A, R, k, _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(cnt)),
+                        C.c_float(min_distance), C.c_float(range_res), _p(out))
+    return out[:n].copy()
+
+
+def compensate(xyzi, mot, ccw=False):
+    out = np.ascontiguousarray(xyzi, dtype=np.float32).copy()
+    m = np.ascontiguousarray(mot, dtype=np.float64)
+    lib().orc_compensate(_p(out), out.shape[0], _p(m), int(bool(ccw)))
+    return out
+
+
+def voxel_centroids(xyzi, radius, downsample_factor=1.0):
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+    n = xyzi.shape[0]
+    cx = np.zeros(n, np.float32); cy = np.zeros(n, np.float32); ci = np.zeros(n, np.float32)
+    vid = np.zeros(n, np.int32); dims = np.zeros(4, np.int32)
+    nv = lib().orc_voxel_centroids(_p(xyzi), n, C.c_float(radius), C.c_double(downsample_factor),
+                                   _p(cx), _p(cy), _p(ci), _p(vid), _p(dims))
+    return cx[:nv], cy[:nv], ci[:nv], vid[:nv], dims
+
+
+def surface_points(xyzi, radius, weight_intensity=True, downsample_factor=1.0, origin=(0.0, 0.0)):
+    """Returns dict of SoA arrays (mean[n,2], normal[n,2], cov[n,2,2], planarity, nsamples, avg_intensity, lambdas)."""
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+    n = xyzi.shape[0]
+    m = max(n, 1)
+    mean = np.zeros((m, 2)); normal = np.zeros((m, 2)); cov = np.zeros((m, 2, 2))
+    plan = np.zeros(m); ns = np.zeros(m, np.int32); avg = np.zeros(m); lam = np.zeros((m, 2))
+    nc = lib().orc_surface_points(_p(xyzi), n, C.c_float(radius), C.c_double(downsample_factor), int(bool(weight_intensity)),
+                                  C.c_double(origin[0]), C.c_double(origin[1]),
+                                  _p(mean), _p(normal), _p(cov), _p(plan), _p(ns), _p(avg), _p(lam))
+    return dict(mean=mean[:nc].copy(), normal=normal[:nc].copy(), cov=cov[:nc].copy(), planarity=plan[:nc].copy(),
+                nsamples=ns[:nc].copy(), avg_intensity=avg[:nc].copy(), lambdas=lam[:nc].copy())
+
+
+def nearest(means, queries, radius):
+    means = np.ascontiguousarray(means, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.float64)
+    out = np.zeros(queries.shape[0], np.int32)
+    lib().orc_nearest(_p(means), means.shape[0], _p(queries), queries.shape[0], C.c_double(radius), _p(out))
+    return out
+
+
+def reg_cfg(cost="P2L", loss="Huber", loss_limit=0.1, weight_opt=0, cov_scale=1.0, regularization=1.0,
+            radius=2.0, max_outer=8, min_outer=3, max_inner=20, solver_mode=0, gn_iters=10):
+    ci = np.array([COST[cost] if isinstance(cost, str) else cost, LOSS[loss] if isinstance(loss, str) else loss,
+                   weight_opt, max_outer, min_outer, max_inner, solver_mode, gn_iters], np.int32)
+    cd = np.array([loss_limit, cov_scale, regularization, radius], np.float64)
+    return ci, cd
+
+
+def concat_cellsets(sets):
+    offs = np.zeros(len(sets) + 1, np.int32)
+    for i, s in enumerate(sets):
+        offs[i + 1] = offs[i] + s["mean"].shape[0]
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(s[k]).reshape(s["mean"].shape[0], -1) for s in sets], 0), dtype=dt)
+    return (offs, cat("mean", np.float64), cat("normal", np.float64), cat("cov", np.float64),
+            cat("planarity", np.float64).ravel(), cat("nsamples", np.int32).ravel())
+
+
+def register(sets, poses, cfg, want_assoc=False):
+    """sets: list of K+1 cell dicts (last = current scan); poses: (K+1,3) (x,y,yaw), last = guess.
+    Returns (success, poses_out, cov6x6, RegStats, assoc or None)."""
+    ci, cd = cfg
+    offs, mean, normal, cov, plan, ns = concat_cellsets(sets)
+    p = np.ascontiguousarray(poses, dtype=np.float64).copy()
+    cov36 = np.zeros(36)
+    st = RegStats()
+    n_src = sets[-1]["mean"].shape[0]
+    assoc = np.full((len(sets) - 1, n_src), -1, np.int32) if want_assoc else None
+    ok = lib().orc_register(_p(ci), _p(cd), len(sets), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
+                            _p(p), _p(cov36), C.byref(st), _p(assoc))
+    return bool(ok), p, cov36.reshape(6, 6), st, assoc
+
+
+def eval_cost(cfg, res8, x):
+    ci, cd = cfg
+    res8 = np.ascontiguousarray(res8, dtype=np.float64)
+    H = np.zeros(6); g = np.zeros(3)
+    c = lib().orc_eval_cost(_p(ci), _p(cd), res8.shape[0], _p(res8), _p(np.ascontiguousarray(x, dtype=np.float64)), _p(H), _p(g))
+    return c, H, g
+
+
+def pipeline_batch(polar, mot, kf_sets, kf_ids, poses, cfg, *, k=12, z_min=60, min_distance=2.5, range_res=0.0438,
+                   radius=3.5, weight_intensity=True, compensate=True, ccw=False, nthreads=1):
+    """Whole per-scan path for nprob independent scans.  polar (nprob,A,R) u8; kf_sets: list of cell dicts;
+    kf_ids (nprob,K) into kf_sets; poses (nprob,K+1,3)."""
+    polar = np.ascontiguousarray(polar, dtype=np.uint8)
+    nprob, A, R = polar.shape
+    kf_ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+    K = kf_ids.shape[1]
+    ci, cd = cfg
+    pipe_i = np.array([A, R, k, int(z_min), int(weight_intensity), int(compensate), int(ccw), K], np.int32)
+    pipe_f = np.array([min_distance, range_res, radius], np.float32)
+    offs, mean, normal, cov, plan, ns = concat_cellsets(kf_sets)
+    p = np.ascontiguousarray(poses, dtype=np.float64).copy()
+    cov36 = np.zeros((nprob, 36))
+    stats = (RegStats * nprob)()
+    ncells = np.zeros(nprob, np.int32); npts = np.zeros(nprob, np.int32)
+    stage_ms = np.zeros(3)
+    m = np.ascontiguousarray(mot, dtype=np.float64)
+    lib().orc_pipeline_batch(int(nthreads), nprob, _p(pipe_i), _p(pipe_f), _p(ci), _p(cd), _p(polar), _p(m),
+                             _p(kf_ids), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
+                             _p(p), _p(cov36), C.byref(stats), _p(ncells), _p(npts), _p(stage_ms))
+    return dict(poses=p, cov=cov36.reshape(nprob, 6, 6), stats=list(stats), ncells=ncells, npts=npts, stage_ms=stage_ms)

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path (through the C ABI, libcfear_b200.so) against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): k-strongest index sets bit-exact; clouds bit-exact (fp32, table-driven cos/sin from host libm);
+surface-point neighbour sets / counts exact, statistics to 1e-9 (fp64 summation order differs);
+poses within 1e-4 m / 1e-5 rad of the oracle after the same iteration counts.
+"""
+import numpy as np
+import pytest
+
+from cfear_radarodometry_code_public_b200 import capi
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, ROT_TOL = 1e-4, 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(max_batch=8, max_cellsets=16, max_keyframes=4)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def imgs():
+    return helpers.scan_images(3)
+
+
+def test_kstrongest_bit_exact_synthetic(ctx, orc, imgs):
+    im, _ = imgs
+    idx, cnt = ctx.kstrongest(im)
+    for i in range(im.shape[0]):
+        oi, oc = orc.kstrongest(im[i], 60, 12)
+        assert np.array_equal(cnt[i], oc)
+        assert np.array_equal(idx[i], oi)
+
+
+def test_kstrongest_bit_exact_adversarial(ctx, orc):
+    im = helpers.adversarial_image(1)
+    idx, cnt = ctx.kstrongest(im[None])
+    oi, oc = orc.kstrongest(im, 60, 12)
+    assert np.array_equal(cnt[0], oc)
+    assert np.array_equal(idx[0], oi)
+
+
+@pytest.mark.parametrize("k,zmin", [(1, 60), (5, 0), (40, 60), (64, 200), (12, 255), (12, 128)])
+def test_kstrongest_k_and_zmin_sweep(orc, k, zmin):
+    c = capi.Context(max_batch=2, k_strongest=k, z_min=float(zmin), max_cellsets=2)
+    im = np.stack([helpers.adversarial_image(2), helpers.scan_images(5, 0)[0][0]])
+    idx, cnt = c.kstrongest(im)
+    for i in range(2):
+        oi, oc = orc.kstrongest(im[i], zmin, k)
+        assert np.array_equal(cnt[i], oc)
+        assert np.array_equal(idx[i], oi)
+    c.close()
+
+
+def test_kstrongest_odd_row_length(orc):
+    # R not a multiple of 16: rows are not 16-byte aligned
+    A, R = 37, 1001
+    rng = np.random.Generator(np.random.PCG64(4))
+    im = rng.integers(0, 256, (3, A, R), dtype=np.uint8)
+    im[0] = (im[0] // 4)
+    c = capi.Context(max_batch=3, azimuths=A, range_bins=R, max_cellsets=2)
+    idx, cnt = c.kstrongest(im)
+    for i in range(3):
+        oi, oc = orc.kstrongest(im[i], 60, 12)
+        assert np.array_equal(cnt[i], oc) and np.array_equal(idx[i], oi)
+    c.close()
+
+
+def test_cloud_and_peaks_bit_exact(ctx, orc, imgs):
+    im, _ = imgs
+    both = np.stack([im[0], helpers.adversarial_image(1)])
+    out = ctx.filter(both, peaks=True)
+    for i in range(2):
+        oi, oc = orc.kstrongest(both[i], 60, 12)
+        ocl = orc.cloud(both[i], oi, oc)
+        assert out["npts"][i] == ocl.shape[0]
+        assert np.array_equal(out["clouds"][i].view(np.uint32), ocl.view(np.uint32))
+        pi, pc = orc.peaks(both[i], oi, oc)
+        opk = orc.cloud(both[i], pi, pc)
+        assert out["peaks"][i].shape == opk.shape
+        assert np.array_equal(out["peaks"][i].view(np.uint32), opk.view(np.uint32))
+
+
+def test_compensate(ctx, orc, imgs):
+    im, _ = imgs
+    oi, oc = orc.kstrongest(im[0], 60, 12)
+    cl = orc.cloud(im[0], oi, oc)
+    mot = np.array([2.5, 0.03, 0.025])
+    for ccw in (False, True):
+        g = ctx.compensate(cl, mot, ccw)
+        o = orc.compensate(cl, mot, ccw)
+        # fp64 atan2/sincos differ from glibc by <= 1-2 ulp(double); after rounding to fp32 that is a rare 1-ulp flip
+        ulp = np.abs(g.view(np.int32).astype(np.int64) - o.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1
+        assert (ulp > 0).mean() < 1e-3
+    z = ctx.compensate(cl, np.zeros(3))
+    assert np.array_equal(z.view(np.uint32), cl.view(np.uint32))       # identity motion is exact
+
+
+def _assert_cells_close(g, o):
+    assert g["mean"].shape == o["mean"].shape
+    assert np.array_equal(g["nsamples"], o["nsamples"])                # neighbour sets: exact fp32 radius test
+    np.testing.assert_allclose(g["mean"], o["mean"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(g["cov"], o["cov"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(g["planarity"], o["planarity"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(g["avg_intensity"], o["avg_intensity"], rtol=1e-12)
+    np.testing.assert_allclose(g["normal"], o["normal"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("radius,wint", [(3.5, True), (3.0, True), (3.5, False), (2.0, True), (5.0, False)])
+def test_surface_points(orc, imgs, radius, wint):
+    im, _ = imgs
+    c = capi.Context(max_batch=2, radius=radius, weight_intensity=int(wint), max_cellsets=4)
+    for i in (0, 4):
+        cl, o = helpers.oracle_cells(orc, im[i], radius=radius, weight_intensity=wint)
+        n = c.surface_points(cl, 1)
+        assert n == o["mean"].shape[0] and n > 50
+        _assert_cells_close(c.cells_download(1), o)
+    c.close()
+
+
+def test_surface_points_edge_cases(ctx, orc):
+    assert ctx.surface_points(np.zeros((0, 4), np.float32), 2) == 0     # reference exits on an empty cloud
+    few = np.array([[10, 10, 0, 100], [10.5, 10, 0, 90], [11, 10.2, 0, 80]], np.float32)
+    assert ctx.surface_points(few, 2) == 0                               # < 6 neighbours
+    rng = np.random.Generator(np.random.PCG64(0))
+    line = np.zeros((50, 4), np.float32); line[:, 0] = np.linspace(5, 8, 50); line[:, 1] = 3.0; line[:, 3] = 100
+    o = orc.surface_points(line, 3.5)
+    assert ctx.surface_points(line, 2) == o["mean"].shape[0] == 0        # degenerate covariance -> invalid
+    dup = np.tile(np.array([[20, -7, 0, 61]], np.float32), (30, 1)); dup[:, :2] += rng.normal(0, 0.3, (30, 2)).astype(np.float32)
+    dup[:, 3] = 60                                                        # all weights 0 -> NaN -> invalid
+    assert ctx.surface_points(dup, 2) == orc.surface_points(dup, 3.5)["mean"].shape[0] == 0
+    blob = np.zeros((200, 4), np.float32); blob[:, :2] = rng.normal(0, 4.0, (200, 2)) + [30, 30]; blob[:, 3] = rng.uniform(61, 200, 200)
+    o = orc.surface_points(blob, 3.5)
+    assert ctx.surface_points(blob, 2) == o["mean"].shape[0] > 0
+    _assert_cells_close(ctx.cells_download(2), o)
+
+
+def test_nearest_exact(ctx, orc, imgs):
+    im, _ = imgs
+    cl, o = helpers.oracle_cells(orc, im[1])
+    ctx.cells_upload(3, o)
+    rng = np.random.Generator(np.random.PCG64(9))
+    q = np.concatenate([o["mean"] + rng.normal(0, 1.0, o["mean"].shape), rng.uniform(-160, 160, (2000, 2)),
+                        o["mean"], np.array([[1e4, 1e4], [-1e4, 3.0]])])
+    for radius in (2.0, 4.0, 0.5):
+        assert np.array_equal(ctx.nearest(3, q, radius), orc.nearest(o["mean"], q, radius))
+    # ties: duplicated means -> the smaller index wins
+    d = dict(o); d = {k: np.concatenate([v, v]) for k, v in o.items()}
+    ctx.cells_upload(3, d)
+    assert np.array_equal(ctx.nearest(3, q, 2.0), orc.nearest(d["mean"], q, 2.0))
+
+
+def _problem(orc, imgs, poses, K, radius):
+    sets = [helpers.oracle_cells(orc, imgs[i], radius=radius)[1] for i in range(K + 1)]
+    P = poses[:K + 1].copy()
+    P[K] = P[K - 1]          # guess = previous pose (about 2.5 m / 1.4 deg off)
+    return sets, P
+
+
+@pytest.mark.parametrize("cost,loss,wopt,K,solver", [
+    ("P2L", "Huber", 0, 1, "ceres_lm"), ("P2L", "Huber", 0, 1, "gn_fixed"), ("P2L", "Huber", 0, 4, "ceres_lm"),
+    ("P2D", "Huber", 4, 4, "ceres_lm"), ("P2P", "Huber", 4, 4, "ceres_lm"), ("P2D", "Cauchy", 1, 3, "ceres_lm"),
+    ("P2L", "None", 2, 2, "ceres_lm"), ("P2P", "SoftLOne", 3, 2, "gn_fixed"), ("P2D", "Combined", 0, 4, "ceres_lm"),
+    ("P2L", "Tukey", 0, 2, "ceres_lm")])
+def test_register_parity(orc, imgs, cost, loss, wopt, K, solver):
+    im, poses = imgs
+    radius = 3.0
+    sets, P = _problem(orc, im, poses, K, radius)
+    reg = 0.1 if cost == "P2D" else 1.0
+    c = capi.Context(max_batch=2, max_cellsets=8, max_keyframes=4, cost=cost, loss=loss, weight_opt=wopt,
+                     solver_mode=solver, regularization=reg, radius=radius)
+    for i, s in enumerate(sets):
+        c.cells_upload(i, s)
+    slots = np.arange(K + 1, dtype=np.int32)[None]
+    gp, gcov, gst, gassoc = c.register_batch(slots, P[None], want_assoc=True)
+    ocfg = orc.reg_cfg(cost=cost, loss=loss, weight_opt=wopt, regularization=reg, solver_mode=capi.SOLVER[solver])
+    ok, op, ocov, ost, oassoc = orc.register(sets, P, ocfg, want_assoc=True)
+    assert bool(gst["success"][0]) == ok
+    assert gst["outer_iterations"][0] == ost.outer_iterations
+    assert gst["inner_iterations"][0] == ost.inner_iterations
+    assert gst["num_residuals"][0] == ost.num_residuals
+    d = gp[0, K] - op[K]
+    assert np.hypot(d[0], d[1]) < POS_TOL and abs(d[2]) < ROT_TOL, d
+    assert np.array_equal(gp[0, :K], P[:K])                       # keyframe blocks are constant
+    n_src = sets[-1]["mean"].shape[0]
+    assert np.array_equal(gassoc[0, :, :n_src], oassoc)
+    np.testing.assert_allclose(gst["final_cost"][0], ost.final_cost, rtol=1e-6)
+    np.testing.assert_allclose(gst["score"][0], ost.score, rtol=1e-6)
+    np.testing.assert_allclose(gcov[0], ocov, rtol=1e-5, atol=1e-12)
+    # the solve actually moved toward the truth
+    if loss != "Tukey":      # Tukey(0.1) has zero gradient beyond 0.1 m: it (like the oracle) stays near the guess
+        assert np.hypot(*(gp[0, K, :2] - poses[K, :2])) < 0.3
+    c.close()
+
+
+def test_register_failure_modes(orc, imgs):
+    im, poses = imgs
+    sets, P = _problem(orc, im, poses, 1, 3.0)
+    c = capi.Context(max_batch=1, max_cellsets=4, max_keyframes=2)
+    c.cells_upload(0, sets[0]); c.cells_upload(1, sets[1])
+    far = P.copy(); far[1] = [500.0, 500.0, 0.0]                   # no correspondences -> Register() returns false
+    gp, gcov, gst = c.register([0, 1], far)
+    ok, op, ocov, ost, _ = orc.register(sets[:2], far, orc.reg_cfg())
+    assert not ok and gst["success"] == 0 and gst["num_residuals"] == ost.num_residuals == 0
+    assert np.array_equal(gp, far)                                 # pose untouched
+    assert np.array_equal(gcov, ocov)
+    with pytest.raises(capi.CfearError):
+        c.register([0, 9], P)                                      # bad slot
+    with pytest.raises(capi.CfearError):
+        c.register([0], P[:1])                                     # needs >= 2 scans (n_scan_normal.cpp:190)
+    c.close()
+
+
+def test_odometry_step_batch_matches_oracle_pipeline(orc):
+    """Whole path on host images: filter -> compensate -> surface points -> register, 6 independent problems."""
+    K, radius, nprob = 4, 3.0, 6
+    c = capi.Context(max_batch=nprob * (K + 1), max_cellsets=nprob * (K + 1), max_keyframes=K, cost="P2D", loss="Huber",
+                     weight_opt=4, regularization=0.1, radius=radius)
+    ocfg = orc.reg_cfg(cost="P2D", loss="Huber", weight_opt=4, regularization=0.1)
+    polar, kf_sets, kf_ids, poses, mot = [], [], [], [], []
+    for b in range(nprob):
+        im, tp = helpers.scan_images(20 + b, K)
+        ids = []
+        for i in range(K):
+            ids.append(len(kf_sets))
+            kf_sets.append(helpers.oracle_cells(orc, im[i], radius=radius)[1])
+        kf_ids.append(ids)
+        polar.append(im[K])
+        P = tp.copy(); P[K] = tp[K - 1]
+        poses.append(P)
+        from cfear_radarodometry_code_public_b200.synth import se2_inv, se2_mul
+        mot.append(se2_mul(se2_inv(tp[K - 2]), tp[K - 1]))
+    polar = np.stack(polar); poses = np.stack(poses); mot = np.stack(mot); kf_ids = np.array(kf_ids, np.int32)
+    ref = orc.pipeline_batch(polar, mot, kf_sets, kf_ids, poses, ocfg, radius=radius)
+    # keyframe cell sets are built by the GPU path itself from the keyframe images
+    for b in range(nprob):
+        im, _ = helpers.scan_images(20 + b, K)
+        for i in range(K):
+            out = c.filter(im[i][None])
+            c.surface_points(out["clouds"][0], kf_ids[b, i])
+    cur = np.arange(nprob, dtype=np.int32) + nprob * K
+    out = c.odometry_step_batch(polar, mot, kf_ids, cur, poses)
+    npts, ncells = c.last_counts(cur)
+    assert np.array_equal(npts, ref["npts"]) and np.array_equal(ncells, ref["ncells"])
+    for b in range(nprob):
+        d = out["poses"][b, K] - ref["poses"][b, K]
+        assert np.hypot(d[0], d[1]) < POS_TOL and abs(d[2]) < ROT_TOL, (b, d)
+        assert out["stats"]["outer_iterations"][b] == ref["stats"][b].outer_iterations
+        assert out["stats"]["num_residuals"][b] == ref["stats"][b].num_residuals
+    c.close()
