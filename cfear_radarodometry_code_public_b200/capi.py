@@ -47,7 +47,7 @@ STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), (
 # every symbol include/cfear_b200.h declares
 SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
-           "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
+           "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
            "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_dev", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h"]
@@ -89,6 +89,7 @@ def load():
         lib.cfear_filter.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_compensate.argtypes = [vp, vp, i32, vp, i32]
         lib.cfear_surface_points.argtypes = [vp, vp, i32, i32, vp]
+        lib.cfear_scans_to_cells_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         lib.cfear_cells_count.argtypes = [vp, i32, vp]
         lib.cfear_cells_download.argtypes = [vp, i32, vp, i32, vp]
         lib.cfear_cells_upload.argtypes = [vp, i32, vp, i32]
@@ -222,6 +223,16 @@ class Context:
                  "cfear_surface_points")
         return nc.value
 
+    def scans_to_cells_batch(self, polar, mot, slots):
+        polar = np.ascontiguousarray(polar, dtype=np.uint8).reshape(-1, self.A, self.R)
+        n = polar.shape[0]
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        m = None if mot is None else np.ascontiguousarray(mot, dtype=np.float64)
+        npts = np.zeros(n, np.int32); nc = np.zeros(n, np.int32)
+        self._ck(self.lib.cfear_scans_to_cells_batch(self.h, n, _ptr(polar), _ptr(m), _ptr(slots), _ptr(npts), _ptr(nc)),
+                 "cfear_scans_to_cells_batch")
+        return npts, nc
+
     def cells_count(self, slot):
         nc = C.c_int32(0)
         self._ck(self.lib.cfear_cells_count(self.h, int(slot), C.byref(nc)), "cfear_cells_count")
@@ -297,9 +308,16 @@ class Context:
         return npts, nc
 
     def stage_timing(self, enable=True):
+        """Returns (nsteps, [ms_kstrongest, ms_surface, ms_register]) summed since the previous call."""
         ms = (C.c_float * 3)()
-        self._ck(self.lib.cfear_stage_timing(self.h, int(bool(enable)), ms), "cfear_stage_timing")
-        return [ms[0], ms[1], ms[2]]
+        rc = self.lib.cfear_stage_timing(self.h, int(bool(enable)), ms)
+        if rc < 0:
+            self._ck(rc, "cfear_stage_timing")
+        return rc, [ms[0], ms[1], ms[2]]
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.cfear_stream(self.h))
 
     def sync(self):
         self._ck(self.lib.cfear_sync(self.h), "cfear_sync")

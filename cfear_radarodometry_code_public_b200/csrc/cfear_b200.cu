@@ -113,7 +113,9 @@ static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 struct cfear_ctx {
   cfear_config cfg;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev;      // 4 per timed step: before K1, after K1, after K3, after K5
+  int ev_used = 0;                  // timed steps recorded since the last cfear_stage_timing call
+  cudaEvent_t* evset = nullptr;     // current step's 4 events
   std::vector<cudaEvent_t> chunk_ev;
   int64_t launches = 0;
   int timing = 0;
@@ -197,7 +199,6 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (auto& e : c->ev) CK(cudaEventCreate(&e));
   const int A = cfg->azimuths, R = cfg->range_bins, k = cfg->k_strongest, B = cfg->max_batch;
   c->cap_pts = A * k;
   c->max_cells = cfg->max_cells > 0 ? cfg->max_cells : A * k;
@@ -358,6 +359,19 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   return CFEAR_OK;
 }
 
+static int begin_timed_step(cfear_ctx* c) {
+  if (!c->timing) return CFEAR_OK;
+  const int cap_steps = 4096;
+  if (c->ev_used >= cap_steps) c->ev_used = cap_steps - 1;
+  while ((int)c->ev.size() < 4 * (c->ev_used + 1)) {
+    cudaEvent_t e; CK(cudaEventCreate(&e));
+    c->ev.push_back(e);
+  }
+  c->evset = c->ev.data() + 4 * c->ev_used;
+  c->ev_used++;
+  return CFEAR_OK;
+}
+
 static int check_slot(cfear_ctx* c, int slot) {
   if (slot < 0 || slot >= c->cfg.max_cellsets) { g_err = "cell-set slot out of range"; return CFEAR_ERR_ARG; }
   return CFEAR_OK;
@@ -432,6 +446,29 @@ int cfear_surface_points(cfear_ctx* c, const cfear_point* cloud, int n, int slot
   CK(cudaStreamSynchronize(c->stream));
   if (st != 0) { g_err = "voxel grid exceeds capacity (extent / leaf too large)"; return CFEAR_ERR_CAPACITY; }
   if (ncells) *ncells = nc;
+  return CFEAR_OK;
+}
+
+int cfear_scans_to_cells_batch(cfear_ctx* c, int nscans, const uint8_t* polar, const double* mot, const int32_t* slots,
+                               int32_t* npts_out, int32_t* ncells_out) {
+  ENTER(c);
+  if (!polar || !slots) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (nscans < 0 || nscans > c->cfg.max_batch) { g_err = "nscans exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nscans == 0) return CFEAR_OK;
+  for (int i = 0; i < nscans; ++i) RC(check_slot(c, slots[i]));
+  const size_t img = (size_t)c->cfg.azimuths * c->cfg.range_bins;
+  CK(cudaMemcpyAsync(c->d_polar, polar, (size_t)nscans * img, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_curslots, slots, (size_t)nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  const bool have_mot = mot != nullptr && c->cfg.compensate;
+  if (have_mot) CK(cudaMemcpyAsync(c->d_mot, mot, (size_t)nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  RC(launch_k1(c, c->d_polar, nscans));
+  RC(launch_k3(c, 0, nscans, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
+  std::vector<int32_t> st(nscans);
+  CK(cudaMemcpyAsync(st.data(), c->d_status, (size_t)nscans * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nscans; ++i)
+    if (st[i] != 0) { g_err = "voxel grid exceeds capacity (extent / leaf too large)"; return CFEAR_ERR_CAPACITY; }
+  if (npts_out || ncells_out) RC(cfear_last_counts(c, nscans, slots, npts_out, ncells_out));
   return CFEAR_OK;
 }
 
@@ -541,16 +578,17 @@ __global__ void k_merge_slots(const int32_t* kf, const int32_t* cur, int K, int 
 
 static int step_dev(cfear_ctx* c, int nprob, const uint8_t* d_polar, const double* d_mot, const int32_t* d_kf_slots, int K,
                     const int32_t* d_cur_slots, double* d_poses, double* d_cov36, cfear_reg_stats* d_stats, bool k1_done) {
-  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  RC(begin_timed_step(c));
+  if (c->timing) CK(cudaEventRecord(c->evset[0], c->stream));
   if (!k1_done) RC(launch_k1(c, d_polar, nprob));
-  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing) CK(cudaEventRecord(c->evset[1], c->stream));
   RC(launch_k3(c, 0, nprob, d_mot, d_cur_slots, false));
-  if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+  if (c->timing) CK(cudaEventRecord(c->evset[2], c->stream));
   k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf_slots, d_cur_slots, K, nprob, c->d_slots);
   c->launches++;
   CK(cudaGetLastError());
   RC(launch_k5(c, nprob, K + 1, c->d_slots, d_poses, d_cov36, d_stats, nullptr));
-  if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
+  if (c->timing) CK(cudaEventRecord(c->evset[3], c->stream));
   return CFEAR_OK;
 }
 
@@ -592,7 +630,8 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->chunk_ev.push_back(e);
   }
-  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  RC(begin_timed_step(c));
+  if (c->timing) CK(cudaEventRecord(c->evset[0], c->stream));
   CK(cudaEventRecord(c->chunk_ev[nchunks], c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nchunks], 0));          // d_polar free (previous work done)
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -614,16 +653,14 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     CK(cudaGetLastError());
   }
   const int timing = c->timing;
-  c->timing = 0;                       // ev[0] already recorded; record the rest here
-  if (timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  if (timing) CK(cudaEventRecord(c->evset[1], c->stream));
   RC(launch_k3(c, 0, nprob, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
-  if (timing) CK(cudaEventRecord(c->ev[2], c->stream));
+  if (timing) CK(cudaEventRecord(c->evset[2], c->stream));
   k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf, c->d_curslots, K, nprob, c->d_slots);
   c->launches++;
   CK(cudaGetLastError());
   RC(launch_k5(c, nprob, K + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr));
-  if (timing) CK(cudaEventRecord(c->ev[3], c->stream));
-  c->timing = timing;
+  if (timing) CK(cudaEventRecord(c->evset[3], c->stream));
   CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * (K + 1) * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
@@ -635,16 +672,23 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
 
 int cfear_stage_timing(cfear_ctx* c, int enable, float ms_out[3]) {
   ENTER(c);
+  int steps = 0;
   if (ms_out) {
     ms_out[0] = ms_out[1] = ms_out[2] = 0.f;
-    if (c->timing) {
+    if (c->timing && c->ev_used > 0) {
       CK(cudaStreamSynchronize(c->stream));
-      for (int i = 0; i < 3; ++i)
-        if (cudaEventElapsedTime(&ms_out[i], c->ev[i], c->ev[i + 1]) != cudaSuccess) { ms_out[i] = 0.f; (void)cudaGetLastError(); }
+      for (int s = 0; s < c->ev_used; ++s)
+        for (int i = 0; i < 3; ++i) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, c->ev[4 * s + i], c->ev[4 * s + i + 1]) != cudaSuccess) { ms = 0.f; (void)cudaGetLastError(); }
+          ms_out[i] += ms;
+        }
+      steps = c->ev_used;
     }
   }
+  c->ev_used = 0;
   c->timing = enable;
-  return CFEAR_OK;
+  return steps;       /* >= 0: number of timed steps summed into ms_out */
 }
 
 int cfear_last_counts(cfear_ctx* c, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out) {

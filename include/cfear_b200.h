@@ -136,6 +136,10 @@ int cfear_compensate(cfear_ctx* ctx, cfear_point* cloud, int n, const double mot
 /* ---- surface points -------------------------------------------------------------------------------------------- */
 /* Build the cell set of one (already compensated) host cloud into device slot `slot`; returns ncells via *ncells. */
 int cfear_surface_points(cfear_ctx* ctx, const cfear_point* cloud, int n, int slot, int32_t* ncells);
+/* radarDriver::CallbackOffline -> Compensate -> MapPointNormal for nscans HOST images at once: cell set i lands in
+ * slots[i] (mot [nscans][3] may be NULL = no compensation).  This is how keyframe sets become device resident. */
+int cfear_scans_to_cells_batch(cfear_ctx* ctx, int nscans, const uint8_t* polar, const double* mot,
+                               const int32_t* slots, int32_t* npts_out, int32_t* ncells_out);
 int cfear_cells_count(cfear_ctx* ctx, int slot, int32_t* ncells);
 int cfear_cells_download(cfear_ctx* ctx, int slot, cfear_cell* out, int capacity, int32_t* ncells);
 /* Upload an arbitrary cell set (also builds its nearest-neighbour index). */
@@ -172,9 +176,10 @@ int cfear_odometry_step_batch_dev(cfear_ctx* ctx, int nprob, const uint8_t* d_po
 int cfear_sync(cfear_ctx* ctx);
 /* The CUDA stream (cudaStream_t as void*) the context launches on, for event timing by the caller. */
 void* cfear_stream(cfear_ctx* ctx);
-/* Device-time (ms, CUDA events on the context stream) spent in each stage of the most recent
- * cfear_odometry_step_batch[_dev] call: [0] k-strongest, [1] surface points, [2] registration.
- * Only recorded when enabled (it adds event records around the launches). */
+/* Device time (ms, CUDA events on the context stream) per stage, SUMMED over every cfear_odometry_step_batch[_dev]
+ * call since the previous cfear_stage_timing call: [0] k-strongest (+ its H2D chunks on the host-buffer path),
+ * [1] surface points, [2] registration.  Returns the number of steps summed (>= 0) or a negative status.
+ * `enable` switches recording for the following steps (it adds 4 event records per step). */
 int cfear_stage_timing(cfear_ctx* ctx, int enable, float ms_out[3]);
 /* Per-scan counts of the most recent step (device->host copy): npts/ncells of cur_slots order. */
 int cfear_last_counts(cfear_ctx* ctx, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out);
