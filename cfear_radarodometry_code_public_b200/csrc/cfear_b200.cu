@@ -353,7 +353,14 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
   p.radius = c->cfg.reg_radius;
-  k5_register<<<nprob, K5_THREADS, 0, c->stream>>>(p);
+  if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
+#define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, 0, c->stream>>>(p); break;
+  switch (p.cost * 6 + p.loss) {
+    K5_CASE(0, 0) K5_CASE(0, 1) K5_CASE(0, 2) K5_CASE(0, 3) K5_CASE(0, 4) K5_CASE(0, 5)
+    K5_CASE(1, 0) K5_CASE(1, 1) K5_CASE(1, 2) K5_CASE(1, 3) K5_CASE(1, 4) K5_CASE(1, 5)
+    K5_CASE(2, 0) K5_CASE(2, 1) K5_CASE(2, 2) K5_CASE(2, 3) K5_CASE(2, 4) K5_CASE(2, 5)
+  }
+#undef K5_CASE
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;

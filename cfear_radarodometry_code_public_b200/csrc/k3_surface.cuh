@@ -307,109 +307,133 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     bufB[pos] = q;
   }
   __syncthreads();
+  // restore input order inside every voxel (VoxelGrid sums a voxel's points in a fixed order; the oracle's is
+  // ascending input index): rank by counting, one thread per point, neighbours in a warp share the segment
+  for (int a = tid; a < n; a += T) {
+    const float4 q = bufB[a];
+    const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
+    const int v = i0 + i1 * divx;
+    const int s = v ? hist[v - 1] : 0, e = hist[v];
+    const int me = __float_as_int(q.z);
+    int rank = 0;
+    for (int b = s; b < e; ++b) rank += (__float_as_int(bufB[b].z) < me);
+    bufA[s + rank] = q;
+  }
+  __syncthreads();
+  float4* pts = bufA;                                      // points bucketed by voxel, input order inside a voxel
 
-  // ---- per voxel: restore input order, sequential fp32 centroid; ordered list of non-empty voxels ---
-  float2* cxy = reinterpret_cast<float2*>(bufA);           // bufA is free now: centroid list, later fp32 cell means
+  // ---- ordered list of non-empty voxels, sequential fp32 centroid per voxel ---------------------------
+  float2* cxy = reinterpret_cast<float2*>(bufB);           // bufB is free now: centroid list, later fp32 cell means
+  int* vlist = reinterpret_cast<int*>(cxy + cap);          // non-empty voxel ids, ascending
   {
     const int chunk = (nbins + T - 1) / T;
     const int lo = min(tid * chunk, nbins), hi = min(lo + chunk, nbins);
     int nonempty = 0;
-    for (int v = lo; v < hi; ++v) {
-      const int s = v ? hist[v - 1] : 0, e = hist[v];
-      if (e > s) {
-        ++nonempty;
-        for (int a = s + 1; a < e; ++a) {                   // insertion sort by input index
-          const float4 key = bufB[a];
-          const int ki = __float_as_int(key.z);
-          int b = a - 1;
-          while (b >= s && __float_as_int(bufB[b].z) > ki) { bufB[b + 1] = bufB[b]; --b; }
-          bufB[b + 1] = key;
-        }
-      }
-    }
+    for (int v = lo; v < hi; ++v) nonempty += (hist[v] > (v ? hist[v - 1] : 0));
     int total;
     int base = block_excl_scan(nonempty, s_warp, &total);
-    for (int v = lo; v < hi; ++v) {
-      const int s = v ? hist[v - 1] : 0, e = hist[v];
-      if (e > s) {
-        float sx = 0.f, sy = 0.f;
-        for (int a = s; a < e; ++a) { sx += bufB[a].x; sy += bufB[a].y; }
-        const float cnt = (float)(e - s);
-        cxy[base++] = make_float2(sx / cnt, sy / cnt);
-      }
-    }
+    for (int v = lo; v < hi; ++v)
+      if (hist[v] > (v ? hist[v - 1] : 0)) vlist[base++] = v;
     if (tid == 0) s_misc[0] = total;
     __syncthreads();
   }
   const int nvox = s_misc[0];
+  for (int c = tid; c < nvox; c += T) {
+    const int v = vlist[c];
+    const int s = v ? hist[v - 1] : 0, e = hist[v];
+    float sx = 0.f, sy = 0.f;
+    for (int a = s; a < e; ++a) { sx += pts[a].x; sy += pts[a].y; }
+    const float cnt = (float)(e - s);
+    cxy[c] = make_float2(sx / cnt, sy / cnt);
+  }
+  __syncthreads();
 
-  // ---- per centroid: radius neighbourhood -> cell ---------------------------------------------------
+  // ---- per centroid: radius neighbourhood -> cell.  8 lanes share one centroid; a block round handles
+  // T centroids (group g takes centroids c0+8g..c0+8g+7 in turn, sub-lane s keeps the s-th result) so that
+  // thread order == centroid order for the ordered compaction ------------------------------------------
   const float r = p.radius;
   const float r2 = (float)((double)r * (double)r);
   const float rq = r * 1.0001f + 1e-4f;                    // bin-range margin (the d2 test itself is exact)
   const size_t cbase = (size_t)slot * p.pool.max_cells;
+  const int grp = tid >> 3, sl = tid & 7;
+  const unsigned gmask = 0xffu << (lane_id() & 24);
+  const bool wint = p.weight_intensity != 0;
   int ncells = 0;                                          // block-uniform running count
   for (int c0 = 0; c0 < nvox; c0 += T) {
-    const int c = c0 + tid;
     bool valid = false;
     double ux = 0, uy = 0, cxx = 0, cxy_ = 0, cyx = 0, cyy = 0, scale = 0, nx_ = 0, ny_ = 0, avgI = 0;
     int N = 0;
-    if (c < nvox) {
+    for (int sub = 0; sub < 8; ++sub) {
+      const int c = c0 + grp * 8 + sub;                     // uniform over the 8-lane group
+      if (c >= nvox) break;
       const float2 q = cxy[c];
       int bx0 = (int)(floorf((q.x - rq) * inv) - fminbx), bx1 = (int)(floorf((q.x + rq) * inv) - fminbx);
       int by0 = (int)(floorf((q.y - rq) * inv) - fminby), by1 = (int)(floorf((q.y + rq) * inv) - fminby);
       bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, divx - 1); by1 = min(by1, divy - 1);
-      double wsum = 0.0;
+      int gN = 0; double wsum = 0.0;
       for (int by = by0; by <= by1; ++by) {                 // pass 1: N, sum of weights
         const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
         const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-        for (int a = s; a < e; ++a) {
-          const float4 pt = bufB[a];
+        for (int a = s + sl; a < e; a += 8) {
+          const float4 pt = pts[a];
           const float dx = q.x - pt.x, dy = q.y - pt.y;
           float d2 = dx * dx; d2 += dy * dy;
           if (d2 < r2) {
-            ++N;
-            wsum += p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0;    // pointnormal.cpp:15
+            ++gN;
+            wsum += wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0;                   // pointnormal.cpp:15
           }
         }
       }
-      if (N >= 6) {                                         // pointnormal.cpp:291
-        for (int by = by0; by <= by1; ++by) {               // pass 2: weighted mean (:21-24)
-          const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-          const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-          for (int a = s; a < e; ++a) {
-            const float4 pt = bufB[a];
-            const float dx = q.x - pt.x, dy = q.y - pt.y;
-            float d2 = dx * dx; d2 += dy * dy;
-            if (d2 < r2) {
-              const double w = (p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
-              ux += w * (double)pt.x; uy += w * (double)pt.y;
-            }
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) { gN += __shfl_xor_sync(gmask, gN, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
+      if (gN < 6) continue;                                 // pointnormal.cpp:291 (uniform over the group)
+      double mx = 0.0, my = 0.0;
+      for (int by = by0; by <= by1; ++by) {                 // pass 2: weighted mean (:21-24)
+        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+        for (int a = s + sl; a < e; a += 8) {
+          const float4 pt = pts[a];
+          const float dx = q.x - pt.x, dy = q.y - pt.y;
+          float d2 = dx * dx; d2 += dy * dy;
+          if (d2 < r2) {
+            const double w = (wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
+            mx += w * (double)pt.x; my += w * (double)pt.y;
           }
         }
-        for (int by = by0; by <= by1; ++by) {               // pass 3: weighted scatter (:26-33)
-          const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-          const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-          for (int a = s; a < e; ++a) {
-            const float4 pt = bufB[a];
-            const float dx = q.x - pt.x, dy = q.y - pt.y;
-            float d2 = dx * dx; d2 += dy * dy;
-            if (d2 < r2) {
-              const double w = (p.weight_intensity ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
-              const double ex = (double)pt.x - ux, ey = (double)pt.y - uy;
-              const double wx = w * ex, wy = w * ey;
-              cxx += ex * wx; cxy_ += ex * wy; cyx += ey * wx; cyy += ey * wy;
-            }
+      }
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) { mx += __shfl_xor_sync(gmask, mx, d); my += __shfl_xor_sync(gmask, my, d); }
+      double sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
+      for (int by = by0; by <= by1; ++by) {                 // pass 3: weighted scatter (:26-33)
+        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+        for (int a = s + sl; a < e; a += 8) {
+          const float4 pt = pts[a];
+          const float dx = q.x - pt.x, dy = q.y - pt.y;
+          float d2 = dx * dx; d2 += dy * dy;
+          if (d2 < r2) {
+            const double w = (wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
+            const double ex = (double)pt.x - mx, ey = (double)pt.y - my;
+            const double wx = w * ex, wy = w * ey;
+            sxx += ex * wx; sxy += ex * wy; syx += ey * wx; syy += ey * wy;
           }
         }
-        const Eig2 eg = eig2_sym(cxx, cyx, cyy);            // ComputeNormal (:37-63)
+      }
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        sxx += __shfl_xor_sync(gmask, sxx, d); sxy += __shfl_xor_sync(gmask, sxy, d);
+        syx += __shfl_xor_sync(gmask, syx, d); syy += __shfl_xor_sync(gmask, syy, d);
+      }
+      if (sl == sub) {                                      // this sub-lane keeps centroid c's cell
+        const Eig2 eg = eig2_sym(sxx, syx, syy);            // ComputeNormal (:37-63)
         const double cond = fabs(eg.lmax / eg.lmin);
         const double det = eg.lmax * eg.lmin;
         valid = (cond <= 10000) && (det > 0.00001) && eg.lmin > 0 && eg.lmax > 0;
         scale = log(1.0 + cond / 2);
         nx_ = eg.nx; ny_ = eg.ny;
-        if (nx_ * (p.origin_x - ux) + ny_ * (p.origin_y - uy) < 0) { nx_ = -nx_; ny_ = -ny_; }
-        avgI = wsum / (double)N;
+        if (nx_ * (p.origin_x - mx) + ny_ * (p.origin_y - my) < 0) { nx_ = -nx_; ny_ = -ny_; }
+        ux = mx; uy = my; cxx = sxx; cxy_ = sxy; cyx = syx; cyy = syy;
+        avgI = wsum / (double)gN; N = gN;
       }
     }
     int total;
@@ -421,7 +445,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
       p.pool.planarity[cbase + pos] = scale;
       p.pool.avg_intensity[cbase + pos] = avgI;
       p.pool.nsamples[cbase + pos] = N;
-      cxy[pos] = make_float2((float)ux, (float)uy);        // pointnormal.cpp:153-157 (pos <= c: safe in place)
+      cxy[pos] = make_float2((float)ux, (float)uy);        // pointnormal.cpp:153-157 (pos <= own centroid index)
     }
     ncells += total;
     __syncthreads();

@@ -19,7 +19,7 @@
 
 namespace cfear {
 
-constexpr int K5_THREADS = 512;
+constexpr int K5_THREADS = 128;      // 4 warps per problem; several problems resident per SM
 constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int K5_MAXSCANS = 65;     // K+1 <= 65
 
@@ -45,35 +45,31 @@ struct RegStatsDev {             // == cfear_reg_stats
 
 struct Resid { double px, py, qx, qy, a, b, c, w; };
 
-// ceres/loss_function.cc
-__device__ __forceinline__ void loss_eval(int loss, double a, double s, double rho[3]) {
-  switch (loss) {
-    case 1: {
-      const double b = a * a;
-      if (s > b) { const double r = sqrt(s); rho[0] = 2.0 * a * r - b; rho[1] = fmax(2.2250738585072014e-308, a / r); rho[2] = -rho[1] / (2.0 * s); }
-      else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
-      return; }
-    case 2: {
-      const double b = a * a, c = 1.0 / b;
-      const double sum = 1.0 + s * c, inv = 1.0 / sum;
-      rho[0] = b * log(sum); rho[1] = fmax(2.2250738585072014e-308, inv); rho[2] = -c * (inv * inv);
-      return; }
-    case 3: {
-      const double b = a * a, c = 1.0 / b;
-      const double sum = 1.0 + s * c, tmp = sqrt(sum);
-      rho[0] = 2.0 * b * (tmp - 1.0); rho[1] = fmax(2.2250738585072014e-308, 1.0 / tmp); rho[2] = -(c * rho[1]) / (2.0 * sum);
-      return; }
-    case 4: {   // ComposedLoss(Huber(1), Cauchy(1))  registration.cpp:88-92
-      double g[3], f[3];
-      loss_eval(2, 1.0, s, g); loss_eval(1, 1.0, g[0], f);
-      rho[0] = f[0]; rho[1] = f[1] * g[1]; rho[2] = f[2] * g[1] * g[1] + f[1] * g[2];
-      return; }
-    case 5: {
-      const double a2 = a * a;
-      if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho[0] = a2 / 3.0 * (1.0 - v2 * v); rho[1] = v2; rho[2] = -2.0 / a2 * v; }
-      else { rho[0] = a2 / 3.0; rho[1] = 0.0; rho[2] = 0.0; }
-      return; }
-    default: rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return;
+// ceres/loss_function.cc (rho[2] is only needed by Ceres' corrector when rho'' > 0, which none of these have)
+template <int LOSS>
+__device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
+  if constexpr (LOSS == 1) {            // HuberLoss
+    const double b = a * a;
+    if (s > b) { const double r = sqrt(s); rho[0] = 2.0 * a * r - b; rho[1] = fmax(2.2250738585072014e-308, a / r); rho[2] = -rho[1] / (2.0 * s); }
+    else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+  } else if constexpr (LOSS == 2) {     // CauchyLoss
+    const double b = a * a, c = 1.0 / b;
+    const double sum = 1.0 + s * c, inv = 1.0 / sum;
+    rho[0] = b * log(sum); rho[1] = fmax(2.2250738585072014e-308, inv); rho[2] = -c * (inv * inv);
+  } else if constexpr (LOSS == 3) {     // SoftLOneLoss
+    const double b = a * a, c = 1.0 / b;
+    const double sum = 1.0 + s * c, tmp = sqrt(sum);
+    rho[0] = 2.0 * b * (tmp - 1.0); rho[1] = fmax(2.2250738585072014e-308, 1.0 / tmp); rho[2] = -(c * rho[1]) / (2.0 * sum);
+  } else if constexpr (LOSS == 4) {     // ComposedLoss(Huber(1), Cauchy(1))  registration.cpp:88-92
+    double g[3], f[3];
+    loss_eval<2>(1.0, s, g); loss_eval<1>(1.0, g[0], f);
+    rho[0] = f[0]; rho[1] = f[1] * g[1]; rho[2] = f[2] * g[1] * g[1] + f[1] * g[2];
+  } else if constexpr (LOSS == 5) {     // TukeyLoss
+    const double a2 = a * a;
+    if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho[0] = a2 / 3.0 * (1.0 - v2 * v); rho[1] = v2; rho[2] = -2.0 / a2 * v; }
+    else { rho[0] = a2 / 3.0; rho[1] = 0.0; rho[2] = 0.0; }
+  } else {                              // None: ScaledLoss(nullptr, w)
+    rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
   }
 }
 
@@ -81,9 +77,10 @@ struct EvalOut { double cost, H[6], g[3]; };
 
 // Block-wide evaluation of cost (and normal equations) over the residual list at x.
 // s_part: [2][K5_WARPS][10] doubles; *parity toggles per call (one __syncthreads per evaluation).
-__device__ inline void block_evaluate(int cost_kind, int loss, double loss_limit, const double4* __restrict__ res,
-                                      int nres, const double x[3], bool with_jac, EvalOut& ev,
-                                      double* s_part, int& parity) {
+template <int COST, int LOSS>
+__device__ __forceinline__ void block_evaluate(double loss_limit, const double4* __restrict__ res,
+                                               int nres, const double x[3], bool with_jac, EvalOut& ev,
+                                               double* s_part, int& parity) {
   double cs, sn; sincos(x[2], &sn, &cs);
   double acc[10];
 #pragma unroll
@@ -97,10 +94,10 @@ __device__ inline void block_evaluate(int cost_kind, int loss, double loss_limit
     const double a = v1.x, b = v1.y, c = v1.z, w = v1.w;
     double r0, r1 = 0.0, J0[3], J1[3] = {0, 0, 0};
     bool two;
-    if (cost_kind == 1) {
+    if constexpr (COST == 1) {
       r0 = ex * a + ey * b; two = false;
       J0[0] = a; J0[1] = b; J0[2] = dpx * a + dpy * b;
-    } else if (cost_kind == 2) {
+    } else if constexpr (COST == 2) {
       r0 = a * ex; r1 = b * ex + c * ey; two = true;
       J0[0] = a; J0[1] = 0.0; J0[2] = a * dpx;
       J1[0] = b; J1[1] = c; J1[2] = b * dpx + c * dpy;
@@ -111,7 +108,7 @@ __device__ inline void block_evaluate(int cost_kind, int loss, double loss_limit
     }
     const double s = r0 * r0 + r1 * r1;
     double rho[3];
-    loss_eval(loss, loss_limit, s, rho);
+    loss_eval<LOSS>(loss_limit, s, rho);
     acc[0] += 0.5 * w * rho[0];
     if (with_jac) {
       const double wr = w * rho[1];
@@ -171,7 +168,8 @@ struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usa
 
 // Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc),
 // block-uniform control flow.
-__device__ inline void lm_solve(const RegParams& P, const double4* res, int nres, double x[3], SolveSum& sum,
+template <int COST, int LOSS>
+__device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res, int nres, double x[3], SolveSum& sum,
                                 double* s_part, int& parity) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
@@ -182,7 +180,7 @@ __device__ inline void lm_solve(const RegParams& P, const double4* res, int nres
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
   EvalOut ev;
-  block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+  block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -228,7 +226,7 @@ __device__ inline void lm_solve(const RegParams& P, const double4* res, int nres
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     EvalOut evc;
-    block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, xc, false, evc, s_part, parity);
+    block_evaluate<COST, LOSS>(P.loss_limit, res, nres, xc, false, evc, s_part, parity);
     const double cand_cost = evc.cost;
     const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
@@ -239,7 +237,7 @@ __device__ inline void lm_solve(const RegParams& P, const double4* res, int nres
     if (rel > kMinRelDecrease) {
       x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
       x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
       x_cost = ev.cost;
       gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
       const double t = 2.0 * rel - 1.0;
@@ -289,7 +287,8 @@ __device__ __forceinline__ int nn_query(const CellPool& pool, int slot, const NN
 __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) / (x + y); }
 
 // One outer iteration's association pass.  Returns the number of residual blocks (block-uniform).
-__device__ inline int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
+template <int COST>
+__device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
                                     const NNGrid* s_grid, const double x[3], int itr, double4* res, int32_t* assoc,
                                     int* s_warp) {
   const int ns = P.nscans, K = ns - 1;
@@ -337,9 +336,9 @@ __device__ inline int build_problem(const RegParams& P, const int32_t* slots, co
           const double2 tm = P.pool.mean[tb];
           R.qx = ct * tm.x - st * tm.y + pt[0]; R.qy = st * tm.x + ct * tm.y + pt[1];
           R.a = R.b = R.c = 0.0;
-          if (P.cost == 1) {                                                           // :279-289
+          if constexpr (COST == 1) {                                                   // :279-289
             R.a = ct * ntar.x - st * ntar.y; R.b = st * ntar.x + ct * ntar.y;
-          } else if (P.cost == 2) {                                                    // :290-300
+          } else if constexpr (COST == 2) {                                            // :290-300
             const double4 C = P.pool.cov[tb];
             const double a00 = ct * C.x - st * C.z, a01 = ct * C.y - st * C.w;
             const double a10 = st * C.x + ct * C.z, a11 = st * C.y + ct * C.w;
@@ -370,7 +369,8 @@ __device__ inline int build_problem(const RegParams& P, const int32_t* slots, co
   return min(nres, P.res_cap);
 }
 
-__global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) {
+template <int COST, int LOSS>
+__global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) {
   __shared__ int s_warp[33];
   __shared__ double s_part[2 * K5_WARPS * 10];
   __shared__ double s_pose[K5_MAXSCANS * 5];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) 
   double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
   double4* res = P.res + (size_t)prob * P.res_cap * 4;
   int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * K * P.pool.max_cells : nullptr;
-  const int per_block = (P.cost == 1) ? 1 : 2;
+  constexpr int per_block = (COST == 1) ? 1 : 2;
   int parity = 0;
 
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
@@ -404,10 +404,10 @@ __global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) 
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
-      nres = build_problem(P, s_slots, s_pose, s_grid, x, it, res, assoc, s_warp);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, x, it, res, assoc, s_warp);
       if (nres * per_block <= 1) { success = false; break; }
       EvalOut ev;
-      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
       double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
       if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
       x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) 
     outer = it;
     if (success) {
       EvalOut ev;
-      block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, false, ev, s_part, parity);
+      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, false, ev, s_part, parity);
       sum.final_cost = ev.cost;
     }
   } else {
@@ -425,9 +425,9 @@ __global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) 
     double prev_score = 1.7976931348623157e308;
     int itr;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
-      nres = build_problem(P, s_slots, s_pose, s_grid, x, itr, res, assoc, s_warp);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, x, itr, res, assoc, s_warp);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
-      lm_solve(P, res, nres, x, sum, s_part, parity);                           // :117
+      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity);                           // :117
       success = sum.usable;
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) k5_register(const RegParams P) 
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     EvalOut ev;                                                                 // GetCovariance :392-433
-    block_evaluate(P.cost, P.loss, P.loss_limit, res, nres, x, true, ev, s_part, parity);
+    block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
     double inv[9]; bool ok = true;
     for (int c = 0; c < 3 && ok; ++c) {
       double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
