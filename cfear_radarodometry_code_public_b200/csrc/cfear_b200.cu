@@ -75,7 +75,8 @@ __global__ void k4b_nearest(CellPool pool, int slot, const double* q, int nq, do
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const NNGrid G = pool.grid[slot];
-  out[i] = nn_query(pool, slot, G, q[2 * i], q[2 * i + 1], radius);
+  GridView V; V.gs = pool.gstart + (size_t)slot * pool.grid_stride; V.gp = pool.gpt + (size_t)slot * pool.max_cells;
+  out[i] = nn_query(V, G, q[2 * i], q[2 * i + 1], radius);
 }
 
 // AoS cfear_cell <-> pool SoA
@@ -121,7 +122,7 @@ struct cfear_ctx {
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
-  int pts_in_smem = 0; size_t k3_smem = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0; int k5_smem = 0;
   int g_hist_cap = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -131,7 +132,7 @@ struct cfear_ctx {
   int* d_ghist = nullptr; int32_t* d_status = nullptr;
   double* d_mot = nullptr; int32_t *d_slots = nullptr, *d_curslots = nullptr, *d_kfslots = nullptr;
   double *d_poses = nullptr, *d_cov36 = nullptr; cfear_reg_stats* d_stats = nullptr; int32_t* d_assoc = nullptr;
-  double4* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
+  double2* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
   CellPool pool;
   std::vector<double2> h_cs;
 
@@ -184,8 +185,9 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   *out = nullptr;
   if (cfg->azimuths < 1 || cfg->range_bins < 1 || cfg->k_strongest < 1 || cfg->k_strongest > K1_MAXK ||
       cfg->max_batch < 1 || cfg->max_keyframes < 1 || cfg->max_keyframes + 1 > K5_MAXSCANS || cfg->max_cellsets < 1 ||
-      cfg->range_bins > 65535 || !(cfg->radius > 0.f) || !(cfg->downsample_factor > 0.0)) {
-    g_err = "invalid configuration (need 1<=k<=64, range_bins<=65535, max_keyframes<=64, radius>0)";
+      cfg->range_bins > 65535 || !(cfg->radius > 0.f) || !(cfg->downsample_factor > 0.0) || cfg->max_cells > 65535 ||
+      (cfg->max_cells <= 0 && (long long)cfg->azimuths * cfg->k_strongest > 65535)) {
+    g_err = "invalid configuration (need 1<=k<=64, range_bins<=65535, max_keyframes<=64, radius>0, max_cells<=65535)";
     return CFEAR_ERR_ARG;
   }
   int ndev = 0;
@@ -214,6 +216,12 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
   CK(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+  c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
+#define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
+  K5_ATTR(0, 0) K5_ATTR(0, 1) K5_ATTR(0, 2) K5_ATTR(0, 3) K5_ATTR(0, 4) K5_ATTR(0, 5)
+  K5_ATTR(1, 0) K5_ATTR(1, 1) K5_ATTR(1, 2) K5_ATTR(1, 3) K5_ATTR(1, 4) K5_ATTR(1, 5)
+  K5_ATTR(2, 0) K5_ATTR(2, 1) K5_ATTR(2, 2) K5_ATTR(2, 3) K5_ATTR(2, 4) K5_ATTR(2, 5)
+#undef K5_ATTR
 
   const size_t rows = (size_t)B * A;
   AL(c->d_polar, rows * R);
@@ -235,10 +243,11 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   const size_t S = (size_t)cfg->max_cellsets, M = (size_t)c->max_cells;
   P.max_cells = c->max_cells; P.grid_cap = c->grid_cap;
   AL(P.ncells, S); AL(P.mean, S * M); AL(P.normal, S * M); AL(P.cov, S * M); AL(P.planarity, S * M);
-  AL(P.avg_intensity, S * M); AL(P.nsamples, S * M); AL(P.grid, S); AL(P.gstart, S * (P.grid_cap + 1));
-  AL(P.gxy, S * M); AL(P.gidx, S * M); AL(P.fm_scratch, S * M);
+  AL(P.avg_intensity, S * M); AL(P.nsamples, S * M); AL(P.grid, S);
+  P.grid_stride = P.grid_cap + 8;
+  AL(P.gstart, S * P.grid_stride); AL(P.gpt, S * M); AL(P.fm_scratch, S * M);
   CK(cudaMemsetAsync(P.ncells, 0, S * sizeof(int), c->stream));
-  CK(cudaMemsetAsync(P.gstart, 0, S * (P.grid_cap + 1) * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(P.gstart, 0, S * P.grid_stride * sizeof(uint16_t), c->stream));
   {
     std::vector<NNGrid> g(S);
     for (auto& x : g) { x.ox = x.oy = 0.f; x.g = 4.f; x.inv_g = 0.25f; x.nx = x.ny = 1; }
@@ -354,7 +363,8 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
   p.radius = c->cfg.reg_radius;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
-#define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, 0, c->stream>>>(p); break;
+  p.smem_bytes = c->k5_smem;
+#define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); break;
   switch (p.cost * 6 + p.loss) {
     K5_CASE(0, 0) K5_CASE(0, 1) K5_CASE(0, 2) K5_CASE(0, 3) K5_CASE(0, 4) K5_CASE(0, 5)
     K5_CASE(1, 0) K5_CASE(1, 1) K5_CASE(1, 2) K5_CASE(1, 3) K5_CASE(1, 4) K5_CASE(1, 5)

@@ -27,12 +27,12 @@ struct CellPool {
   double* planarity;       // scale_
   double* avg_intensity;
   int* nsamples;
-  // NN index
+  // NN index: uniform bucket grid over the fp32 means
   NNGrid* grid;            // [slots]
-  int* gstart;             // [slots][grid_cap+1]
-  float2* gxy;             // [slots][max_cells]  fp32 means sorted by grid cell
-  int* gidx;               // [slots][max_cells]  original cell index
-  float2* fm_scratch;      // [slots][max_cells]  fp32 means staging for the index build of uploaded sets
+  uint16_t* gstart;        // [slots][grid_stride]  bucket start offsets (nx*ny+1 used); u16: max_cells <= 65535
+  float4* gpt;             // [slots][max_cells]    (x, y, cell index as int bits, 0) sorted by bucket
+  float2* fm_scratch;      // [slots][max_cells]    fp32 means staging for the index build of uploaded sets
+  int grid_stride;         // u16 entries per slot (grid_cap + 8: keeps every slot 16-byte aligned for bulk copies)
 };
 
 // ------------------------------------------------------------------------------------------------

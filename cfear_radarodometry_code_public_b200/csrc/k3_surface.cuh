@@ -144,17 +144,16 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
   }
   __syncthreads();
   block_array_excl_scan(hist, nb + 1, s_warp);      // hist[b] = start of bucket b, hist[nb] = n
-  int* gstart = pool.gstart + (size_t)slot * (pool.grid_cap + 1);
-  for (int b = tid; b <= nb; b += T) gstart[b] = hist[b];
+  uint16_t* gstart = pool.gstart + (size_t)slot * pool.grid_stride;
+  for (int b = tid; b <= nb; b += T) gstart[b] = (uint16_t)hist[b];
   __syncthreads();
-  float2* gxy = pool.gxy + (size_t)slot * pool.max_cells;
-  int* gidx = pool.gidx + (size_t)slot * pool.max_cells;
+  float4* gpt = pool.gpt + (size_t)slot * pool.max_cells;
   for (int i = tid; i < n; i += T) {
     const float2 p = fm[i];
     int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
     bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
     const int pos = atomicAdd(&hist[bx + by * nx], 1);
-    gxy[pos] = p; gidx[pos] = i;
+    gpt[pos] = make_float4(p.x, p.y, __int_as_float(i), 0.f);
   }
   if (tid == 0) {
     NNGrid G; G.ox = mnx; G.oy = mny; G.inv_g = inv; G.g = g; G.nx = nx; G.ny = ny;
@@ -261,8 +260,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
       p.pool.ncells[slot] = 0;
       NNGrid G; G.ox = G.oy = 0.f; G.g = p.nn_cell; G.inv_g = 1.f / p.nn_cell; G.nx = G.ny = 1;
       p.pool.grid[slot] = G;
-      p.pool.gstart[(size_t)slot * (p.pool.grid_cap + 1)] = 0;
-      p.pool.gstart[(size_t)slot * (p.pool.grid_cap + 1) + 1] = 0;
+      p.pool.gstart[(size_t)slot * p.pool.grid_stride] = 0;
+      p.pool.gstart[(size_t)slot * p.pool.grid_stride + 1] = 0;
     }
     return;
   }

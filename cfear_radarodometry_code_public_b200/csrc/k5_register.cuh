@@ -16,12 +16,14 @@
 // scalar trust-region logic is executed redundantly by every thread on identical inputs.
 #pragma once
 #include "common.cuh"
+#include "k3_surface.cuh"   // mbarrier / TMA bulk-copy helpers
 
 namespace cfear {
 
-constexpr int K5_THREADS = 128;      // 4 warps per problem; several problems resident per SM
+constexpr int K5_THREADS = 256;      // 8 warps per problem, 2 problems resident per SM
 constexpr int K5_WARPS = K5_THREADS / 32;
-constexpr int K5_MAXSCANS = 65;     // K+1 <= 65
+constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
+constexpr int K5_SMEM_BYTES = 100 * 1024;   // dynamic smem per CTA: keyframe NN grids staged by TMA bulk copies
 
 struct RegParams {
   CellPool pool;
@@ -31,8 +33,9 @@ struct RegParams {
   double* cov36;                 // [nprob][36]
   void* stats;                   // [nprob] cfear_reg_stats
   int32_t* assoc;                // [nprob][nscans-1][max_cells] or null
-  double4* res;                  // [nprob][res_cap][4]  residual scratch (64 B each)
+  double2* res;                  // [nprob][4][res_cap] residual scratch, SoA: (px,py) (qx,qy) (a,b) (c,w)
   int res_cap;
+  int smem_bytes;                // dynamic shared memory given to the kernel
   int cost, loss, weight_opt, solver_mode;
   int max_outer, min_outer, max_inner, gn_iters;
   double loss_limit, cov_scale, regularization, radius;
@@ -42,8 +45,6 @@ struct RegStatsDev {             // == cfear_reg_stats
   int32_t success, outer_iterations, inner_iterations, num_residuals, num_blocks, usable;
   double final_cost, score;
 };
-
-struct Resid { double px, py, qx, qy, a, b, c, w; };
 
 // ceres/loss_function.cc (rho[2] is only needed by Ceres' corrector when rho'' > 0, which none of these have)
 template <int LOSS>
@@ -75,71 +76,89 @@ __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
 
 struct EvalOut { double cost, H[6], g[3]; };
 
-// Block-wide evaluation of cost (and normal equations) over the residual list at x.
-// s_part: [2][K5_WARPS][10] doubles; *parity toggles per call (one __syncthreads per evaluation).
-template <int COST, int LOSS>
-__device__ __forceinline__ void block_evaluate(double loss_limit, const double4* __restrict__ res,
-                                               int nres, const double x[3], bool with_jac, EvalOut& ev,
-                                               double* s_part, int& parity) {
+// One residual block's contribution at x (cs = cos psi, sn = sin psi): cost and (optionally) normal equations.
+// Residuals / Jacobians: n_scan_normal.h:180-255, 330-361; loss: ScaledLoss(w) around the base loss with
+// Ceres' corrector in its rho'' <= 0 form (rows scaled by sqrt(w rho')).
+template <int COST, int LOSS, bool JAC>
+__device__ __forceinline__ void accumulate(double loss_limit, double cs, double sn, const double x[3], double2 p, double2 q,
+                                           double2 ab, double2 cw, double acc[10]) {
+  const double rx = cs * p.x - sn * p.y, ry = sn * p.x + cs * p.y;
+  const double ex = rx + x[0] - q.x, ey = ry + x[1] - q.y;
+  const double dpx = -ry, dpy = rx;
+  const double a = ab.x, b = ab.y, c = cw.x, w = cw.y;
+  double r0, r1 = 0.0, J0[3], J1[3] = {0, 0, 0};
+  if constexpr (COST == 1) {
+    r0 = ex * a + ey * b;
+    J0[0] = a; J0[1] = b; J0[2] = dpx * a + dpy * b;
+  } else if constexpr (COST == 2) {
+    r0 = a * ex; r1 = b * ex + c * ey;
+    J0[0] = a; J0[1] = 0.0; J0[2] = a * dpx;
+    J1[0] = b; J1[1] = c; J1[2] = b * dpx + c * dpy;
+  } else {
+    r0 = -ex; r1 = -ey;
+    J0[0] = -1.0; J0[1] = 0.0; J0[2] = -dpx;
+    J1[0] = 0.0; J1[1] = -1.0; J1[2] = -dpy;
+  }
+  const double s = r0 * r0 + r1 * r1;
+  double rho[3];
+  loss_eval<LOSS>(loss_limit, s, rho);
+  acc[0] += 0.5 * w * rho[0];
+  if constexpr (JAC) {
+    const double wr = w * rho[1];
+    acc[1] += wr * J0[0] * J0[0]; acc[2] += wr * J0[0] * J0[1]; acc[3] += wr * J0[0] * J0[2];
+    acc[4] += wr * J0[1] * J0[1]; acc[5] += wr * J0[1] * J0[2]; acc[6] += wr * J0[2] * J0[2];
+    acc[7] += wr * J0[0] * r0; acc[8] += wr * J0[1] * r0; acc[9] += wr * J0[2] * r0;
+    if constexpr (COST != 1) {
+      acc[1] += wr * J1[0] * J1[0]; acc[2] += wr * J1[0] * J1[1]; acc[3] += wr * J1[0] * J1[2];
+      acc[4] += wr * J1[1] * J1[1]; acc[5] += wr * J1[1] * J1[2]; acc[6] += wr * J1[2] * J1[2];
+      acc[7] += wr * J1[0] * r1; acc[8] += wr * J1[1] * r1; acc[9] += wr * J1[2] * r1;
+    }
+  }
+}
+
+// Block-wide evaluation over the residual list at x.  Loads of two residual blocks are issued before either
+// is consumed (the list lives in L2).  s_part: [2][K5_WARPS][10]; parity toggles per call -> one
+// __syncthreads per evaluation.  Deterministic: fixed per-thread order, xor-butterfly, fixed cross-warp order.
+template <int COST, int LOSS, bool JAC>
+__device__ __forceinline__ void block_evaluate(double loss_limit, const double2* __restrict__ res, int res_cap,
+                                               int nres, const double x[3], EvalOut& ev, double* s_part, int& parity) {
   double cs, sn; sincos(x[2], &sn, &cs);
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
-  for (int r = threadIdx.x; r < nres; r += blockDim.x) {
-    const double4 v0 = res[4 * (size_t)r + 0], v1 = res[4 * (size_t)r + 1];   // px py qx qy | a b c w
-    const double2 pq = make_double2(v0.x, v0.y);
-    const double rx = cs * pq.x - sn * pq.y, ry = sn * pq.x + cs * pq.y;
-    const double ex = rx + x[0] - v0.z, ey = ry + x[1] - v0.w;
-    const double dpx = -ry, dpy = rx;
-    const double a = v1.x, b = v1.y, c = v1.z, w = v1.w;
-    double r0, r1 = 0.0, J0[3], J1[3] = {0, 0, 0};
-    bool two;
-    if constexpr (COST == 1) {
-      r0 = ex * a + ey * b; two = false;
-      J0[0] = a; J0[1] = b; J0[2] = dpx * a + dpy * b;
-    } else if constexpr (COST == 2) {
-      r0 = a * ex; r1 = b * ex + c * ey; two = true;
-      J0[0] = a; J0[1] = 0.0; J0[2] = a * dpx;
-      J1[0] = b; J1[1] = c; J1[2] = b * dpx + c * dpy;
-    } else {
-      r0 = -ex; r1 = -ey; two = true;
-      J0[0] = -1.0; J0[1] = 0.0; J0[2] = -dpx;
-      J1[0] = 0.0; J1[1] = -1.0; J1[2] = -dpy;
-    }
-    const double s = r0 * r0 + r1 * r1;
-    double rho[3];
-    loss_eval<LOSS>(loss_limit, s, rho);
-    acc[0] += 0.5 * w * rho[0];
-    if (with_jac) {
-      const double wr = w * rho[1];
-      acc[1] += wr * J0[0] * J0[0]; acc[2] += wr * J0[0] * J0[1]; acc[3] += wr * J0[0] * J0[2];
-      acc[4] += wr * J0[1] * J0[1]; acc[5] += wr * J0[1] * J0[2]; acc[6] += wr * J0[2] * J0[2];
-      acc[7] += wr * J0[0] * r0; acc[8] += wr * J0[1] * r0; acc[9] += wr * J0[2] * r0;
-      if (two) {
-        acc[1] += wr * J1[0] * J1[0]; acc[2] += wr * J1[0] * J1[1]; acc[3] += wr * J1[0] * J1[2];
-        acc[4] += wr * J1[1] * J1[1]; acc[5] += wr * J1[1] * J1[2]; acc[6] += wr * J1[2] * J1[2];
-        acc[7] += wr * J1[0] * r1; acc[8] += wr * J1[1] * r1; acc[9] += wr * J1[2] * r1;
-      }
-    }
+  const double2* f0 = res; const double2* f1 = res + res_cap; const double2* f2 = res + 2 * (size_t)res_cap;
+  const double2* f3 = res + 3 * (size_t)res_cap;
+  int r = threadIdx.x;
+  for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
+    const int r2 = r + K5_THREADS;
+    const double2 p0 = f0[r], q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
+    const double2 p1 = f0[r2], q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
+    accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
+    accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
   }
-  const int nv = with_jac ? 10 : 1;
+  if (r < nres) accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, f0[r], f1[r], f2[r], f3[r], acc);
+  constexpr int nv = JAC ? 10 : 1;
   double* part = s_part + parity * (K5_WARPS * 10);
   parity ^= 1;
+#pragma unroll
   for (int i = 0; i < nv; ++i) {
     const double v = warp_sum(acc[i]);
     if (lane_id() == 0) part[warp_id() * 10 + i] = v;
   }
   __syncthreads();
-  const int nw = blockDim.x >> 5;
   double tot[10];
+#pragma unroll
   for (int i = 0; i < nv; ++i) {
     double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += part[w * 10 + i];
+#pragma unroll
+    for (int w = 0; w < K5_WARPS; ++w) t += part[w * 10 + i];
     tot[i] = t;
   }
   ev.cost = tot[0];
-  if (with_jac) {
+  if constexpr (JAC) {
+#pragma unroll
     for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
+#pragma unroll
     for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
   }
 }
@@ -167,10 +186,11 @@ __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3]
 struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usable; };
 
 // Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc),
-// block-uniform control flow.
+// block-uniform control flow.  The candidate point is evaluated with its Jacobian in the same pass, so an
+// accepted step needs no second pass over the residuals (the sums are the ones a re-evaluation would give).
 template <int COST, int LOSS>
-__device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res, int nres, double x[3], SolveSum& sum,
-                                double* s_part, int& parity) {
+__device__ __forceinline__ void lm_solve(const RegParams& P, const double2* res, int nres, double x[3], SolveSum& sum,
+                                         double* s_part, int& parity) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -180,7 +200,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res,
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
   EvalOut ev;
-  block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
+  block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -226,7 +246,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res,
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     EvalOut evc;
-    block_evaluate<COST, LOSS>(P.loss_limit, res, nres, xc, false, evc, s_part, parity);
+    block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, xc, evc, s_part, parity);
     const double cand_cost = evc.cost;
     const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
@@ -237,7 +257,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res,
     if (rel > kMinRelDecrease) {
       x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
       x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      ev = evc;
       x_cost = ev.cost;
       gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
       const double t = 2.0 * rel - 1.0;
@@ -256,28 +276,26 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double4* res,
   }
 }
 
-// GetClosestIdx: exact fp32 nearest neighbour through the slot's bucket grid; ties -> smallest cell index.
-__device__ __forceinline__ int nn_query(const CellPool& pool, int slot, const NNGrid& G, double pxd, double pyd,
-                                        double radius) {
+// One keyframe's NN index as seen by the block: bucket starts + packed points, in shared memory when staged.
+struct GridView { const uint16_t* gs; const float4* gp; };
+
+// GetClosestIdx: exact fp32 nearest neighbour through the bucket grid; ties -> smallest cell index.
+__device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, double radius) {
   const float qx = (float)pxd, qy = (float)pyd;             // pointnormal.cpp:241-242
   const float rq = (float)radius * 1.0001f + 1e-3f;         // bucket-range margin only
   int bx0 = (int)floorf((qx - rq - G.ox) * G.inv_g), bx1 = (int)floorf((qx + rq - G.ox) * G.inv_g);
   int by0 = (int)floorf((qy - rq - G.oy) * G.inv_g), by1 = (int)floorf((qy + rq - G.oy) * G.inv_g);
   bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, G.nx - 1); by1 = min(by1, G.ny - 1);
-  const int* gstart = pool.gstart + (size_t)slot * (pool.grid_cap + 1);
-  const float2* gxy = pool.gxy + (size_t)slot * pool.max_cells;
-  const int* gidx = pool.gidx + (size_t)slot * pool.max_cells;
   float best = 3.4028234e38f; int besti = -1;
+  if (bx0 > bx1) return -1;
   for (int by = by0; by <= by1; ++by) {
-    const int s = gstart[bx0 + by * G.nx], e = gstart[bx1 + by * G.nx + 1];
+    const int s = V.gs[bx0 + by * G.nx], e = V.gs[bx1 + by * G.nx + 1];
     for (int a = s; a < e; ++a) {
-      const float2 m = gxy[a];
+      const float4 m = V.gp[a];
       const float dx = qx - m.x, dy = qy - m.y;
       float d2 = dx * dx; d2 += dy * dy;
-      if (d2 <= best) {
-        const int i = gidx[a];
-        if (d2 < best || i < besti) { best = d2; besti = i; }
-      }
+      const int i = __float_as_int(m.z);
+      if (d2 < best || (d2 == best && i < besti)) { best = d2; besti = i; }
     }
   }
   if (besti >= 0 && (double)best < radius * radius) return besti;   // pointnormal.cpp:250
@@ -289,8 +307,8 @@ __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmi
 // One outer iteration's association pass.  Returns the number of residual blocks (block-uniform).
 template <int COST>
 __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
-                                    const NNGrid* s_grid, const double x[3], int itr, double4* res, int32_t* assoc,
-                                    int* s_warp) {
+                                             const NNGrid* s_grid, const GridView* s_view, const double x[3], int itr,
+                                             double2* res, int32_t* assoc, int* s_warp) {
   const int ns = P.nscans, K = ns - 1;
   const int src_slot = slots[K];
   const int n_src = P.pool.ncells[src_slot];
@@ -299,25 +317,26 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
   const double angle_outlier = cos(M_PI / 6.0);
   const double curr_radius = (itr == 1) ? 2 * P.radius : P.radius;       // n_scan_normal.cpp:222
   const int npairs = K * n_src;
+  const int cap = P.res_cap;
   int nres = 0;
   for (int t0 = 0; t0 < npairs; t0 += blockDim.x) {
     const int t = t0 + threadIdx.x;
     bool valid = false;
-    Resid R; int i = 0, j = 0, m = -1;
+    double2 rp = make_double2(0, 0), rq = rp, rab = rp, rcw = rp;
     if (t < npairs) {
-      i = t / n_src; j = t - i * n_src;
+      const int i = t / n_src, j = t - i * n_src;
       const double* pt = s_pose + 5 * i;
       const double ct = pt[3], st = pt[4];
       const double rc = ct * cs_s + st * sn_s, rs = ct * sn_s - st * cs_s;     // Ttar^-1 * Tsrc   :224
       const double dx = x[0] - pt[0], dy = x[1] - pt[1];
       const double tx = ct * dx + st * dy, ty = -st * dx + ct * dy;
       const double2 mu = P.pool.mean[sbase + j];
+      const double2 nsrc = P.pool.normal[sbase + j];
       const double qx = rc * mu.x - rs * mu.y + tx, qy = rs * mu.x + rc * mu.y + ty;   // :240
       const int tslot = slots[i];
-      m = nn_query(P.pool, tslot, s_grid[i], qx, qy, curr_radius);                    // :241
+      const int m = nn_query(s_view[i], s_grid[i], qx, qy, curr_radius);              // :241
       if (m >= 0) {
         const size_t tb = (size_t)tslot * P.pool.max_cells + m;
-        const double2 nsrc = P.pool.normal[sbase + j];
         const double2 ntar = P.pool.normal[tb];
         const double ntx = rc * nsrc.x - rs * nsrc.y, nty = rs * nsrc.x + rc * nsrc.y;  // :244
         const double sim = fmax(ntx * ntar.x + nty * ntar.y, 0.0);                      // :246
@@ -332,12 +351,12 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
             else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
             else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
           }
-          R.w = w; R.px = mu.x; R.py = mu.y;
+          rp = mu;
           const double2 tm = P.pool.mean[tb];
-          R.qx = ct * tm.x - st * tm.y + pt[0]; R.qy = st * tm.x + ct * tm.y + pt[1];
-          R.a = R.b = R.c = 0.0;
+          rq = make_double2(ct * tm.x - st * tm.y + pt[0], st * tm.x + ct * tm.y + pt[1]);
+          rcw.y = w;
           if constexpr (COST == 1) {                                                   // :279-289
-            R.a = ct * ntar.x - st * ntar.y; R.b = st * ntar.x + ct * ntar.y;
+            rab = make_double2(ct * ntar.x - st * ntar.y, st * ntar.x + ct * ntar.y);
           } else if constexpr (COST == 2) {                                            // :290-300
             const double4 C = P.pool.cov[tb];
             const double a00 = ct * C.x - st * C.z, a01 = ct * C.y - st * C.w;
@@ -351,7 +370,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
             const double l00 = sqrt(i00);
             const double l10 = i10 / l00;
             const double l11 = sqrt(i11 - l10 * l10);
-            R.a = l00; R.b = l10; R.c = l11;
+            rab = make_double2(l00, l10); rcw.x = l11;
           }
         }
       }
@@ -359,23 +378,25 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
     }
     int total;
     const int pos = nres + block_excl_scan(valid ? 1 : 0, s_warp, &total);
-    if (valid && pos < P.res_cap) {
-      res[4 * (size_t)pos + 0] = make_double4(R.px, R.py, R.qx, R.qy);
-      res[4 * (size_t)pos + 1] = make_double4(R.a, R.b, R.c, R.w);
+    if (valid && pos < cap) {
+      res[pos] = rp; res[cap + pos] = rq; res[2 * (size_t)cap + pos] = rab; res[3 * (size_t)cap + pos] = rcw;
     }
     nres += total;
   }
   __syncthreads();                 // residual list visible to the whole block
-  return min(nres, P.res_cap);
+  return min(nres, cap);
 }
 
 template <int COST, int LOSS>
-__global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) {
+__global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ double s_part[2 * K5_WARPS * 10];
   __shared__ double s_pose[K5_MAXSCANS * 5];
   __shared__ NNGrid s_grid[K5_MAXSCANS];
+  __shared__ GridView s_view[K5_MAXSCANS];
   __shared__ int32_t s_slots[K5_MAXSCANS];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int prob = blockIdx.x;
   const int ns = P.nscans, K = ns - 1;
@@ -390,9 +411,47 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) 
     s_pose[5 * tid + 0] = poses[3 * tid + 0]; s_pose[5 * tid + 1] = poses[3 * tid + 1];
     s_pose[5 * tid + 2] = yaw; s_pose[5 * tid + 3] = c; s_pose[5 * tid + 4] = s;
   }
+  if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
+  // Stage the keyframes' NN indices (bucket starts + packed fp32 means) into shared memory with TMA bulk
+  // copies, keyframe by keyframe while they fit; the rest is read through L2.
+  if (tid == 0) {
+    uint32_t off = 0, tx = 0;
+    for (int i = 0; i < K; ++i) {
+      const int sl = s_slots[i];
+      const NNGrid G = s_grid[i];
+      const int n = P.pool.ncells[sl];
+      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
+      const uint32_t gp_bytes = (uint32_t)n * 16u;
+      const uint16_t* g_gs = P.pool.gstart + (size_t)sl * P.pool.grid_stride;
+      const float4* g_gp = P.pool.gpt + (size_t)sl * P.pool.max_cells;
+      GridView V; V.gs = g_gs; V.gp = g_gp;
+      if (off + gs_bytes + gp_bytes <= (uint32_t)P.smem_bytes) {
+        V.gs = reinterpret_cast<const uint16_t*>(dyn_smem + off);
+        V.gp = reinterpret_cast<const float4*>(dyn_smem + off + gs_bytes);
+        off += gs_bytes + gp_bytes; tx += gs_bytes + gp_bytes;
+      }
+      s_view[i] = V;
+    }
+    mbar_expect_tx(&s_bar, tx);
+    for (int i = 0; i < K; ++i) {
+      const int sl = s_slots[i];
+      const NNGrid G = s_grid[i];
+      const int n = P.pool.ncells[sl];
+      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
+      const uint32_t gp_bytes = (uint32_t)n * 16u;
+      const uint16_t* g_gs = P.pool.gstart + (size_t)sl * P.pool.grid_stride;
+      if (s_view[i].gs != g_gs) {
+        tma_bulk_g2s(const_cast<uint16_t*>(s_view[i].gs), g_gs, gs_bytes, &s_bar);
+        if (gp_bytes) tma_bulk_g2s(const_cast<float4*>(s_view[i].gp), P.pool.gpt + (size_t)sl * P.pool.max_cells, gp_bytes, &s_bar);
+      }
+    }
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
   double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
-  double4* res = P.res + (size_t)prob * P.res_cap * 4;
+  double2* res = P.res + (size_t)prob * P.res_cap * 4;
   int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * K * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
   int parity = 0;
@@ -404,10 +463,10 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) 
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, x, it, res, assoc, s_warp);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp);
       if (nres * per_block <= 1) { success = false; break; }
       EvalOut ev;
-      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
+      block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
       double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
       if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
       x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
@@ -417,7 +476,7 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) 
     outer = it;
     if (success) {
       EvalOut ev;
-      block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, false, ev, s_part, parity);
+      block_evaluate<COST, LOSS, false>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
       sum.final_cost = ev.cost;
     }
   } else {
@@ -425,9 +484,9 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) 
     double prev_score = 1.7976931348623157e308;
     int itr;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, x, itr, res, assoc, s_warp);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
-      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity);                           // :117
+      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity);               // :117
       success = sum.usable;
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
@@ -454,7 +513,7 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_register(const RegParams P) 
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     EvalOut ev;                                                                 // GetCovariance :392-433
-    block_evaluate<COST, LOSS>(P.loss_limit, res, nres, x, true, ev, s_part, parity);
+    block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
     double inv[9]; bool ok = true;
     for (int c = 0; c < 3 && ok; ++c) {
       double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
