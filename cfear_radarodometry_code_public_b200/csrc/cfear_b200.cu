@@ -129,7 +129,7 @@ struct cfear_ctx {
   uint8_t* d_polar = nullptr; double2* d_cs = nullptr;
   int32_t *d_kidx = nullptr, *d_kcnt = nullptr, *d_rowcnt = nullptr, *d_rowpeakcnt = nullptr, *d_npts = nullptr, *d_npeaks = nullptr;
   float4 *d_rowcloud = nullptr, *d_rowpeaks = nullptr, *d_cloud = nullptr, *d_peaks = nullptr, *d_bufA = nullptr, *d_bufB = nullptr;
-  int* d_ghist = nullptr; int32_t* d_status = nullptr;
+  int* d_ghist = nullptr; int32_t* d_status = nullptr; double2* d_celltmp = nullptr;
   double* d_mot = nullptr; int32_t *d_slots = nullptr, *d_curslots = nullptr, *d_kfslots = nullptr;
   double *d_poses = nullptr, *d_cov36 = nullptr; cfear_reg_stats* d_stats = nullptr; int32_t* d_assoc = nullptr;
   double2* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
@@ -232,6 +232,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   AL(c->d_npts, B); AL(c->d_npeaks, B); AL(c->d_status, B);
   if (!c->pts_in_smem) { AL(c->d_bufA, (size_t)B * c->cap_pts); AL(c->d_bufB, (size_t)B * c->cap_pts); }
   AL(c->d_ghist, (size_t)B * (c->g_hist_cap + 1));
+  AL(c->d_celltmp, (size_t)B * c->cap_pts * 6);
   AL(c->d_mot, (size_t)B * 3);
   const int ns = cfg->max_keyframes + 1;
   AL(c->d_slots, (size_t)B * ns); AL(c->d_curslots, B); AL(c->d_kfslots, (size_t)B * ns);
@@ -346,7 +347,7 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
   p.weight_intensity = c->cfg.weight_intensity; p.origin_x = 0.0; p.origin_y = 0.0;   // odometrykeyframefuser.cpp:161
   p.nn_cell = 4.0f;
   p.pts_in_smem = c->pts_in_smem; p.g_bufA = c->d_bufA; p.g_bufB = c->d_bufB;
-  p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.pool = c->pool;
+  p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.cell_tmp = c->d_celltmp; p.pool = c->pool;
   k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());

@@ -47,6 +47,7 @@ struct K3Params {
   float4* g_bufA; float4* g_bufB;   // [nscans][cap_pts] global fallback
   int* g_hist; int g_hist_cap;      // [nscans][g_hist_cap+1] global fallback for large grids
   int32_t* status;             // [nscans] 0 ok, 1 voxel grid over capacity
+  double2* cell_tmp;           // [nscans][cap_pts][6] uncompacted cells (scratch)
   CellPool pool;
 };
 
@@ -347,104 +348,97 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   }
   __syncthreads();
 
-  // ---- per centroid: radius neighbourhood -> cell.  8 lanes share one centroid; a block round handles
-  // T centroids (group g takes centroids c0+8g..c0+8g+7 in turn, sub-lane s keeps the s-th result) so that
-  // thread order == centroid order for the ordered compaction ------------------------------------------
+  // ---- per centroid: radius neighbourhood -> cell.  8 lanes share one centroid and groups pull centroids
+  // from a shared counter (dense neighbourhoods cluster in voxel order, static assignment would idle most
+  // of the block).  One pass accumulates the weight / first / second moments about the centroid q
+  // (exact in fp64: q and the points are fp32), from which the weighted mean and the central covariance of
+  // pointnormal.cpp:21-33 follow.  Cells land in a per-scan scratch at their centroid index; an ordered
+  // compaction of the valid ones follows. ---------------------------------------------------------------
   const float r = p.radius;
   const float r2 = (float)((double)r * (double)r);
   const float rq = r * 1.0001f + 1e-4f;                    // bin-range margin (the d2 test itself is exact)
   const size_t cbase = (size_t)slot * p.pool.max_cells;
-  const int grp = tid >> 3, sl = tid & 7;
+  const int sl = tid & 7;
   const unsigned gmask = 0xffu << (lane_id() & 24);
+  const int gleader = lane_id() & 24;
   const bool wint = p.weight_intensity != 0;
-  int ncells = 0;                                          // block-uniform running count
-  for (int c0 = 0; c0 < nvox; c0 += T) {
-    bool valid = false;
-    double ux = 0, uy = 0, cxx = 0, cxy_ = 0, cyx = 0, cyy = 0, scale = 0, nx_ = 0, ny_ = 0, avgI = 0;
-    int N = 0;
-    for (int sub = 0; sub < 8; ++sub) {
-      const int c = c0 + grp * 8 + sub;                     // uniform over the 8-lane group
-      if (c >= nvox) break;
-      const float2 q = cxy[c];
-      int bx0 = (int)(floorf((q.x - rq) * inv) - fminbx), bx1 = (int)(floorf((q.x + rq) * inv) - fminbx);
-      int by0 = (int)(floorf((q.y - rq) * inv) - fminby), by1 = (int)(floorf((q.y + rq) * inv) - fminby);
-      bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, divx - 1); by1 = min(by1, divy - 1);
-      int gN = 0; double wsum = 0.0;
-      for (int by = by0; by <= by1; ++by) {                 // pass 1: N, sum of weights
-        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-        for (int a = s + sl; a < e; a += 8) {
-          const float4 pt = pts[a];
-          const float dx = q.x - pt.x, dy = q.y - pt.y;
-          float d2 = dx * dx; d2 += dy * dy;
-          if (d2 < r2) {
-            ++gN;
-            wsum += wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0;                   // pointnormal.cpp:15
-          }
+  unsigned char* vflag = reinterpret_cast<unsigned char*>(vlist + cap);     // [cap] validity per centroid
+  double2* tmp = p.cell_tmp + (size_t)scan * cap * 6;                        // [cap][6] double2
+  if (tid == 0) s_misc[1] = 0;
+  __syncthreads();
+  for (;;) {
+    int c = 0;
+    if (sl == 0) c = atomicAdd(&s_misc[1], 1);
+    c = __shfl_sync(gmask, c, gleader);
+    if (c >= nvox) break;
+    const float2 q = cxy[c];
+    int bx0 = (int)(floorf((q.x - rq) * inv) - fminbx), bx1 = (int)(floorf((q.x + rq) * inv) - fminbx);
+    int by0 = (int)(floorf((q.y - rq) * inv) - fminby), by1 = (int)(floorf((q.y + rq) * inv) - fminby);
+    bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, divx - 1); by1 = min(by1, divy - 1);
+    int gN = 0;
+    double S0 = 0.0, S1x = 0.0, S1y = 0.0, Sxx = 0.0, Sxy = 0.0, Syy = 0.0;
+    for (int by = by0; by <= by1; ++by) {
+      const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
+      const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+      for (int a = s + sl; a < e; a += 8) {
+        const float4 pt = pts[a];
+        const float dx = q.x - pt.x, dy = q.y - pt.y;
+        float d2 = dx * dx; d2 += dy * dy;                  // FLANN L2_Simple in fp32, strict d2 < r2
+        if (d2 < r2) {
+          ++gN;
+          const double w = wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0;          // pointnormal.cpp:15
+          const double ex = (double)pt.x - (double)q.x, ey = (double)pt.y - (double)q.y;
+          const double wx = w * ex, wy = w * ey;
+          S0 += w; S1x += wx; S1y += wy; Sxx += wx * ex; Sxy += wx * ey; Syy += wy * ey;
         }
       }
+    }
 #pragma unroll
-      for (int d = 1; d < 8; d <<= 1) { gN += __shfl_xor_sync(gmask, gN, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
-      if (gN < 6) continue;                                 // pointnormal.cpp:291 (uniform over the group)
-      double mx = 0.0, my = 0.0;
-      for (int by = by0; by <= by1; ++by) {                 // pass 2: weighted mean (:21-24)
-        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-        for (int a = s + sl; a < e; a += 8) {
-          const float4 pt = pts[a];
-          const float dx = q.x - pt.x, dy = q.y - pt.y;
-          float d2 = dx * dx; d2 += dy * dy;
-          if (d2 < r2) {
-            const double w = (wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
-            mx += w * (double)pt.x; my += w * (double)pt.y;
-          }
-        }
-      }
-#pragma unroll
-      for (int d = 1; d < 8; d <<= 1) { mx += __shfl_xor_sync(gmask, mx, d); my += __shfl_xor_sync(gmask, my, d); }
-      double sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
-      for (int by = by0; by <= by1; ++by) {                 // pass 3: weighted scatter (:26-33)
-        const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-        const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-        for (int a = s + sl; a < e; a += 8) {
-          const float4 pt = pts[a];
-          const float dx = q.x - pt.x, dy = q.y - pt.y;
-          float d2 = dx * dx; d2 += dy * dy;
-          if (d2 < r2) {
-            const double w = (wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0) / wsum;
-            const double ex = (double)pt.x - mx, ey = (double)pt.y - my;
-            const double wx = w * ex, wy = w * ey;
-            sxx += ex * wx; sxy += ex * wy; syx += ey * wx; syy += ey * wy;
-          }
-        }
-      }
-#pragma unroll
-      for (int d = 1; d < 8; d <<= 1) {
-        sxx += __shfl_xor_sync(gmask, sxx, d); sxy += __shfl_xor_sync(gmask, sxy, d);
-        syx += __shfl_xor_sync(gmask, syx, d); syy += __shfl_xor_sync(gmask, syy, d);
-      }
-      if (sl == sub) {                                      // this sub-lane keeps centroid c's cell
-        const Eig2 eg = eig2_sym(sxx, syx, syy);            // ComputeNormal (:37-63)
+    for (int d = 1; d < 8; d <<= 1) {
+      gN += __shfl_xor_sync(gmask, gN, d);
+      S0 += __shfl_xor_sync(gmask, S0, d); S1x += __shfl_xor_sync(gmask, S1x, d); S1y += __shfl_xor_sync(gmask, S1y, d);
+      Sxx += __shfl_xor_sync(gmask, Sxx, d); Sxy += __shfl_xor_sync(gmask, Sxy, d); Syy += __shfl_xor_sync(gmask, Syy, d);
+    }
+    if (sl == 0) {
+      bool valid = false;
+      if (gN >= 6) {                                        // pointnormal.cpp:291
+        const double mdx = S1x / S0, mdy = S1y / S0;        // weighted mean relative to q
+        const double ux = (double)q.x + mdx, uy = (double)q.y + mdy;
+        const double cxx = Sxx / S0 - mdx * mdx, cxy_ = Sxy / S0 - mdx * mdy, cyy = Syy / S0 - mdy * mdy;
+        const Eig2 eg = eig2_sym(cxx, cxy_, cyy);           // ComputeNormal (:37-63)
         const double cond = fabs(eg.lmax / eg.lmin);
         const double det = eg.lmax * eg.lmin;
         valid = (cond <= 10000) && (det > 0.00001) && eg.lmin > 0 && eg.lmax > 0;
-        scale = log(1.0 + cond / 2);
-        nx_ = eg.nx; ny_ = eg.ny;
-        if (nx_ * (p.origin_x - mx) + ny_ * (p.origin_y - my) < 0) { nx_ = -nx_; ny_ = -ny_; }
-        ux = mx; uy = my; cxx = sxx; cxy_ = sxy; cyx = syx; cyy = syy;
-        avgI = wsum / (double)gN; N = gN;
+        if (valid) {
+          double nx_ = eg.nx, ny_ = eg.ny;
+          if (nx_ * (p.origin_x - ux) + ny_ * (p.origin_y - uy) < 0) { nx_ = -nx_; ny_ = -ny_; }
+          double2* o = tmp + (size_t)c * 6;
+          o[0] = make_double2(ux, uy); o[1] = make_double2(nx_, ny_);
+          o[2] = make_double2(cxx, cxy_); o[3] = make_double2(cxy_, cyy);
+          o[4] = make_double2(log(1.0 + cond / 2), S0 / (double)gN);              // scale_, avg_intensity_
+          o[5] = make_double2(__longlong_as_double((long long)gN), 0.0);
+        }
       }
+      vflag[c] = valid ? 1 : 0;
     }
+  }
+  __syncthreads();
+  int ncells = 0;                                          // block-uniform running count
+  for (int c0 = 0; c0 < nvox; c0 += T) {
+    const int c = c0 + tid;
+    const bool valid = c < nvox && vflag[c];
     int total;
     const int pos = ncells + block_excl_scan(valid ? 1 : 0, s_warp, &total);
     if (valid && pos < p.pool.max_cells) {
-      p.pool.mean[cbase + pos] = make_double2(ux, uy);
-      p.pool.normal[cbase + pos] = make_double2(nx_, ny_);
-      p.pool.cov[cbase + pos] = make_double4(cxx, cxy_, cyx, cyy);
-      p.pool.planarity[cbase + pos] = scale;
-      p.pool.avg_intensity[cbase + pos] = avgI;
-      p.pool.nsamples[cbase + pos] = N;
-      cxy[pos] = make_float2((float)ux, (float)uy);        // pointnormal.cpp:153-157 (pos <= own centroid index)
+      const double2* o = tmp + (size_t)c * 6;
+      const double2 m = o[0], c0v = o[2], c1v = o[3], sa = o[4];
+      p.pool.mean[cbase + pos] = m;
+      p.pool.normal[cbase + pos] = o[1];
+      p.pool.cov[cbase + pos] = make_double4(c0v.x, c0v.y, c1v.x, c1v.y);
+      p.pool.planarity[cbase + pos] = sa.x;
+      p.pool.avg_intensity[cbase + pos] = sa.y;
+      p.pool.nsamples[cbase + pos] = (int)__double_as_longlong(o[5].x);
+      cxy[pos] = make_float2((float)m.x, (float)m.y);      // pointnormal.cpp:153-157 (pos <= c: safe in place)
     }
     ncells += total;
     __syncthreads();

@@ -146,14 +146,16 @@ __device__ __forceinline__ void block_evaluate(double loss_limit, const double2*
     if (lane_id() == 0) part[warp_id() * 10 + i] = v;
   }
   __syncthreads();
+  // cross-warp sum in fixed order: lane i (< nv) of every warp adds the K5_WARPS partials of value i, then the
+  // totals are broadcast inside the warp (every warp computes the same bits)
+  double mine = 0.0;
+  if (lane_id() < nv) {
+#pragma unroll
+    for (int w = 0; w < K5_WARPS; ++w) mine += part[w * 10 + lane_id()];
+  }
   double tot[10];
 #pragma unroll
-  for (int i = 0; i < nv; ++i) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < K5_WARPS; ++w) t += part[w * 10 + i];
-    tot[i] = t;
-  }
+  for (int i = 0; i < nv; ++i) tot[i] = __shfl_sync(FULL, mine, i);
   ev.cost = tot[0];
   if constexpr (JAC) {
 #pragma unroll
@@ -163,23 +165,27 @@ __device__ __forceinline__ void block_evaluate(double loss_limit, const double2*
   }
 }
 
+// Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal per pivot.
 __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3], double y[3]) {
   const double l00 = sqrt(A[0]);
   if (!(l00 > 0.0) || !isfinite(l00)) return false;
-  const double l10 = A[1] / l00, l20 = A[2] / l00;
+  const double r00 = 1.0 / l00;
+  const double l10 = A[1] * r00, l20 = A[2] * r00;
   const double d1 = A[3] - l10 * l10;
   if (!(d1 > 0.0)) return false;
   const double l11 = sqrt(d1);
-  const double l21 = (A[4] - l20 * l10) / l11;
+  const double r11 = 1.0 / l11;
+  const double l21 = (A[4] - l20 * l10) * r11;
   const double d2 = A[5] - l20 * l20 - l21 * l21;
   if (!(d2 > 0.0)) return false;
   const double l22 = sqrt(d2);
-  const double z0 = b[0] / l00;
-  const double z1 = (b[1] - l10 * z0) / l11;
-  const double z2 = (b[2] - l20 * z0 - l21 * z1) / l22;
-  y[2] = z2 / l22;
-  y[1] = (z1 - l21 * y[2]) / l11;
-  y[0] = (z0 - l10 * y[1] - l20 * y[2]) / l00;
+  const double r22 = 1.0 / l22;
+  const double z0 = b[0] * r00;
+  const double z1 = (b[1] - l10 * z0) * r11;
+  const double z2 = (b[2] - l20 * z0 - l21 * z1) * r22;
+  y[2] = z2 * r22;
+  y[1] = (z1 - l21 * y[2]) * r11;
+  y[0] = (z0 - l10 * y[1] - l20 * y[2]) * r00;
   return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
 }
 
