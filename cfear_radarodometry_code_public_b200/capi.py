@@ -45,7 +45,7 @@ STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), (
                         ("final_cost", np.float64), ("score", np.float64)])
 
 # every symbol include/cfear_b200.h declares
-SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_last_error", "cfear_version",
+SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_update_config", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
            "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_dev", "cfear_sync",
@@ -83,6 +83,7 @@ def load():
         lib.cfear_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         lib.cfear_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.cfear_destroy.argtypes = [C.c_void_p]
+        lib.cfear_update_config.argtypes = [C.c_void_p, C.POINTER(Config)]
         lib.cfear_sync.argtypes = [C.c_void_p]
         vp, i32 = C.c_void_p, C.c_int
         lib.cfear_kstrongest.argtypes = [vp, vp, i32, vp, vp]
@@ -164,6 +165,17 @@ class Context:
         self.A, self.R, self.k = self.cfg.azimuths, self.cfg.range_bins, self.cfg.k_strongest
         self.cap_pts = self.A * self.k
         self.max_cells = self.cfg.max_cells if self.cfg.max_cells > 0 else self.cap_pts
+
+    def update_config(self, **kw):
+        for k, v in kw.items():
+            if k == "cost" and isinstance(v, str):
+                v = COST[v]
+            if k == "loss" and isinstance(v, str):
+                v = LOSS[v]
+            if k == "solver_mode" and isinstance(v, str):
+                v = SOLVER[v]
+            setattr(self.cfg, k, v)
+        self._ck(self.lib.cfear_update_config(self.h, C.byref(self.cfg)), "cfear_update_config")
 
     def close(self):
         if getattr(self, "h", None):

@@ -267,6 +267,23 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   return CFEAR_OK;
 }
 
+int cfear_update_config(cfear_ctx* c, const cfear_config* cfg) {
+  if (!c || !cfg) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  const cfear_config& o = c->cfg;
+  if (cfg->device != o.device || cfg->max_batch != o.max_batch || cfg->azimuths != o.azimuths ||
+      cfg->range_bins != o.range_bins || cfg->k_strongest != o.k_strongest || cfg->max_keyframes != o.max_keyframes ||
+      cfg->max_cellsets != o.max_cellsets || cfg->max_cells != o.max_cells) {
+    g_err = "cfear_update_config: structural fields (device, max_batch, azimuths, range_bins, k_strongest, max_*) are fixed at create";
+    return CFEAR_ERR_ARG;
+  }
+  if (!(cfg->radius > 0.f) || !(cfg->downsample_factor > 0.0) || cfg->cost < 0 || cfg->cost > 2 || cfg->loss < 0 || cfg->loss > 5) {
+    g_err = "cfear_update_config: invalid radius / downsample_factor / cost / loss";
+    return CFEAR_ERR_ARG;
+  }
+  c->cfg = *cfg;
+  return CFEAR_OK;
+}
+
 int64_t cfear_launch_count(const cfear_ctx* c) { return c ? c->launches : 0; }
 void* cfear_stream(cfear_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int cfear_sync(cfear_ctx* c) {
@@ -336,7 +353,7 @@ static int launch_peaks(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
   return CFEAR_OK;
 }
 
-static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud) {
+static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud, int off = 0) {
   K3Params p;
   p.mode = mode; p.A = c->cfg.azimuths; p.k = c->cfg.k_strongest;
   p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
@@ -348,6 +365,14 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
   p.nn_cell = 4.0f;
   p.pts_in_smem = c->pts_in_smem; p.g_bufA = c->d_bufA; p.g_bufB = c->d_bufB;
   p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.cell_tmp = c->d_celltmp; p.pool = c->pool;
+  if (off) {   // sub-batch: every per-scan array starts at scan `off` (d_mot / d_slots are passed already offset)
+    const size_t o = (size_t)off;
+    p.rowcloud += o * p.A * p.k; p.rowcnt += o * p.A;
+    if (p.cloud) p.cloud += o * p.cap_pts;
+    p.npts += o; p.status += o; p.cell_tmp += o * p.cap_pts * 6;
+    if (p.g_bufA) { p.g_bufA += o * p.cap_pts; p.g_bufB += o * p.cap_pts; }
+    p.g_hist += o * (p.g_hist_cap + 1);
+  }
   k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());
@@ -355,10 +380,10 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
 }
 
 static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
-                     cfear_reg_stats* d_stats, int32_t* d_assoc) {
+                     cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0) {
   RegParams p;
   p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
-  p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res; p.res_cap = c->res_cap;
+  p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
   p.cost = c->cfg.cost; p.loss = c->cfg.loss; p.weight_opt = c->cfg.weight_opt; p.solver_mode = c->cfg.solver_mode;
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
@@ -642,14 +667,24 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
   CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * (K + 1) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   const bool have_mot = mot != nullptr && c->cfg.compensate;
   if (have_mot) CK(cudaMemcpyAsync(c->d_mot, mot, (size_t)nprob * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  const int chunk = 16;
+  // Sub-batches of `chunk` scans: the copy stream moves sub-batch i+1 host->device while the compute stream
+  // runs K1 -> K3 -> K5 on sub-batch i, so only the last sub-batch's kernels are exposed behind PCIe.
+  const int chunk = 32;
   const int nchunks = (nprob + chunk - 1) / chunk;
   while ((int)c->chunk_ev.size() < nchunks + 1) {
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->chunk_ev.push_back(e);
   }
   RC(begin_timed_step(c));
-  if (c->timing) CK(cudaEventRecord(c->evset[0], c->stream));
+  const int timing = c->timing;
+  if (timing) {   // stages interleave on this path: the whole step is reported under [2], nothing under [0], [1]
+    CK(cudaEventRecord(c->evset[0], c->stream));
+    CK(cudaEventRecord(c->evset[1], c->stream));
+    CK(cudaEventRecord(c->evset[2], c->stream));
+  }
+  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf, c->d_curslots, K, nprob, c->d_slots);
+  c->launches++;
+  CK(cudaGetLastError());
   CK(cudaEventRecord(c->chunk_ev[nchunks], c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nchunks], 0));          // d_polar free (previous work done)
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -657,8 +692,7 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     CK(cudaMemcpyAsync(c->d_polar + b0 * img, polar + b0 * img, nb * img, cudaMemcpyHostToDevice, c->copy_stream));
     CK(cudaEventRecord(c->chunk_ev[ch], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->chunk_ev[ch], 0));
-    // K1 on this chunk (row-indexed outputs are offset by the chunk)
-    K1Params p;
+    K1Params p;                                                              // K1 on this sub-batch
     p.polar = c->d_polar + b0 * img; p.nrows = nb * A; p.A = A; p.R = R;
     p.polar_end = c->d_polar + (size_t)nprob * img;
     p.zmin = (int)(uint8_t)(int)c->cfg.z_min; p.k = c->cfg.k_strongest;
@@ -669,15 +703,10 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     k1_kstrongest<<<(p.nrows + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, c->stream>>>(p);
     c->launches++;
     CK(cudaGetLastError());
+    RC(launch_k3(c, 0, nb, have_mot ? c->d_mot + 3 * (size_t)b0 : nullptr, c->d_curslots + b0, false, b0));
+    RC(launch_k5(c, nb, K + 1, c->d_slots + (size_t)b0 * (K + 1), c->d_poses + (size_t)b0 * (K + 1) * 3,
+                 c->d_cov36 + (size_t)b0 * 36, c->d_stats + b0, nullptr, b0));
   }
-  const int timing = c->timing;
-  if (timing) CK(cudaEventRecord(c->evset[1], c->stream));
-  RC(launch_k3(c, 0, nprob, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
-  if (timing) CK(cudaEventRecord(c->evset[2], c->stream));
-  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf, c->d_curslots, K, nprob, c->d_slots);
-  c->launches++;
-  CK(cudaGetLastError());
-  RC(launch_k5(c, nprob, K + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr));
   if (timing) CK(cudaEventRecord(c->evset[3], c->stream));
   CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * (K + 1) * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

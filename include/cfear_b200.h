@@ -116,6 +116,11 @@ typedef struct cfear_ctx cfear_ctx;
 void cfear_default_config(cfear_config* cfg);
 int  cfear_create(const cfear_config* cfg, cfear_ctx** out);
 void cfear_destroy(cfear_ctx* ctx);
+/* Change the non-structural parameters (filter thresholds, radius, weights, cost/loss, solver limits) of a live
+ * context; device, max_batch, azimuths, range_bins, k_strongest and the max_* capacities must equal the create-time
+ * values.  This is what lets one context serve MapPointNormal(radius, weight_intensity) / n_scan_normal_reg(cost, loss,
+ * ...) objects constructed with different arguments, like the reference. */
+int  cfear_update_config(cfear_ctx* ctx, const cfear_config* cfg);
 const char* cfear_last_error(void);
 const char* cfear_version(void);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */

@@ -1,0 +1,399 @@
+// cfear_b200.hpp -- C++ host mirror of the reference's per-scan API over the C ABI (cfear_b200.h).
+//
+// Same class names, argument meaning and error behaviour as the reference
+// (dan11003/CFEAR_Radarodometry_code_public), minus ROS / PCL / Eigen / Ceres types, which are replaced by
+// the small PODs below.  A maintainer of the reference swaps the bodies of radarDriver::Process,
+// MapPointNormal::MapPointNormal and n_scan_normal_reg::Register for calls into this layer.
+//
+//   radarDriver            include/cfear_radarodometry/radar_driver.h:30-118, src/.../radar_driver.cpp:23-176
+//   cell, MapPointNormal   include/cfear_radarodometry/pointnormal.h:45-199, src/.../pointnormal.cpp:7-297
+//   Registration,
+//   n_scan_normal_reg      include/cfear_radarodometry/registration.h:48-131, n_scan_normal.h:28-81,
+//                          src/.../n_scan_normal.cpp:82-187
+//   OdometryKeyframeFuser  include/cfear_radarodometry/odometrykeyframefuser.h, src/.../odometrykeyframefuser.cpp:62-259,470-494
+//   vectorToAffine3d, Affine3dToVectorXYeZ   registration.cpp:130-144, utils.cpp:115-122
+//
+// Header-only; link with libcfear_b200.so.  Everything computes on the GPU; with no CUDA device the first
+// call throws std::runtime_error (there is no CPU fallback).
+#ifndef CFEAR_B200_HPP_
+#define CFEAR_B200_HPP_
+
+#include <array>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "cfear_b200.h"
+
+namespace CFEAR_Radarodometry {
+
+// ---- minimal stand-ins for the Eigen / PCL / sensor_msgs types on the reference's signatures ------------
+struct Vector2d {
+  double v[2];
+  Vector2d() : v{0, 0} {}
+  Vector2d(double x, double y) : v{x, y} {}
+  double& operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double dot(const Vector2d& o) const { return v[0] * o.v[0] + v[1] * o.v[1]; }
+  double norm() const { return std::sqrt(dot(*this)); }
+};
+struct Matrix2d {
+  double m[4];
+  Matrix2d() : m{0, 0, 0, 0} {}
+  double& operator()(int r, int c) { return m[2 * r + c]; }
+  double operator()(int r, int c) const { return m[2 * r + c]; }
+};
+struct Matrix6d {
+  double m[36];
+  Matrix6d() { for (double& x : m) x = 0; }
+  static Matrix6d Identity() { Matrix6d I; for (int i = 0; i < 6; ++i) I.m[7 * i] = 1; return I; }
+  double& operator()(int r, int c) { return m[6 * r + c]; }
+  double operator()(int r, int c) const { return m[6 * r + c]; }
+};
+// Rigid transform as the 4x4 homogeneous matrix Eigen::Affine3d stores (row-major here).
+struct Affine3d {
+  double m[16];
+  Affine3d() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+  static Affine3d Identity() { return Affine3d(); }
+  double& operator()(int r, int c) { return m[4 * r + c]; }
+  double operator()(int r, int c) const { return m[4 * r + c]; }
+  Affine3d operator*(const Affine3d& o) const {
+    Affine3d r;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += m[4 * i + k] * o.m[4 * k + j];
+        r.m[4 * i + j] = s;
+      }
+    return r;
+  }
+  Affine3d inverse() const {   // rigid inverse
+    Affine3d r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r.m[4 * i + j] = m[4 * j + i];
+    for (int i = 0; i < 3; ++i) r.m[4 * i + 3] = -(r.m[4 * i] * m[3] + r.m[4 * i + 1] * m[7] + r.m[4 * i + 2] * m[11]);
+    return r;
+  }
+};
+// registration.cpp:130-144
+inline Affine3d vectorToAffine3d(const std::vector<double>& vek) {
+  assert(vek.size() == 3);
+  Affine3d T;
+  const double c = std::cos(vek[2]), s = std::sin(vek[2]);
+  T(0, 0) = c; T(0, 1) = -s; T(1, 0) = s; T(1, 1) = c; T(0, 3) = vek[0]; T(1, 3) = vek[1];
+  return T;
+}
+inline Affine3d vectorToAffine3d(double x, double y, double yaw) { return vectorToAffine3d(std::vector<double>{x, y, yaw}); }
+// utils.cpp:115-122: (x, y, eulerAngles(0,1,2)[2]); for a planar pose that angle is atan2(R(1,0), R(1,1)).
+inline void Affine3dToVectorXYeZ(const Affine3d& T, std::vector<double>& par) {
+  if (par.size() != 3) par.resize(3, 0);
+  par[0] = T(0, 3); par[1] = T(1, 3); par[2] = std::atan2(T(1, 0), T(1, 1));
+}
+
+typedef cfear_point PointXYZI;                       // pcl::PointXYZI (x, y, z, intensity)
+struct PointCloud {                                  // pcl::PointCloud<pcl::PointXYZI>
+  std::vector<PointXYZI> points;
+  uint64_t stamp = 0;
+  size_t size() const { return points.size(); }
+  void clear() { points.clear(); }
+  void push_back(const PointXYZI& p) { points.push_back(p); }
+};
+typedef std::shared_ptr<PointCloud> CloudPtr;
+struct PolarImage {                                  // sensor_msgs::Image, 8UC1: rows = azimuths, cols = range bins
+  int rows = 0, cols = 0;
+  const uint8_t* data = nullptr;
+  uint64_t stamp = 0;
+};
+
+typedef enum weight_options { Uniform = 0, Sim_N = 1, Sim_direciton = 2, Sim_scale = 3, Combined_weights = 4 } weightoption;   // registration.h:50
+typedef enum costmetric { P2P, P2L, P2D } cost_metric;                                                                     // registration.h:55
+typedef enum losstype { None, Huber, Cauchy, SoftLOne, Combined, Tukey } loss_type;                                        // registration.h:60
+
+inline cost_metric Str2Cost(const std::string& s) { return s == "P2P" ? P2P : (s == "P2D" ? P2D : P2L); }
+inline loss_type Str2loss(const std::string& s) {
+  return s == "Huber" ? Huber : s == "Cauchy" ? Cauchy : s == "SoftLOne" ? SoftLOne : s == "Combined" ? Combined : s == "Tukey" ? Tukey : None;
+}
+
+// ---- the one device context all mirror objects share (the reference keeps comparable process-wide state:
+// statics in pointnormal.cpp:4-5, types.cpp:74, statistics.cpp:6) ------------------------------------------
+class Backend {
+ public:
+  // Must be called before the first object is built if the defaults (400x3360, k=12, 64 cell-set slots) do not fit.
+  static void Configure(const cfear_config& cfg) {
+    Backend& b = get();
+    std::lock_guard<std::mutex> l(b.mu_);
+    if (b.ctx_) throw std::runtime_error("cfear Backend already created");
+    b.cfg_ = cfg; b.configured_ = true;
+  }
+  static Backend& get() { static Backend b; return b; }
+  cfear_ctx* ctx() {
+    std::lock_guard<std::mutex> l(mu_);
+    if (!ctx_) {
+      if (!configured_) { cfear_default_config(&cfg_); cfg_.max_cellsets = 64; cfg_.max_keyframes = 8; }
+      if (cfear_create(&cfg_, &ctx_) != CFEAR_OK) throw std::runtime_error(std::string("cfear_create: ") + cfear_last_error());
+      for (int s = cfg_.max_cellsets - 1; s >= 0; --s) free_.push_back(s);
+    }
+    return ctx_;
+  }
+  cfear_config& cfg() { ctx(); return cfg_; }
+  void apply() { if (cfear_update_config(ctx(), &cfg_) != CFEAR_OK) throw std::runtime_error(cfear_last_error()); }
+  int acquire_slot() {
+    ctx();
+    std::lock_guard<std::mutex> l(mu_);
+    if (free_.empty()) throw std::runtime_error("cfear Backend: out of cell-set slots (raise cfear_config.max_cellsets)");
+    int s = free_.back(); free_.pop_back(); return s;
+  }
+  void release_slot(int s) { std::lock_guard<std::mutex> l(mu_); free_.push_back(s); }
+  ~Backend() { if (ctx_) cfear_destroy(ctx_); }
+
+ private:
+  Backend() {}
+  std::mutex mu_;
+  cfear_config cfg_;
+  bool configured_ = false;
+  cfear_ctx* ctx_ = nullptr;
+  std::vector<int> free_;
+};
+
+// ---- radarDriver (radar_driver.h:30-118) ---------------------------------------------------------------------
+class radarDriver {
+ public:
+  class Parameters {
+   public:
+    float z_min = 60;
+    float range_res = 0.0438f;
+    int azimuths = 400, k_strongest = 12;
+    float min_distance = 2.5f, max_distance = 200;
+    std::string dataset = "oxford";
+    std::string ToString() {
+      std::ostringstream s;
+      s << "range res, " << range_res << std::endl << "z min, " << z_min << std::endl << "min distance, " << min_distance << std::endl
+        << "max distance, " << max_distance << std::endl << "k strongest, " << k_strongest << std::endl << "dataset, " << dataset << std::endl
+        << "filter type, kstrong" << std::endl;
+      return s.str();
+    }
+  };
+  radarDriver(const Parameters& pars, bool disable_callback = false) : par(pars) {
+    (void)disable_callback;
+    cloud_filtered_ = std::make_shared<PointCloud>();
+    cloud_filtered_peaks_ = std::make_shared<PointCloud>();
+  }
+  // radar_driver.cpp:163-176 -> CallbackOxford :99-111 -> Process :48-73.  Hands out the driver's internal clouds
+  // (aliasing, like the reference).  A NULL image terminates the process (radar_driver.cpp:101-104).
+  void CallbackOffline(const PolarImage& radar_image_polar, CloudPtr& cloud, CloudPtr& cloud_peaks) {
+    if (radar_image_polar.data == nullptr) { std::cerr << "Radar image NULL" << std::endl; std::exit(0); }
+    Backend& b = Backend::get();
+    cfear_config& cfg = b.cfg();
+    if (radar_image_polar.rows != cfg.azimuths || radar_image_polar.cols != cfg.range_bins || par.k_strongest != cfg.k_strongest)
+      throw std::runtime_error("radarDriver: image shape / k_strongest differ from the Backend configuration");
+    cfg.z_min = par.z_min; cfg.range_res = par.range_res; cfg.min_distance = par.min_distance;
+    b.apply();
+    polar_image = radar_image_polar;                                    // cv_polar_image (radar_driver.h:92)
+    const int cap = cfg.azimuths * cfg.k_strongest;
+    cloud_filtered_ = std::make_shared<PointCloud>();
+    cloud_filtered_peaks_ = std::make_shared<PointCloud>();
+    cloud_filtered_->points.resize(cap); cloud_filtered_peaks_->points.resize(cap);
+    int32_t n = 0, np = 0;
+    if (cfear_filter(b.ctx(), radar_image_polar.data, 1, nullptr, nullptr, cloud_filtered_->points.data(), &n,
+                     cloud_filtered_peaks_->points.data(), &np) != CFEAR_OK)
+      throw std::runtime_error(std::string("cfear_filter: ") + cfear_last_error());
+    cloud_filtered_->points.resize(n); cloud_filtered_peaks_->points.resize(np);
+    cloud_filtered_->stamp = cloud_filtered_peaks_->stamp = radar_image_polar.stamp;
+    cloud = cloud_filtered_; cloud_peaks = cloud_filtered_peaks_;
+  }
+  PolarImage polar_image;   // latest radar image (cv_polar_image)
+
+ private:
+  Parameters par;
+  CloudPtr cloud_filtered_, cloud_filtered_peaks_;
+};
+
+// Compensate(cloud, Tmotion, ccw)  utils.cpp:96-113 (in place, like the reference)
+inline void Compensate(PointCloud& cloud, const Affine3d& Tmotion, bool ccw) {
+  std::vector<double> mot;
+  Affine3dToVectorXYeZ(Tmotion, mot);
+  if (cloud.points.empty()) return;
+  if (cfear_compensate(Backend::get().ctx(), cloud.points.data(), (int)cloud.points.size(), mot.data(), ccw ? 1 : 0) != CFEAR_OK)
+    throw std::runtime_error(std::string("cfear_compensate: ") + cfear_last_error());
+}
+
+// ---- cell / MapPointNormal (pointnormal.h:45-199) -------------------------------------------------------------
+class cell {
+ public:
+  double GetPlanarity() { return scale_; }
+  Vector2d u_;
+  Matrix2d cov_;
+  double scale_ = 0;
+  Vector2d snormal_;
+  double avg_intensity_ = 0;
+  size_t Nsamples_ = 0;
+  bool valid_ = true;
+};
+
+class MapPointNormal;
+typedef std::shared_ptr<MapPointNormal> MapNormalPtr;
+
+class MapPointNormal {
+ public:
+  static double& downsample_factor() { static double f = 1; return f; }   // pointnormal.cpp:5
+  // pointnormal.cpp:65-90.  An empty cloud terminates the process like the reference (:72-75).
+  MapPointNormal(const CloudPtr& cld, float radius, const Vector2d& origin = Vector2d(0, 0), const bool weight_intensity = false,
+                 const bool raw = false)
+      : input_(cld), radius_(radius) {
+    if (input_->size() == 0) { std::cout << "error, cloud empty" << std::endl; std::exit(0); }
+    if (origin(0) != 0.0 || origin(1) != 0.0) throw std::runtime_error("MapPointNormal: only origin (0,0) is supported (the only value the reference passes)");
+    Backend& b = Backend::get();
+    slot_ = b.acquire_slot();
+    int32_t nc = 0;
+    if (raw) {                                   // :76-82 identity cell per point
+      std::vector<cfear_cell> cs(input_->size());
+      for (size_t i = 0; i < cs.size(); ++i) {
+        cfear_cell& c = cs[i];
+        c.mean[0] = input_->points[i].x; c.mean[1] = input_->points[i].y; c.normal[0] = 1; c.normal[1] = 0;
+        c.cov[0] = 0.1; c.cov[1] = 0; c.cov[2] = 0; c.cov[3] = 0.1; c.planarity = 1.0; c.avg_intensity = 1.0; c.nsamples = 1; c.pad = 0;
+      }
+      if (cfear_cells_upload(b.ctx(), slot_, cs.data(), (int)cs.size()) != CFEAR_OK) fail("cfear_cells_upload");
+      nc = (int32_t)cs.size();
+    } else {
+      cfear_config& cfg = b.cfg();
+      cfg.radius = radius; cfg.weight_intensity = weight_intensity ? 1 : 0; cfg.downsample_factor = downsample_factor();
+      b.apply();
+      if (cfear_surface_points(b.ctx(), input_->points.data(), (int)input_->size(), slot_, &nc) != CFEAR_OK) fail("cfear_surface_points");
+    }
+    std::vector<cfear_cell> cs(nc > 0 ? nc : 1);
+    if (cfear_cells_download(b.ctx(), slot_, cs.data(), (int)cs.size(), &nc) != CFEAR_OK) fail("cfear_cells_download");
+    cells.resize(nc);
+    for (int i = 0; i < nc; ++i) {
+      cell& c = cells[i];
+      c.u_ = Vector2d(cs[i].mean[0], cs[i].mean[1]); c.snormal_ = Vector2d(cs[i].normal[0], cs[i].normal[1]);
+      for (int k = 0; k < 4; ++k) c.cov_.m[k] = cs[i].cov[k];
+      c.scale_ = cs[i].planarity; c.avg_intensity_ = cs[i].avg_intensity; c.Nsamples_ = (size_t)cs[i].nsamples;
+    }
+  }
+  ~MapPointNormal() { if (slot_ >= 0) Backend::get().release_slot(slot_); }
+  MapPointNormal(const MapPointNormal&) = delete;
+  MapPointNormal& operator=(const MapPointNormal&) = delete;
+
+  std::vector<cell> GetCells() { return cells; }
+  cell& GetCell(const size_t i) { return cells[i]; }
+  Vector2d GetMean2d(const size_t i) { return cells[i].u_; }
+  Matrix2d GetCov2d(const size_t i) { return cells[i].cov_; }
+  Vector2d GetNormal2d(const size_t i) { return cells[i].snormal_; }
+  size_t GetSize() { return cells.size(); }
+  CloudPtr GetScan() { return input_; }
+  // pointnormal.cpp:238-254: 0 or 1 index
+  std::vector<int> GetClosestIdx(const Vector2d& p, double d) {
+    int32_t idx = -1;
+    const double q[2] = {p(0), p(1)};
+    if (cfear_nearest(Backend::get().ctx(), slot_, q, 1, d, &idx) != CFEAR_OK) fail("cfear_nearest");
+    return idx >= 0 ? std::vector<int>{idx} : std::vector<int>();
+  }
+  int slot() const { return slot_; }
+
+ private:
+  static void fail(const char* what) { throw std::runtime_error(std::string(what) + ": " + cfear_last_error()); }
+  std::vector<cell> cells;
+  CloudPtr input_;
+  float radius_;
+  int slot_ = -1;
+};
+
+// ---- Registration / n_scan_normal_reg (registration.h:63-131, n_scan_normal.h:28-81) ----------------------------
+struct SolverSummary {            // the fields of ceres::Solver::Summary the reference reads (n_scan_normal.cpp:123-166)
+  double final_cost = 0;
+  int num_residuals = 0, num_residual_blocks = 0;
+  int num_inner_iterations = 0;   // summed over the outer iterations
+  bool usable = true;
+  bool IsSolutionUsable() const { return usable; }
+};
+
+class Registration {
+ public:
+  virtual ~Registration() {}
+  virtual bool Register(std::vector<MapNormalPtr>& scans, std::vector<Affine3d>& Tsrc, std::vector<Matrix6d>& reg_cov, bool soft_constraints = false) = 0;
+  virtual double getScore() { return score_; }
+  weightoption weight_opt_ = Uniform;
+  size_t itr_ = 0;
+  SolverSummary summary_;
+
+ protected:
+  cost_metric cost_ = P2L;
+  loss_type loss_ = Huber;
+  double loss_limit_ = 0.1;
+  double radius_ = 2.0;           // registration.h:122
+  double score_ = 0;
+};
+
+class n_scan_normal_reg : public Registration {
+ public:
+  n_scan_normal_reg() {}
+  n_scan_normal_reg(const cost_metric& cost, loss_type loss = Huber, double loss_limit = 0.1, const weightoption opt = Uniform) {
+    cost_ = cost; loss_ = loss; loss_limit_ = loss_limit; weight_opt_ = opt;
+  }
+  void SetD2dPar(const double cov_scale, const double regularization) { cov_scale_ = cov_scale; regularization_ = regularization; }
+  void SetParameters(unsigned int max_itr_association, unsigned int max_itr_solver) { max_itr_association_ = max_itr_association; max_itr_solver_ = max_itr_solver; }
+  double getScore() { return score_; }
+  void getScore(double& score, int& num_residuals) { score = score_; num_residuals = summary_.num_residuals; }
+
+  // n_scan_normal.cpp:82-187.  scans.back() is the free block, the others are fixed keyframes
+  // (mode_ is always incremental_last_to_previous).  Tsrc / reg_cov are rewritten like the reference.
+  bool Register(std::vector<MapNormalPtr>& scans, std::vector<Affine3d>& Tsrc, std::vector<Matrix6d>& reg_cov, bool soft_constraints = false) {
+    const size_t n_scans = scans.size();
+    assert(Tsrc.size() == n_scans && reg_cov.size() == n_scans);
+    if (soft_constraints) throw std::runtime_error("n_scan_normal_reg: soft_constraints is not supported (off in every reference preset)");
+    Backend& b = Backend::get();
+    cfear_config& cfg = b.cfg();
+    cfg.cost = cost_ == P2P ? CFEAR_COST_P2P : (cost_ == P2L ? CFEAR_COST_P2L : CFEAR_COST_P2D);
+    cfg.loss = (int)loss_; cfg.loss_limit = loss_limit_; cfg.weight_opt = (int)weight_opt_;
+    cfg.cov_scale = cov_scale_; cfg.regularization = regularization_; cfg.reg_radius = radius_;
+    cfg.max_outer = (int)max_itr_association_; cfg.min_outer = (int)min_itr_; cfg.max_inner = (int)max_itr_solver_;
+    cfg.solver_mode = CFEAR_SOLVER_CERES_LM;
+    b.apply();
+    std::vector<int32_t> slots(n_scans);
+    std::vector<double> poses(3 * n_scans);
+    std::vector<double> par;
+    for (size_t i = 0; i < n_scans; ++i) {
+      assert(scans[i] != nullptr);
+      slots[i] = scans[i]->slot();
+      Affine3dToVectorXYeZ(Tsrc[i], par);                     // :88-92
+      poses[3 * i] = par[0]; poses[3 * i + 1] = par[1]; poses[3 * i + 2] = par[2];
+    }
+    double cov36[36];
+    cfear_reg_stats st;
+    if (cfear_register(b.ctx(), slots.data(), (int)n_scans, poses.data(), cov36, &st) != CFEAR_OK)
+      throw std::runtime_error(std::string("cfear_register: ") + cfear_last_error());
+    itr_ = (size_t)st.outer_iterations;
+    summary_.final_cost = st.final_cost; summary_.num_residuals = st.num_residuals; summary_.num_residual_blocks = st.num_blocks;
+    summary_.num_inner_iterations = st.inner_iterations; summary_.usable = st.usable != 0;
+    // Tsrc[i] = vectorToAffine3d(parameters[i]) happens after every successful solve (:119-121,177-178)
+    if (st.num_residuals > 1 && st.usable)
+      for (size_t i = 0; i < n_scans; ++i) Tsrc[i] = vectorToAffine3d(poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]);
+    const bool reached_cov = st.num_residuals > 1 && st.usable;   // the `if(success)` block at :163
+    if (reached_cov) {
+      score_ = st.score;
+      Matrix6d d; d(0, 0) = 0.01; d(1, 1) = 0.01; d(5, 5) = 0.0001;   // :171-175
+      for (size_t i = 0; i < n_scans; ++i) reg_cov[i] = d;
+      Matrix6d c; for (int i = 0; i < 36; ++i) c.m[i] = cov36[i];
+      if (st.success) reg_cov.back() = c;                              // GetCovariance :392-433
+    }
+    return st.success != 0;
+  }
+
+ private:
+  double cov_scale_ = 1;
+  double regularization_ = 0.01;
+  double max_itr_association_ = 8, min_itr_ = 3;
+  unsigned int max_itr_solver_ = 20;
+};
+
+}  // namespace CFEAR_Radarodometry
+#endif  // CFEAR_B200_HPP_

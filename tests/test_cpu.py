@@ -1,0 +1,241 @@
+"""CPU-side tests (no GPU): the oracle against independent definitions and the committed golden vectors, the C-ABI
+library's exported symbols, host-side argument handling, and the synthetic generator's determinism."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+from cfear_radarodometry_code_public_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- oracle vs independent definitions ----------------------------------------------------------------------
+def _kstrongest_def(img, zmin, k):
+    """the k lexicographically largest (intensity, range) pairs with intensity >= z_min, ascending."""
+    A, R = img.shape
+    idx = np.full((A, k), -1, np.int32); cnt = np.zeros(A, np.int32)
+    for a in range(A):
+        cand = [(int(v), r) for r, v in enumerate(img[a]) if v >= zmin]
+        keep = sorted(cand)[-k:] if cand else []
+        cnt[a] = len(keep)
+        idx[a, :len(keep)] = [r for _, r in keep]
+    return idx, cnt
+
+
+@pytest.mark.parametrize("k,zmin", [(12, 60), (1, 60), (40, 0), (5, 255)])
+def test_oracle_kstrongest_vs_definition(orc, k, zmin):
+    img = helpers.adversarial_image(3)[:64, :600].copy()
+    oi, oc = orc.kstrongest(img, zmin, k)
+    di, dc = _kstrongest_def(img, zmin, k)
+    assert np.array_equal(oc, dc) and np.array_equal(oi, di)
+
+
+def test_oracle_cloud_definition(orc):
+    img = helpers.adversarial_image(3)
+    oi, oc = orc.kstrongest(img, 60, 12)
+    cl = orc.cloud(img, oi, oc)
+    A = img.shape[0]
+    res = float(np.float32(0.0438)); mrb = int(np.ceil(float(np.float32(2.5)) / res))
+    pts = []
+    for a in range(A):
+        th = ((a + 1) / A) * 2.0 * np.pi
+        for j in range(oc[a]):
+            r = int(oi[a, j])
+            if r > mrb:
+                rho = res / 2.0 + res * r
+                pts.append((np.float32(rho * np.cos(th)), np.float32(rho * np.sin(th)), 0.0, float(img[a, r])))
+    ref = np.array(pts, np.float32)
+    assert cl.shape == ref.shape and mrb == 58
+    assert np.array_equal(cl, ref)
+
+
+def test_oracle_cells_vs_numpy_and_ckdtree(orc):
+    from scipy.spatial import cKDTree
+    im, _ = helpers.scan_images(3, 0)
+    cl, sp = helpers.oracle_cells(orc, im[0], radius=3.5)
+    cx, cy, ci, vid, dims = orc.voxel_centroids(cl, 3.5)
+    tree = cKDTree(cl[:, :2].astype(np.float64))
+    nc = 0
+    for c in range(cx.shape[0]):
+        q = np.array([cx[c], cy[c]], np.float32)
+        d2 = ((q[None, :] - cl[:, :2]) ** 2).astype(np.float32)
+        nb = np.nonzero((d2[:, 0] + d2[:, 1]).astype(np.float32) < np.float32(3.5 * 3.5))[0]   # fp32 L2_Simple
+        assert set(nb) == set(i for i in tree.query_ball_point(q.astype(np.float64), 3.5 + 1e-3) if i in set(nb))
+        if nb.size < 6:
+            continue
+        w = np.maximum(cl[nb, 3].astype(np.float64) - 60.0, 0.0)
+        if w.sum() == 0:
+            continue
+        wn = w / w.sum()
+        mu = (wn[:, None] * cl[nb, :2]).sum(0)
+        xc = cl[nb, :2] - mu
+        cov = xc.T @ (wn[:, None] * xc)
+        lam, vec = np.linalg.eigh(cov)
+        cond = abs(lam[1] / lam[0])
+        if not (cond <= 1e4 and lam[0] * lam[1] > 1e-5 and lam[0] > 0 and lam[1] > 0):
+            continue
+        assert sp["nsamples"][nc] == nb.size
+        np.testing.assert_allclose(sp["mean"][nc], mu, atol=1e-10)
+        np.testing.assert_allclose(sp["cov"][nc], cov, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(sp["lambdas"][nc], lam, rtol=1e-8)
+        n = vec[:, 0] if vec[:, 0] @ (-mu) >= 0 else -vec[:, 0]
+        np.testing.assert_allclose(sp["normal"][nc], n, atol=1e-7)
+        np.testing.assert_allclose(sp["planarity"][nc], np.log(1 + cond / 2), rtol=1e-8)
+        nc += 1
+    assert nc == sp["mean"].shape[0] > 100
+
+
+def test_oracle_nearest_vs_ckdtree(orc):
+    from scipy.spatial import cKDTree
+    rng = np.random.Generator(np.random.PCG64(2))
+    means = rng.uniform(-100, 100, (700, 2))
+    q = rng.uniform(-110, 110, (3000, 2))
+    got = orc.nearest(means, q, 2.0)
+    m32 = means.astype(np.float32).astype(np.float64); q32 = q.astype(np.float32).astype(np.float64)
+    d, i = cKDTree(m32).query(q32, k=1)
+    exp = np.where(d * d < 4.0 - 1e-4, i, -1)
+    sure = np.abs(d * d - 4.0) > 1e-4                      # away from the fp32 acceptance boundary
+    assert np.array_equal(got[sure], exp[sure])
+
+
+def _residuals(rng, n, cost):
+    res = np.zeros((n, 8))
+    res[:, 0:2] = rng.uniform(-50, 50, (n, 2)); res[:, 2:4] = res[:, 0:2] + rng.normal(0, 0.3, (n, 2))
+    th = rng.uniform(0, 2 * np.pi, n)
+    if cost == "P2L":
+        res[:, 4], res[:, 5] = np.cos(th), np.sin(th)
+    elif cost == "P2D":
+        res[:, 4] = rng.uniform(0.5, 3, n); res[:, 5] = rng.normal(0, 0.5, n); res[:, 6] = rng.uniform(0.5, 3, n)
+    res[:, 7] = rng.uniform(0.5, 3, n)
+    return res
+
+
+@pytest.mark.parametrize("cost", ["P2L", "P2D", "P2P"])
+@pytest.mark.parametrize("loss", ["None", "Huber", "Cauchy", "SoftLOne", "Combined", "Tukey"])
+def test_oracle_cost_gradient_and_gauss_newton(orc, cost, loss):
+    """J^T r and J^T J of the oracle against numerical differentiation of an independent numpy cost."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    res = _residuals(rng, 200, cost)
+    cfg = orc.reg_cfg(cost=cost, loss=loss, loss_limit=0.1)
+    a = 0.1
+
+    def rho(s):
+        if loss == "None":
+            return s
+        if loss == "Huber":
+            return np.where(s > a * a, 2 * a * np.sqrt(s) - a * a, s)
+        if loss == "Cauchy":
+            return a * a * np.log1p(s / (a * a))
+        if loss == "SoftLOne":
+            return 2 * a * a * (np.sqrt(1 + s / (a * a)) - 1)
+        if loss == "Combined":
+            g = np.log1p(s)
+            return np.where(g > 1, 2 * np.sqrt(g) - 1, g)
+        return np.where(s <= a * a, a * a / 3 * (1 - (1 - s / (a * a)) ** 3), a * a / 3)
+
+    def cost_np(x):
+        c, s_ = np.cos(x[2]), np.sin(x[2])
+        ex = c * res[:, 0] - s_ * res[:, 1] + x[0] - res[:, 2]
+        ey = s_ * res[:, 0] + c * res[:, 1] + x[1] - res[:, 3]
+        if cost == "P2L":
+            s = (ex * res[:, 4] + ey * res[:, 5]) ** 2
+        elif cost == "P2D":
+            s = (res[:, 4] * ex) ** 2 + (res[:, 5] * ex + res[:, 6] * ey) ** 2
+        else:
+            s = ex ** 2 + ey ** 2
+        return 0.5 * (res[:, 7] * rho(s)).sum()
+
+    x = np.array([0.05, -0.02, 0.01])
+    c, H, g = orc.eval_cost(cfg, res, x)
+    np.testing.assert_allclose(c, cost_np(x), rtol=1e-12)
+    num = np.array([(cost_np(x + h) - cost_np(x - h)) / 2e-6 for h in np.eye(3) * 1e-6])
+    np.testing.assert_allclose(g, num, rtol=2e-4, atol=1e-6)
+
+
+def test_oracle_lm_reaches_scipy_optimum(orc):
+    """The restated Ceres loop must land on the same Huber optimum as scipy.optimize.least_squares."""
+    from scipy.optimize import least_squares
+    im, tp = helpers.scan_images(3, 1)
+    sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(2)]
+    P = tp[:2].copy(); P[1] = tp[1] + [0.15, -0.1, 0.01]
+    cfg = orc.reg_cfg(cost="P2L", loss="Huber", max_outer=1, max_inner=50)
+    ok, op, _, st, assoc = orc.register(sets, P, cfg, want_assoc=True)
+    assert ok
+    j = np.nonzero(assoc[0] >= 0)[0]; m = assoc[0][j]
+    p = sets[1]["mean"][j]; q = sets[0]["mean"][m]; n = sets[0]["normal"][m]
+
+    def fun(x):
+        c, s = np.cos(x[2]), np.sin(x[2])
+        ex = c * p[:, 0] - s * p[:, 1] + x[0] - q[:, 0]; ey = s * p[:, 0] + c * p[:, 1] + x[1] - q[:, 1]
+        return ex * n[:, 0] + ey * n[:, 1]
+    sol = least_squares(fun, P[1], loss="huber", f_scale=0.1, xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    assert np.hypot(*(op[1, :2] - sol.x[:2])) < 2e-4 and abs(op[1, 2] - sol.x[2]) < 2e-5
+
+
+# ---- golden vectors ------------------------------------------------------------------------------------------
+def test_golden_vectors(orc):
+    g = np.load(os.path.join(GOLD, "cfear_golden_v1.npz"))
+    img = synth.make_problem_images(int(g["seed"]), 1)[0]
+    assert np.array_equal(img[1, ::8, ::8], g["img_sub"])                      # generator is reproducible
+    idx, cnt = orc.kstrongest(img[1], 60, 12)
+    assert np.array_equal(idx, g["kidx"]) and np.array_equal(cnt, g["kcnt"])
+    cl = orc.cloud(img[1], idx, cnt)
+    assert np.array_equal(cl, g["cloud"])
+    sp = orc.surface_points(cl, 3.5, True)
+    assert np.array_equal(sp["nsamples"], g["nsamples"])
+    np.testing.assert_allclose(sp["mean"], g["mean"], atol=1e-12)
+    np.testing.assert_allclose(sp["normal"], g["normal"], atol=1e-10)
+    sp0 = helpers.oracle_cells(orc, img[0])[1]
+    ok, op, cov, st, _ = orc.register([sp0, sp], g["poses_in"], orc.reg_cfg(cost="P2L"))
+    assert ok and st.outer_iterations == int(g["outer"]) and st.inner_iterations == int(g["inner"])
+    np.testing.assert_allclose(op, g["poses_out"], atol=1e-9)
+
+
+# ---- boundary: header <-> library <-> binding -------------------------------------------------------------------
+def test_capi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cfear_b200.h")).read()
+    declared = set(re.findall(r"\b(cfear_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+def test_config_struct_layout_matches_header():
+    cfg = capi.default_config()
+    assert (cfg.azimuths, cfg.range_bins, cfg.k_strongest) == (400, 3360, 12)
+    assert abs(cfg.z_min - 60) < 1e-6 and abs(cfg.range_res - 0.0438) < 1e-6 and abs(cfg.radius - 3.5) < 1e-6
+    assert (cfg.cost, cfg.loss, cfg.max_outer, cfg.min_outer, cfg.max_inner) == (1, 1, 8, 3, 20)
+    assert cfg.reg_radius == 2.0 and cfg.loss_limit == 0.1 and cfg.regularization == 1.0
+    assert ctypes.sizeof(capi.RegStats) == capi.STATS_DTYPE.itemsize == 40
+    assert capi.CELL_DTYPE.itemsize == 88
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.CfearError, match="no CUDA device|CUDA"):
+        capi.Context()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+                assert "cfear_oracle" not in src and "orc_" not in src, f
+
+
+def test_synth_is_seeded():
+    a = synth.make_problem_images(11, 1)
+    b = synth.make_problem_images(11, 1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].shape == (2, 400, 3360) and a[0].dtype == np.uint8

@@ -1,0 +1,57 @@
+"""The C++ host mirror (include/cfear_b200.hpp: radarDriver / MapPointNormal / n_scan_normal_reg over the C ABI)
+driven like offline_odometry drives the reference classes, checked against the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from cfear_radarodometry_code_public_b200.synth import se2_inv, se2_mul
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cpp") / "mirror_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "mirror_test.cpp"), "-o", out, "-L" + PKG, "-lcfear_b200",
+                           "-Wl,-rpath," + PKG])
+    return out
+
+
+@pytest.mark.parametrize("cost,loss,wopt,K", [("P2L", "Huber", 0, 1), ("P2D", "Huber", 4, 4), ("P2P", "Cauchy", 4, 3)])
+def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K):
+    im, tp = helpers.scan_images(31, K)
+    radius, reg = 3.5, 0.1
+    P = tp.copy(); P[K] = tp[K - 1]
+    mot = se2_mul(se2_inv(tp[K - 2]), tp[K - 1]) if K >= 2 else np.array([2.5, 0.0, 0.02])
+    ci, li = orc.COST[cost], orc.LOSS[loss]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<iiifiiid", K + 1, im.shape[1], im.shape[2], radius, ci, li, wopt, reg))
+        f.write(im[:K + 1].tobytes()); f.write(P.astype(np.float64).tobytes()); f.write(mot.astype(np.float64).tobytes())
+    subprocess.check_call([exe, fin, fout])
+    raw = open(fout, "rb").read()
+    ok, itr, nres, ncells, npts = struct.unpack_from("<5i", raw, 0)
+    pose = np.frombuffer(raw, np.float64, 3, 20)
+    score = np.frombuffer(raw, np.float64, 1, 44)[0]
+    cov = np.frombuffer(raw, np.float64, 36, 52).reshape(6, 6)
+    near = struct.unpack_from("<i", raw, 52 + 288)[0]
+    # oracle, same call sequence
+    sets = []
+    for i in range(K + 1):
+        cl, s = helpers.oracle_cells(orc, im[i], radius=radius, mot=(mot if i == K else None))
+        sets.append(s)
+    o_ok, op, ocov, ost, _ = orc.register(sets, P, orc.reg_cfg(cost=cost, loss=loss, weight_opt=wopt, regularization=reg))
+    assert bool(ok) == o_ok and itr == ost.outer_iterations and nres == ost.num_residuals
+    assert ncells == sets[-1]["mean"].shape[0] and npts == cl.shape[0]
+    d = pose - op[K]
+    assert np.hypot(d[0], d[1]) < 1e-4 and abs(d[2]) < 1e-5
+    np.testing.assert_allclose(score, ost.score, rtol=1e-6)
+    np.testing.assert_allclose(cov, ocov, rtol=1e-5, atol=1e-12)
+    assert near == orc.nearest(sets[-1]["mean"], np.array([[10.0, 0.0]]), 50.0)[0]
