@@ -232,7 +232,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   AL(c->d_npts, B); AL(c->d_npeaks, B); AL(c->d_status, B);
   if (!c->pts_in_smem) { AL(c->d_bufA, (size_t)B * c->cap_pts); AL(c->d_bufB, (size_t)B * c->cap_pts); }
   AL(c->d_ghist, (size_t)B * (c->g_hist_cap + 1));
-  AL(c->d_celltmp, (size_t)B * c->cap_pts * 6);
+  AL(c->d_celltmp, (size_t)B * c->cap_pts * 4);
   AL(c->d_mot, (size_t)B * 3);
   const int ns = cfg->max_keyframes + 1;
   AL(c->d_slots, (size_t)B * ns); AL(c->d_curslots, B); AL(c->d_kfslots, (size_t)B * ns);
@@ -362,14 +362,14 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
   p.slots = d_slots; p.radius = c->cfg.radius;
   p.leaf = (float)((double)c->cfg.radius / c->cfg.downsample_factor);        // pointnormal.cpp:279
   p.weight_intensity = c->cfg.weight_intensity; p.origin_x = 0.0; p.origin_y = 0.0;   // odometrykeyframefuser.cpp:161
-  p.nn_cell = 4.0f;
+  p.nn_cell = 8.0f;
   p.pts_in_smem = c->pts_in_smem; p.g_bufA = c->d_bufA; p.g_bufB = c->d_bufB;
   p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.cell_tmp = c->d_celltmp; p.pool = c->pool;
   if (off) {   // sub-batch: every per-scan array starts at scan `off` (d_mot / d_slots are passed already offset)
     const size_t o = (size_t)off;
     p.rowcloud += o * p.A * p.k; p.rowcnt += o * p.A;
     if (p.cloud) p.cloud += o * p.cap_pts;
-    p.npts += o; p.status += o; p.cell_tmp += o * p.cap_pts * 6;
+    p.npts += o; p.status += o; p.cell_tmp += o * p.cap_pts * 4;
     if (p.g_bufA) { p.g_bufA += o * p.cap_pts; p.g_bufB += o * p.cap_pts; }
     p.g_hist += o * (p.g_hist_cap + 1);
   }
@@ -553,7 +553,7 @@ int cfear_cells_upload(cfear_ctx* c, int slot, const cfear_cell* cells, int n) {
   CK(cudaGetLastError());
   const int32_t s32 = slot;
   CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = 4.0f;
+  K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = 8.0f;
   k4_build_index<<<1, K3_THREADS, (K3_HIST_CAP + 1) * sizeof(int), c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());

@@ -47,7 +47,7 @@ struct K3Params {
   float4* g_bufA; float4* g_bufB;   // [nscans][cap_pts] global fallback
   int* g_hist; int g_hist_cap;      // [nscans][g_hist_cap+1] global fallback for large grids
   int32_t* status;             // [nscans] 0 ok, 1 voxel grid over capacity
-  double2* cell_tmp;           // [nscans][cap_pts][6] uncompacted cells (scratch)
+  double2* cell_tmp;           // [nscans][cap_pts][4] per-centroid raw moments (scratch)
   CellPool pool;
 };
 
@@ -362,8 +362,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   const unsigned gmask = 0xffu << (lane_id() & 24);
   const int gleader = lane_id() & 24;
   const bool wint = p.weight_intensity != 0;
-  unsigned char* vflag = reinterpret_cast<unsigned char*>(vlist + cap);     // [cap] validity per centroid
-  double2* tmp = p.cell_tmp + (size_t)scan * cap * 6;                        // [cap][6] double2
+  double2* tmp = p.cell_tmp + (size_t)scan * cap * 4;                        // [cap][4] double2: raw moments
   if (tid == 0) s_misc[1] = 0;
   __syncthreads();
   for (;;) {
@@ -399,46 +398,49 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
       S0 += __shfl_xor_sync(gmask, S0, d); S1x += __shfl_xor_sync(gmask, S1x, d); S1y += __shfl_xor_sync(gmask, S1y, d);
       Sxx += __shfl_xor_sync(gmask, Sxx, d); Sxy += __shfl_xor_sync(gmask, Sxy, d); Syy += __shfl_xor_sync(gmask, Syy, d);
     }
-    if (sl == 0) {
-      bool valid = false;
-      if (gN >= 6) {                                        // pointnormal.cpp:291
-        const double mdx = S1x / S0, mdy = S1y / S0;        // weighted mean relative to q
-        const double ux = (double)q.x + mdx, uy = (double)q.y + mdy;
-        const double cxx = Sxx / S0 - mdx * mdx, cxy_ = Sxy / S0 - mdx * mdy, cyy = Syy / S0 - mdy * mdy;
-        const Eig2 eg = eig2_sym(cxx, cxy_, cyy);           // ComputeNormal (:37-63)
-        const double cond = fabs(eg.lmax / eg.lmin);
-        const double det = eg.lmax * eg.lmin;
-        valid = (cond <= 10000) && (det > 0.00001) && eg.lmin > 0 && eg.lmax > 0;
-        if (valid) {
-          double nx_ = eg.nx, ny_ = eg.ny;
-          if (nx_ * (p.origin_x - ux) + ny_ * (p.origin_y - uy) < 0) { nx_ = -nx_; ny_ = -ny_; }
-          double2* o = tmp + (size_t)c * 6;
-          o[0] = make_double2(ux, uy); o[1] = make_double2(nx_, ny_);
-          o[2] = make_double2(cxx, cxy_); o[3] = make_double2(cxy_, cyy);
-          o[4] = make_double2(log(1.0 + cond / 2), S0 / (double)gN);              // scale_, avg_intensity_
-          o[5] = make_double2(__longlong_as_double((long long)gN), 0.0);
-        }
-      }
-      vflag[c] = valid ? 1 : 0;
+    if (sl == 0) {                                          // raw moments; finalised one centroid per thread below
+      double2* o = tmp + (size_t)c * 4;
+      o[0] = make_double2(S0, S1x); o[1] = make_double2(S1y, Sxx); o[2] = make_double2(Sxy, Syy);
+      o[3] = make_double2(__longlong_as_double((long long)gN), 0.0);
     }
   }
   __syncthreads();
   int ncells = 0;                                          // block-uniform running count
   for (int c0 = 0; c0 < nvox; c0 += T) {
     const int c = c0 + tid;
-    const bool valid = c < nvox && vflag[c];
+    bool valid = false;
+    double ux = 0, uy = 0, nx_ = 0, ny_ = 0, cxx = 0, cxy_ = 0, cyy = 0, scale = 0, avgI = 0;
+    int gN = 0;
+    if (c < nvox) {
+      const double2* o = tmp + (size_t)c * 4;
+      const double2 m0 = o[0], m1 = o[1], m2 = o[2];
+      gN = (int)__double_as_longlong(o[3].x);
+      if (gN >= 6) {                                        // pointnormal.cpp:291
+        const float2 q = cxy[c];
+        const double S0 = m0.x;
+        const double mdx = m0.y / S0, mdy = m1.x / S0;      // weighted mean relative to q
+        ux = (double)q.x + mdx; uy = (double)q.y + mdy;
+        cxx = m1.y / S0 - mdx * mdx; cxy_ = m2.x / S0 - mdx * mdy; cyy = m2.y / S0 - mdy * mdy;
+        const Eig2 eg = eig2_sym(cxx, cxy_, cyy);           // ComputeNormal (:37-63)
+        const double cond = fabs(eg.lmax / eg.lmin);
+        const double det = eg.lmax * eg.lmin;
+        valid = (cond <= 10000) && (det > 0.00001) && eg.lmin > 0 && eg.lmax > 0;
+        nx_ = eg.nx; ny_ = eg.ny;
+        if (nx_ * (p.origin_x - ux) + ny_ * (p.origin_y - uy) < 0) { nx_ = -nx_; ny_ = -ny_; }
+        scale = log(1.0 + cond / 2);                        // scale_
+        avgI = S0 / (double)gN;                             // avg_intensity_
+      }
+    }
     int total;
-    const int pos = ncells + block_excl_scan(valid ? 1 : 0, s_warp, &total);
+    const int pos = ncells + block_excl_scan(valid ? 1 : 0, s_warp, &total);   // (the scan's barrier orders the cxy reads above before the writes below)
     if (valid && pos < p.pool.max_cells) {
-      const double2* o = tmp + (size_t)c * 6;
-      const double2 m = o[0], c0v = o[2], c1v = o[3], sa = o[4];
-      p.pool.mean[cbase + pos] = m;
-      p.pool.normal[cbase + pos] = o[1];
-      p.pool.cov[cbase + pos] = make_double4(c0v.x, c0v.y, c1v.x, c1v.y);
-      p.pool.planarity[cbase + pos] = sa.x;
-      p.pool.avg_intensity[cbase + pos] = sa.y;
-      p.pool.nsamples[cbase + pos] = (int)__double_as_longlong(o[5].x);
-      cxy[pos] = make_float2((float)m.x, (float)m.y);      // pointnormal.cpp:153-157 (pos <= c: safe in place)
+      p.pool.mean[cbase + pos] = make_double2(ux, uy);
+      p.pool.normal[cbase + pos] = make_double2(nx_, ny_);
+      p.pool.cov[cbase + pos] = make_double4(cxx, cxy_, cxy_, cyy);
+      p.pool.planarity[cbase + pos] = scale;
+      p.pool.avg_intensity[cbase + pos] = avgI;
+      p.pool.nsamples[cbase + pos] = gN;
+      cxy[pos] = make_float2((float)ux, (float)uy);        // pointnormal.cpp:153-157 (pos <= c: safe in place)
     }
     ncells += total;
     __syncthreads();

@@ -76,6 +76,28 @@ __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
 
 struct EvalOut { double cost, H[6], g[3]; };
 
+// Residual list of one problem, SoA of double2 fields (p), (q), (a,b), (c,w): the first cap_s entries live in
+// shared memory, the overflow in the problem's global scratch.
+struct ResList {
+  double2* s; int cap_s;       // shared part: field f at s + f*cap_s
+  double2* g; int cap_g;       // global part: field f at g + f*cap_g (indexed by the residual's global position)
+  __device__ __forceinline__ double2 ld(int f, int r) const { return r < cap_s ? s[f * cap_s + r] : g[(size_t)f * cap_g + r]; }
+  __device__ __forceinline__ void st(int f, int r, double2 v) const { if (r < cap_s) s[f * cap_s + r] = v; else g[(size_t)f * cap_g + r] = v; }
+};
+#ifdef CFEAR_K5_PROFILE
+__device__ long long g_prof_dummy;
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(acc, a, b) (acc) += (b) - (a)
+#define PROF_ARG , prof
+#define PROF_PARAM , long long* prof
+#else
+#define PROF_ARG
+#define PROF_PARAM
+#define PROF_T(v)
+#define PROF_ADD(acc, a, b)
+#endif
+
+
 // One residual block's contribution at x (cs = cos psi, sn = sin psi): cost and (optionally) normal equations.
 // Residuals / Jacobians: n_scan_normal.h:180-255, 330-361; loss: ScaledLoss(w) around the base loss with
 // Ceres' corrector in its rho'' <= 0 form (rows scaled by sqrt(w rho')).
@@ -120,23 +142,28 @@ __device__ __forceinline__ void accumulate(double loss_limit, double cs, double 
 // is consumed (the list lives in L2).  s_part: [2][K5_WARPS][10]; parity toggles per call -> one
 // __syncthreads per evaluation.  Deterministic: fixed per-thread order, xor-butterfly, fixed cross-warp order.
 template <int COST, int LOSS, bool JAC>
-__device__ __forceinline__ void block_evaluate(double loss_limit, const double2* __restrict__ res, int res_cap,
-                                               int nres, const double x[3], EvalOut& ev, double* s_part, int& parity) {
+__device__ __forceinline__ void block_evaluate(double loss_limit, const ResList& res,
+                                               int nres, const double x[3], EvalOut& ev, double* s_part, int& parity
+#ifdef CFEAR_K5_PROFILE
+                                               , long long* prof
+#endif
+                                               ) {
+  PROF_T(t0);
   double cs, sn; sincos(x[2], &sn, &cs);
+  PROF_T(t1);
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
-  const double2* f0 = res; const double2* f1 = res + res_cap; const double2* f2 = res + 2 * (size_t)res_cap;
-  const double2* f3 = res + 3 * (size_t)res_cap;
   int r = threadIdx.x;
   for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
     const int r2 = r + K5_THREADS;
-    const double2 p0 = f0[r], q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
-    const double2 p1 = f0[r2], q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
+    const double2 p0 = res.ld(0, r), q0 = res.ld(1, r), ab0 = res.ld(2, r), cw0 = res.ld(3, r);
+    const double2 p1 = res.ld(0, r2), q1 = res.ld(1, r2), ab1 = res.ld(2, r2), cw1 = res.ld(3, r2);
     accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
     accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
   }
-  if (r < nres) accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, f0[r], f1[r], f2[r], f3[r], acc);
+  if (r < nres) accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
+  PROF_T(t2);
   constexpr int nv = JAC ? 10 : 1;
   double* part = s_part + parity * (K5_WARPS * 10);
   parity ^= 1;
@@ -156,6 +183,10 @@ __device__ __forceinline__ void block_evaluate(double loss_limit, const double2*
   double tot[10];
 #pragma unroll
   for (int i = 0; i < nv; ++i) tot[i] = __shfl_sync(FULL, mine, i);
+  PROF_T(t3);
+#ifdef CFEAR_K5_PROFILE
+  PROF_ADD(prof[0], t0, t1); PROF_ADD(prof[1], t1, t2); PROF_ADD(prof[2], t2, t3); prof[3] += 1;
+#endif
   ev.cost = tot[0];
   if constexpr (JAC) {
 #pragma unroll
@@ -165,21 +196,18 @@ __device__ __forceinline__ void block_evaluate(double loss_limit, const double2*
   }
 }
 
-// Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal per pivot.
+// Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal square root per pivot.
 __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3], double y[3]) {
-  const double l00 = sqrt(A[0]);
-  if (!(l00 > 0.0) || !isfinite(l00)) return false;
-  const double r00 = 1.0 / l00;
+  if (!(A[0] > 0.0) || !isfinite(A[0])) return false;
+  const double r00 = rsqrt(A[0]);
   const double l10 = A[1] * r00, l20 = A[2] * r00;
   const double d1 = A[3] - l10 * l10;
   if (!(d1 > 0.0)) return false;
-  const double l11 = sqrt(d1);
-  const double r11 = 1.0 / l11;
+  const double r11 = rsqrt(d1);
   const double l21 = (A[4] - l20 * l10) * r11;
   const double d2 = A[5] - l20 * l20 - l21 * l21;
   if (!(d2 > 0.0)) return false;
-  const double l22 = sqrt(d2);
-  const double r22 = 1.0 / l22;
+  const double r22 = rsqrt(d2);
   const double z0 = b[0] * r00;
   const double z1 = (b[1] - l10 * z0) * r11;
   const double z2 = (b[2] - l20 * z0 - l21 * z1) * r22;
@@ -195,8 +223,8 @@ struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usa
 // block-uniform control flow.  The candidate point is evaluated with its Jacobian in the same pass, so an
 // accepted step needs no second pass over the residuals (the sums are the ones a re-evaluation would give).
 template <int COST, int LOSS>
-__device__ __forceinline__ void lm_solve(const RegParams& P, const double2* res, int nres, double x[3], SolveSum& sum,
-                                         double* s_part, int& parity) {
+__device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
+                                         double* s_part, int& parity PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -206,7 +234,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double2* res,
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
   EvalOut ev;
-  block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
+  block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -227,7 +255,8 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double2* res,
       diag[1] = fmin(fmax(Hs[3], kMinDiag), kMaxDiag);
       diag[2] = fmin(fmax(Hs[5], kMinDiag), kMaxDiag);
     }
-    const double A[6] = {Hs[0] + diag[0] / radius, Hs[1], Hs[2], Hs[3] + diag[1] / radius, Hs[4], Hs[5] + diag[2] / radius};
+    const double inv_radius = 1.0 / radius;
+    const double A[6] = {Hs[0] + diag[0] * inv_radius, Hs[1], Hs[2], Hs[3] + diag[1] * inv_radius, Hs[4], Hs[5] + diag[2] * inv_radius};
     double y[3];
     const double nb[3] = {-gs[0], -gs[1], -gs[2]};
     const bool ok = chol3_solve(A, nb, y);
@@ -252,7 +281,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const double2* res,
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     EvalOut evc;
-    block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, xc, evc, s_part, parity);
+    block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, xc, evc, s_part, parity PROF_ARG);
     const double cand_cost = evc.cost;
     const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
@@ -314,7 +343,7 @@ __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmi
 template <int COST>
 __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
                                              const NNGrid* s_grid, const GridView* s_view, const double x[3], int itr,
-                                             double2* res, int32_t* assoc, int* s_warp) {
+                                             const ResList& res, int32_t* assoc, int* s_warp PROF_PARAM) {
   const int ns = P.nscans, K = ns - 1;
   const int src_slot = slots[K];
   const int n_src = P.pool.ncells[src_slot];
@@ -323,12 +352,16 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
   const double angle_outlier = cos(M_PI / 6.0);
   const double curr_radius = (itr == 1) ? 2 * P.radius : P.radius;       // n_scan_normal.cpp:222
   const int npairs = K * n_src;
-  const int cap = P.res_cap;
+  const int cap = res.cap_g;
   int nres = 0;
   for (int t0 = 0; t0 < npairs; t0 += blockDim.x) {
     const int t = t0 + threadIdx.x;
     bool valid = false;
     double2 rp = make_double2(0, 0), rq = rp, rab = rp, rcw = rp;
+    PROF_T(tq0);
+#ifdef CFEAR_K5_PROFILE
+    long long tq1 = tq0;
+#endif
     if (t < npairs) {
       const int i = t / n_src, j = t - i * n_src;
       const double* pt = s_pose + 5 * i;
@@ -341,30 +374,35 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
       const double qx = rc * mu.x - rs * mu.y + tx, qy = rs * mu.x + rc * mu.y + ty;   // :240
       const int tslot = slots[i];
       const int m = nn_query(s_view[i], s_grid[i], qx, qy, curr_radius);              // :241
+#ifdef CFEAR_K5_PROFILE
+      tq1 = clock64();
+#endif
       if (m >= 0) {
+        // everything the residual may need from the target cell is requested at once (one L2 round trip),
+        // before the normal gate decides whether it is used
         const size_t tb = (size_t)tslot * P.pool.max_cells + m;
         const double2 ntar = P.pool.normal[tb];
+        const double2 tm = P.pool.mean[tb];
+        double4 C = make_double4(0, 0, 0, 0);
+        if constexpr (COST == 2) C = P.pool.cov[tb];
+        double n1 = 0, n2 = 0, p1 = 0, p2 = 0;
+        if (P.weight_opt == 1 || P.weight_opt == 4) { n1 = (double)P.pool.nsamples[sbase + j]; n2 = (double)P.pool.nsamples[tb]; }
+        if (P.weight_opt == 3 || P.weight_opt == 4) { p1 = P.pool.planarity[sbase + j]; p2 = P.pool.planarity[tb]; }
         const double ntx = rc * nsrc.x - rs * nsrc.y, nty = rs * nsrc.x + rc * nsrc.y;  // :244
         const double sim = fmax(ntx * ntar.x + nty * ntar.y, 0.0);                      // :246
         if (sim > angle_outlier) {                                                      // :247
           valid = true;
           double w = 1.0;                                                              // registration.cpp:67-76
-          if (P.weight_opt != 0) {
-            const double n1 = (double)P.pool.nsamples[sbase + j], n2 = (double)P.pool.nsamples[tb];
-            const double p1 = P.pool.planarity[sbase + j], p2 = P.pool.planarity[tb];
-            if (P.weight_opt == 1) w = sim_ratio(n1, n2);
-            else if (P.weight_opt == 2) w = sim;
-            else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
-            else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
-          }
+          if (P.weight_opt == 1) w = sim_ratio(n1, n2);
+          else if (P.weight_opt == 2) w = sim;
+          else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
+          else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
           rp = mu;
-          const double2 tm = P.pool.mean[tb];
           rq = make_double2(ct * tm.x - st * tm.y + pt[0], st * tm.x + ct * tm.y + pt[1]);
           rcw.y = w;
           if constexpr (COST == 1) {                                                   // :279-289
             rab = make_double2(ct * ntar.x - st * ntar.y, st * ntar.x + ct * ntar.y);
           } else if constexpr (COST == 2) {                                            // :290-300
-            const double4 C = P.pool.cov[tb];
             const double a00 = ct * C.x - st * C.z, a01 = ct * C.y - st * C.w;
             const double a10 = st * C.x + ct * C.z, a11 = st * C.y + ct * C.w;
             double s00 = a00 * ct - a01 * st, s01 = a00 * st + a01 * ct;
@@ -382,11 +420,14 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* 
       }
       if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
     }
+    PROF_T(tq2);
     int total;
     const int pos = nres + block_excl_scan(valid ? 1 : 0, s_warp, &total);
-    if (valid && pos < cap) {
-      res[pos] = rp; res[cap + pos] = rq; res[2 * (size_t)cap + pos] = rab; res[3 * (size_t)cap + pos] = rcw;
-    }
+    PROF_T(tq3);
+#ifdef CFEAR_K5_PROFILE
+    prof[5] += tq1 - tq0; prof[6] += tq2 - tq1; prof[7] += tq3 - tq2;
+#endif
+    if (valid && pos < cap) { res.st(0, pos, rp); res.st(1, pos, rq); res.st(2, pos, rab); res.st(3, pos, rcw); }
     nres += total;
   }
   __syncthreads();                 // residual list visible to the whole block
@@ -403,6 +444,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   __shared__ GridView s_view[K5_MAXSCANS];
   __shared__ int32_t s_slots[K5_MAXSCANS];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_misc_off;
 
   const int prob = blockIdx.x;
   const int ns = P.nscans, K = ns - 1;
@@ -423,6 +465,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   // copies, keyframe by keyframe while they fit; the rest is read through L2.
   if (tid == 0) {
     uint32_t off = 0, tx = 0;
+    s_misc_off = 0;
     for (int i = 0; i < K; ++i) {
       const int sl = s_slots[i];
       const NNGrid G = s_grid[i];
@@ -439,6 +482,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
       }
       s_view[i] = V;
     }
+    s_misc_off = off;
     mbar_expect_tx(&s_bar, tx);
     for (int i = 0; i < K; ++i) {
       const int sl = s_slots[i];
@@ -456,8 +500,15 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   __syncthreads();
   mbar_wait(&s_bar, 0);
 
+#ifdef CFEAR_K5_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tk0 = clock64();
+#endif
   double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
-  double2* res = P.res + (size_t)prob * P.res_cap * 4;
+  ResList res;
+  res.g = P.res + (size_t)prob * P.res_cap * 4; res.cap_g = P.res_cap;
+  res.s = reinterpret_cast<double2*>(dyn_smem + s_misc_off);
+  res.cap_s = min(((int)P.smem_bytes - (int)s_misc_off) / 64, P.res_cap);
   int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * K * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
   int parity = 0;
@@ -469,10 +520,10 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp PROF_ARG);
       if (nres * per_block <= 1) { success = false; break; }
       EvalOut ev;
-      block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
+      block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
       double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
       if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
       x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
@@ -482,7 +533,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     outer = it;
     if (success) {
       EvalOut ev;
-      block_evaluate<COST, LOSS, false>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
+      block_evaluate<COST, LOSS, false>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
       sum.final_cost = ev.cost;
     }
   } else {
@@ -490,9 +541,12 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     double prev_score = 1.7976931348623157e308;
     int itr;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp);
+      PROF_T(tb0);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp PROF_ARG);
+      PROF_T(tb1);
+      PROF_ADD(prof[4], tb0, tb1);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
-      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity);               // :117
+      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity PROF_ARG);               // :117
       success = sum.usable;
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
@@ -519,7 +573,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     EvalOut ev;                                                                 // GetCovariance :392-433
-    block_evaluate<COST, LOSS, true>(P.loss_limit, res, P.res_cap, nres, x, ev, s_part, parity);
+    block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
     double inv[9]; bool ok = true;
     for (int c = 0; c < 3 && ok; ++c) {
       double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
@@ -541,6 +595,11 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     reinterpret_cast<RegStatsDev*>(P.stats)[prob] = st;
     double* c36 = P.cov36 + (size_t)prob * 36;
     for (int i = 0; i < 36; ++i) c36[i] = cov[i];
+#ifdef CFEAR_K5_PROFILE
+    c36[8] = (double)prof[0]; c36[9] = (double)prof[1]; c36[10] = (double)prof[2]; c36[11] = (double)prof[3];
+    c36[13] = (double)prof[4]; c36[15] = (double)(clock64() - tk0);
+    c36[14] = (double)prof[5]; c36[16] = (double)prof[6]; c36[17] = (double)prof[7];
+#endif
   }
 }
 

@@ -395,5 +395,140 @@ class n_scan_normal_reg : public Registration {
   unsigned int max_itr_solver_ = 20;
 };
 
+// ---- OdometryKeyframeFuser (odometrykeyframefuser.h:66-293, odometrykeyframefuser.cpp:23-259, 397-416, 470-494) -----
+// Per-scan orchestration: motion compensation with the previous motion, constant-velocity guess, registration against
+// the sliding window of keyframes, sanity check, keyframe insertion.  ROS publishing / TF / pose-graph logging and
+// covariance-by-sampling are out of scope.  Quirk kept from the reference: the return value of Register() lands in a
+// shadowed local (odometrykeyframefuser.cpp:184-186), so the pose in T_vek.back() is used whether or not it succeeded.
+struct RadarScan {                         // the members of types.h:93-143 the pose path touches
+  Affine3d T;                              // GetPose()
+  MapNormalPtr cloud_normal_;
+  uint64_t stamp = 0;
+};
+typedef std::vector<RadarScan> PoseScanVector;
+
+class OdometryKeyframeFuser {
+ public:
+  class Parameters {
+   public:
+    std::string cost_type = "P2L";
+    weightoption weight_opt = Uniform;
+    int submap_scan_size = 3;
+    bool weight_intensity_ = false;
+    bool use_guess = true, disable_registration = false, soft_constraint = false;
+    bool compensate = true, radar_ccw = false;
+    bool use_keyframe = true, use_raw_pointcloud = false;
+    double res = 3.5;
+    double min_keyframe_dist_ = 1.5, min_keyframe_rot_deg_ = 5;
+    std::string loss_type_ = "Huber";
+    double loss_limit_ = 0.1;
+    double covar_scale_ = 1.0;
+    double regularization_ = 0.0;
+  };
+
+  OdometryKeyframeFuser(const Parameters& pars, bool disable_callback = false) : par(pars) {
+    (void)disable_callback;
+    assert(par.res > 0.05 && par.submap_scan_size >= 1);
+    radar_reg = std::make_shared<n_scan_normal_reg>(Str2Cost(par.cost_type), Str2loss(par.loss_type_), par.loss_limit_, par.weight_opt);
+    radar_reg->SetD2dPar(par.covar_scale_, par.regularization_);
+    cov_current = Matrix6d::Identity();
+  }
+
+  // odometrykeyframefuser.cpp:397-416
+  void pointcloudCallback(CloudPtr& cloud_filtered, CloudPtr& cloud_filtered_peaks, Affine3d& Tcurr, const uint64_t& t) {
+    updated = false;
+    processFrame(cloud_filtered, cloud_filtered_peaks, t);
+    nr_callbacks_++;
+    Tcurr = Tcurrent;
+  }
+  void pointcloudCallback(CloudPtr& cloud_filtered, CloudPtr& cloud_filtered_peaks, Affine3d& Tcurr, const uint64_t& t, Matrix6d& cov_curr) {
+    pointcloudCallback(cloud_filtered, cloud_filtered_peaks, Tcurr, t);
+    cov_curr = cov_current;
+  }
+
+  // :62-73
+  static bool KeyFrameBasedFuse(const Affine3d& diff, bool use_keyframe, double min_keyframe_dist, double min_keyframe_rot_deg) {
+    if (!use_keyframe) return true;
+    const double yaw = std::atan2(diff(1, 0), diff(1, 1));          // eulerAngles(0,1,2) of a planar rotation, normalised
+    const double tn = std::sqrt(diff(0, 3) * diff(0, 3) + diff(1, 3) * diff(1, 3) + diff(2, 3) * diff(2, 3));
+    return tn > min_keyframe_dist || std::fabs(yaw) > (min_keyframe_rot_deg * M_PI / 180.0);
+  }
+  // :76-94
+  static bool AccelerationVelocitySanityCheck(const Affine3d& Tmot_prev, const Affine3d& Tmot_curr) {
+    const double dt = 0.25, vel_limit = 200, acc_limit = 200;
+    const double vx = Tmot_curr(0, 3) / dt, vy = Tmot_curr(1, 3) / dt;
+    const double ax = (Tmot_curr(0, 3) - Tmot_prev(0, 3)) / (dt * dt), ay = (Tmot_curr(1, 3) - Tmot_prev(1, 3)) / (dt * dt);
+    if (std::sqrt(ax * ax + ay * ay) > acc_limit) return false;
+    if (std::sqrt(vx * vx + vy * vy) > vel_limit) return false;
+    return true;
+  }
+
+  bool updated = false;
+  size_t nr_callbacks_ = 0, frame_nr_ = 0;
+  double distance_traveled = 0;
+  Affine3d Tcurrent, T_prev, Tmot;
+  Matrix6d cov_current;
+  PoseScanVector keyframes_;
+  std::shared_ptr<n_scan_normal_reg> radar_reg;
+
+ private:
+  // :143-259
+  void processFrame(CloudPtr& cloud, CloudPtr& cloud_peaks, const uint64_t& t) {
+    const Affine3d TprevMot(Tmot);
+    if (par.compensate) {
+      Compensate(*cloud, TprevMot, par.radar_ccw);
+      if (cloud_peaks) Compensate(*cloud_peaks, TprevMot, par.radar_ccw);
+    }
+    std::vector<Matrix6d> cov_vek;
+    std::vector<MapNormalPtr> scans_vek;
+    std::vector<Affine3d> T_vek;
+    MapNormalPtr Pcurrent(new MapPointNormal(cloud, (float)par.res, Vector2d(0, 0), par.weight_intensity_, par.use_raw_pointcloud));
+    const Affine3d Tguess = par.use_guess ? T_prev * TprevMot : T_prev;
+    if (keyframes_.empty()) {                                        // :171-177
+      RadarScan scan; scan.T = Affine3d::Identity(); scan.cloud_normal_ = Pcurrent; scan.stamp = t;
+      updated = true;
+      AddToReference(keyframes_, scan, (size_t)par.submap_scan_size);
+      return;
+    }
+    for (size_t i = 0; i < keyframes_.size(); ++i) {                 // FormatScans :478-494
+      cov_vek.push_back(Matrix6d::Identity()); scans_vek.push_back(keyframes_[i].cloud_normal_); T_vek.push_back(keyframes_[i].T);
+    }
+    cov_vek.push_back(Matrix6d::Identity()); scans_vek.push_back(Pcurrent); T_vek.push_back(Tguess);
+    if (!par.disable_registration) (void)radar_reg->Register(scans_vek, T_vek, cov_vek, par.soft_constraint);   // result ignored (:184-186)
+    Tcurrent = T_vek.back();
+    cov_current = cov_vek.back();
+    const Affine3d Tmot_current = T_prev.inverse() * Tcurrent;
+    if (!AccelerationVelocitySanityCheck(Tmot, Tmot_current)) Tcurrent = Tguess;    // :197-199
+    Tmot = T_prev.inverse() * Tcurrent;
+    const Affine3d Tkeydiff = keyframes_.back().T.inverse() * Tcurrent;
+    const bool fuse = KeyFrameBasedFuse(Tkeydiff, par.use_keyframe, par.min_keyframe_dist_, par.min_keyframe_rot_deg_);
+    if (fuse) {                                                      // `success && fuse` with success always true
+      distance_traveled += std::sqrt(Tkeydiff(0, 3) * Tkeydiff(0, 3) + Tkeydiff(1, 3) * Tkeydiff(1, 3));
+      frame_nr_++;
+      RadarScan scan; scan.T = Tcurrent; scan.cloud_normal_ = Pcurrent; scan.stamp = t;
+      AddToReference(keyframes_, scan, (size_t)par.submap_scan_size);
+      updated = true;
+    }
+    T_prev = Tcurrent;
+  }
+  // :470-476
+  static void AddToReference(PoseScanVector& reference, RadarScan& scan, size_t submap_scan_size) {
+    reference.push_back(scan);
+    if (reference.size() > submap_scan_size) reference.erase(reference.begin());
+  }
+  Parameters par;
+};
+
+// KITTI-format pose row (eval_trajectory.cpp:169-183 via MatToString types.cpp:64-73): the 3x4 row-major matrix,
+// fixed notation with 6 decimals (std::fixed << std::showpoint), space separated.
+inline std::string MatToString(const Affine3d& T) {
+  std::ostringstream s;
+  s << std::fixed << std::showpoint;
+  s.precision(6);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) { s << T(r, c); if (!(r == 2 && c == 3)) s << " "; }
+  return s.str();
+}
+
 }  // namespace CFEAR_Radarodometry
 #endif  // CFEAR_B200_HPP_
