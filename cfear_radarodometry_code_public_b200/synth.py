@@ -123,3 +123,13 @@ def make_problem_images(seed: int, n_keyframes: int = 4, A: int = A_DEFAULT, R: 
     poses = trajectory(n_keyframes + 1, t0=float(rng.uniform(0, 30)))
     imgs = np.stack([render_polar(world, poses[i], seed * 1000 + i, A, R, res) for i in range(n_keyframes + 1)])
     return imgs, poses
+
+
+def make_sequence(seed: int, n_scans: int, A: int = A_DEFAULT, R: int = R_DEFAULT, res: float = RES_DEFAULT):
+    """One synthetic Oxford-shaped (sub)sequence: n_scans images of one world along the 4 Hz trajectory.
+    Returns (images [n,A,R] u8, poses_true [n,3] relative to the first pose)."""
+    world = make_world(seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 104729))
+    poses = trajectory(n_scans, t0=float(rng.uniform(0, 30)))
+    imgs = np.stack([render_polar(world, poses[i], seed * 100003 + i, A, R, res) for i in range(n_scans)])
+    return imgs, poses

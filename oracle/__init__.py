@@ -182,3 +182,19 @@ def pipeline_batch(polar, mot, kf_sets, kf_ids, poses, cfg, *, k=12, z_min=60, m
                              _p(kf_ids), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
                              _p(p), _p(cov36), C.byref(stats), _p(ncells), _p(npts), _p(stage_ms))
     return dict(poses=p, cov=cov36.reshape(nprob, 6, 6), stats=list(stats), ncells=ncells, npts=npts, stage_ms=stage_ms)
+
+
+def odometry_sequence(polar, cfg, *, k=12, z_min=60, min_distance=2.5, range_res=0.0438, radius=3.5, weight_intensity=True,
+                      compensate=True, ccw=False, submap_scan_size=3, use_guess=True, min_keyframe_dist=1.5,
+                      min_keyframe_rot_deg=5.0):
+    """OdometryKeyframeFuser replay of one sequence of polar images (nscans,A,R).  Returns dict(poses [n,3], keyframe, stats, ncells)."""
+    polar = np.ascontiguousarray(polar, dtype=np.uint8)
+    n, A, R = polar.shape
+    ci, cd = cfg
+    pipe_i = np.array([A, R, k, int(z_min), int(weight_intensity), int(compensate), int(ccw), submap_scan_size, int(use_guess)], np.int32)
+    pipe_f = np.array([min_distance, range_res, radius], np.float32)
+    kf_d = np.array([min_keyframe_dist, min_keyframe_rot_deg], np.float64)
+    poses = np.zeros((n, 3)); kf = np.zeros(n, np.int32); ncells = np.zeros(n, np.int32)
+    stats = (RegStats * n)()
+    lib().orc_odometry_sequence(n, _p(pipe_i), _p(pipe_f), _p(kf_d), _p(ci), _p(cd), _p(polar), _p(poses), _p(kf), C.byref(stats), _p(ncells))
+    return dict(poses=poses, keyframe=kf, stats=list(stats), ncells=ncells)

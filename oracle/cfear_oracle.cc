@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -965,4 +966,111 @@ int orc_pipeline_batch(int nthreads, int nprob, const int32_t* pipe_i, const flo
   return 0;
 }
 
+}  // extern "C"
+
+// ----------------------------------------------------------------------------
+// Sequence replay: OdometryKeyframeFuser::processFrame semantics
+// (odometrykeyframefuser.cpp:143-259, 62-94, 470-494) on top of the per-scan
+// path above, one sequence, one scan at a time -- the execution model of
+// offline_odometry (src/offline_odometry.cpp:73-127).  Planar rigid transforms
+// are kept as the 2x3 matrices an Eigen::Affine3d product would hold.
+// ----------------------------------------------------------------------------
+namespace {
+struct T2 { double r00 = 1, r01 = 0, r10 = 0, r11 = 1, x = 0, y = 0; };
+T2 t2_from(double x, double y, double yaw) { T2 t; t.r00 = std::cos(yaw); t.r01 = -std::sin(yaw); t.r10 = std::sin(yaw); t.r11 = std::cos(yaw); t.x = x; t.y = y; return t; }
+T2 t2_mul(const T2& a, const T2& b) {
+  T2 r;
+  r.r00 = a.r00 * b.r00 + a.r01 * b.r10; r.r01 = a.r00 * b.r01 + a.r01 * b.r11;
+  r.r10 = a.r10 * b.r00 + a.r11 * b.r10; r.r11 = a.r10 * b.r01 + a.r11 * b.r11;
+  r.x = a.r00 * b.x + a.r01 * b.y + a.x; r.y = a.r10 * b.x + a.r11 * b.y + a.y;
+  return r;
+}
+T2 t2_inv(const T2& a) {
+  T2 r; r.r00 = a.r00; r.r01 = a.r10; r.r10 = a.r01; r.r11 = a.r11;
+  r.x = -(r.r00 * a.x + r.r01 * a.y); r.y = -(r.r10 * a.x + r.r11 * a.y);
+  return r;
+}
+double t2_yaw(const T2& a) { return std::atan2(a.r10, a.r11); }   // utils.cpp:115-122 (eulerAngles(0,1,2)[2], planar)
+
+struct OwnedCells {
+  std::vector<double> mean, normal, cov, plan; std::vector<int32_t> ns; CellSet cs;
+  void finish(int n) { cs.n = n; cs.mean = mean.data(); cs.normal = normal.data(); cs.cov = cov.data(); cs.planarity = plan.data(); cs.nsamples = ns.data(); cs.build_index(); }
+};
+}  // namespace
+
+extern "C" {
+// pipe_i: A, R, k, z_min, weight_intensity, compensate, ccw, submap_scan_size, use_guess
+// pipe_f: min_distance, range_res, radius(res)
+// kf_d:   min_keyframe_dist, min_keyframe_rot_deg
+int orc_odometry_sequence(int nscans, const int32_t* pipe_i, const float* pipe_f, const double* kf_d,
+                          const int32_t* cfg_i, const double* cfg_d, const uint8_t* polar,
+                          double* poses_out /*nscans*3*/, int32_t* keyframe_out /*nscans*/, void* stats_out /*nscans RegStats*/,
+                          int32_t* ncells_out /*nscans*/) {
+  const int A = pipe_i[0], R = pipe_i[1], k = pipe_i[2], zmin = pipe_i[3];
+  const int wint = pipe_i[4], comp = pipe_i[5], ccw = pipe_i[6], submap = pipe_i[7], use_guess = pipe_i[8];
+  RegCfg cfg;
+  cfg.cost = cfg_i[0]; cfg.loss = cfg_i[1]; cfg.weight_opt = cfg_i[2];
+  cfg.max_outer = cfg_i[3]; cfg.min_outer = cfg_i[4]; cfg.max_inner = cfg_i[5];
+  cfg.solver_mode = cfg_i[6]; cfg.gn_iters = cfg_i[7];
+  cfg.loss_limit = cfg_d[0]; cfg.cov_scale = cfg_d[1]; cfg.regularization = cfg_d[2]; cfg.radius = cfg_d[3];
+  T2 T_prev, Tmot, Tcurrent;
+  std::vector<std::pair<T2, std::shared_ptr<OwnedCells>>> keyframes;
+  std::vector<int32_t> idx((size_t)A * k), cnt(A);
+  std::vector<float> cloud((size_t)A * k * 4);
+  for (int s = 0; s < nscans; ++s) {
+    const uint8_t* img = polar + (size_t)s * A * R;
+    orc_kstrongest(img, A, R, zmin, k, idx.data(), cnt.data());
+    const int n = orc_cloud(img, A, R, k, idx.data(), cnt.data(), pipe_f[0], pipe_f[1], cloud.data());
+    const T2 TprevMot = Tmot;                                              // :146
+    if (comp) { const double mot[3] = {TprevMot.x, TprevMot.y, t2_yaw(TprevMot)}; orc_compensate(cloud.data(), n, mot, ccw); }
+    auto cur = std::make_shared<OwnedCells>();
+    cur->mean.resize(2 * (size_t)n + 2); cur->normal.resize(2 * (size_t)n + 2); cur->cov.resize(4 * (size_t)n + 4);
+    cur->plan.resize(n + 1); cur->ns.resize(n + 1);
+    std::vector<double> avg(n + 1);
+    const int nc = orc_surface_points(cloud.data(), n, pipe_f[2], 1.0, wint, 0.0, 0.0, cur->mean.data(), cur->normal.data(),
+                                      cur->cov.data(), cur->plan.data(), cur->ns.data(), avg.data(), nullptr);   // :161
+    cur->finish(nc);
+    if (ncells_out) ncells_out[s] = nc;
+    RegStats st = RegStats();
+    keyframe_out[s] = 0;
+    const T2 Tguess = use_guess ? t2_mul(T_prev, TprevMot) : T_prev;       // :164-168
+    if (keyframes.empty()) {                                               // :171-177
+      keyframes.push_back(std::make_pair(T2(), cur));
+      keyframe_out[s] = 1;
+      poses_out[3 * s] = Tcurrent.x; poses_out[3 * s + 1] = Tcurrent.y; poses_out[3 * s + 2] = t2_yaw(Tcurrent);
+      if (stats_out) std::memcpy((char*)stats_out + sizeof(RegStats) * (size_t)s, &st, sizeof(RegStats));
+      continue;
+    }
+    std::vector<CellSet*> scans; std::vector<double> poses;                // FormatScans :478-494
+    for (auto& kf : keyframes) { scans.push_back(&kf.second->cs); poses.push_back(kf.first.x); poses.push_back(kf.first.y); poses.push_back(t2_yaw(kf.first)); }
+    scans.push_back(&cur->cs); poses.push_back(Tguess.x); poses.push_back(Tguess.y); poses.push_back(t2_yaw(Tguess));
+    double cov36[36];
+    const std::vector<double> poses_in = poses;
+    do_register(cfg, scans, poses, cov36, st, nullptr);                    // :186 (return value ignored :184-186)
+    // Tsrc is rewritten from the parameters only after a usable solve (n_scan_normal.cpp:119-121,177-178)
+    const bool wrote = st.num_residuals > 1 && st.usable;
+    const size_t L = poses.size() - 3;
+    Tcurrent = wrote ? t2_from(poses[L], poses[L + 1], poses[L + 2]) : Tguess;       // :195
+    const T2 Tmot_current = t2_mul(t2_inv(T_prev), Tcurrent);
+    {                                                                      // AccelerationVelocitySanityCheck :76-94, :197-199
+      const double dt = 0.25;
+      const double vel = std::sqrt(Tmot_current.x * Tmot_current.x + Tmot_current.y * Tmot_current.y) / dt;
+      const double ax = (Tmot_current.x - Tmot.x) / (dt * dt), ay = (Tmot_current.y - Tmot.y) / (dt * dt);
+      if (std::sqrt(ax * ax + ay * ay) > 200 || vel > 200) Tcurrent = Tguess;
+    }
+    Tmot = t2_mul(t2_inv(T_prev), Tcurrent);                               // :200
+    const T2 Tkeydiff = t2_mul(t2_inv(keyframes.back().first), Tcurrent);  // :227
+    const bool fuse = std::sqrt(Tkeydiff.x * Tkeydiff.x + Tkeydiff.y * Tkeydiff.y) > kf_d[0] ||
+                      std::fabs(t2_yaw(Tkeydiff)) > kf_d[1] * M_PI / 180.0;   // :62-73
+    if (fuse) {                                                            // :234-249, AddToReference :470-476
+      keyframes.push_back(std::make_pair(Tcurrent, cur));
+      if ((int)keyframes.size() > submap) keyframes.erase(keyframes.begin());
+      keyframe_out[s] = 1;
+    }
+    T_prev = Tcurrent;                                                     // :257
+    poses_out[3 * s] = Tcurrent.x; poses_out[3 * s + 1] = Tcurrent.y; poses_out[3 * s + 2] = t2_yaw(Tcurrent);
+    if (stats_out) std::memcpy((char*)stats_out + sizeof(RegStats) * (size_t)s, &st, sizeof(RegStats));
+  }
+  return 0;
+}
 }  // extern "C"

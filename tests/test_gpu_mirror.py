@@ -55,3 +55,40 @@ def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K):
     np.testing.assert_allclose(score, ost.score, rtol=1e-6)
     np.testing.assert_allclose(cov, ocov, rtol=1e-5, atol=1e-12)
     assert near == orc.nearest(sets[-1]["mean"], np.array([[10.0, 0.0]]), 50.0)[0]
+
+
+@pytest.fixture(scope="module")
+def fuser_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cpp") / "fuser_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "fuser_test.cpp"), "-o", out, "-L" + PKG, "-lcfear_b200",
+                           "-Wl,-rpath," + PKG])
+    return out
+
+
+@pytest.mark.parametrize("cost,wopt,submap,wint,res", [("P2L", 0, 3, True, 3.5), ("P2P", 4, 4, True, 3.0), ("P2D", 4, 2, False, 3.0)])
+def test_fuser_sequence_replay_matches_oracle(fuser_exe, orc, tmp_path, cost, wopt, submap, wint, res):
+    """OdometryKeyframeFuser::processFrame semantics over a 14-scan synthetic sequence: same keyframe decisions, poses
+    within 1e-4 m / 1e-5 rad of the oracle replay at every scan, KITTI rows in the reference's fixed 6-decimal format."""
+    from cfear_radarodometry_code_public_b200 import synth
+    imgs, truth = synth.make_sequence(7, 14)
+    reg = 0.1 if cost == "P2D" else 0.0
+    fin, fout, fest = str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(tmp_path / "est.txt")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<6if4sd", imgs.shape[0], imgs.shape[1], imgs.shape[2], submap, wopt, int(wint), res,
+                            cost.encode() + b"\0", reg))
+        f.write(imgs.tobytes())
+    subprocess.check_call([fuser_exe, fin, fout, fest])
+    rec = np.frombuffer(open(fout, "rb").read(), dtype=np.dtype([("p", np.float64, 3), ("up", np.int32)]))
+    ref = orc.odometry_sequence(imgs, orc.reg_cfg(cost=cost, weight_opt=wopt, regularization=reg), radius=res,
+                                weight_intensity=wint, submap_scan_size=submap)
+    assert np.array_equal(rec["up"], ref["keyframe"])
+    d = rec["p"] - ref["poses"]
+    assert np.hypot(d[:, 0], d[:, 1]).max() < 1e-4 and np.abs(d[:, 2]).max() < 1e-5
+    assert np.hypot(*(rec["p"][-1, :2] - truth[-1, :2])) < 1.0          # tracks the simulated motion
+    rows = open(fest).read().strip().split("\n")
+    assert len(rows) == imgs.shape[0]
+    x, y, yaw = rec["p"][-1]
+    c, s = np.cos(yaw), np.sin(yaw)
+    exp = "%.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f" % (c, -s, 0, x, s, c, 0, y, 0, 0, 1, 0)
+    assert rows[-1] == exp
