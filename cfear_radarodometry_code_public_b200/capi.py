@@ -37,6 +37,11 @@ class RegStats(C.Structure):
                 ("final_cost", C.c_double), ("score", C.c_double)]
 
 
+class SeqParams(C.Structure):
+    _fields_ = [("submap_scan_size", C.c_int32), ("use_guess", C.c_int32), ("use_keyframe", C.c_int32), ("reserved", C.c_int32),
+                ("min_keyframe_dist", C.c_double), ("min_keyframe_rot_deg", C.c_double)]
+
+
 CELL_DTYPE = np.dtype([("mean", np.float64, 2), ("normal", np.float64, 2), ("cov", np.float64, 4),
                        ("planarity", np.float64), ("avg_intensity", np.float64), ("nsamples", np.int32),
                        ("pad", np.int32)])
@@ -50,7 +55,8 @@ SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_updat
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
            "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_dev", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
-           "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h"]
+           "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
+           "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
 
 _lib = None
 
@@ -101,6 +107,11 @@ def load():
         lib.cfear_odometry_step_batch_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         lib.cfear_stage_timing.argtypes = [vp, i32, vp]
         lib.cfear_last_counts.argtypes = [vp, i32, vp, vp, vp]
+        lib.cfear_seq_create.argtypes = [vp, i32, i32, i32, C.POINTER(SeqParams), C.POINTER(C.c_void_p)]
+        lib.cfear_seq_destroy.argtypes = [vp]
+        lib.cfear_seq_step.argtypes = [vp, vp]
+        lib.cfear_seq_step_dev.argtypes = [vp, vp]
+        lib.cfear_seq_read.argtypes = [vp, i32, i32, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -354,3 +365,36 @@ class Context:
     def odometry_step_batch_dev(self, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats):
         self._ck(self.lib.cfear_odometry_step_batch_dev(self.h, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses,
                                                         d_cov36, d_stats), "cfear_odometry_step_batch_dev")
+
+
+class Sequences:
+    """nseq independent sequences replayed in lock-step on the device (cfear_seq_*)."""
+
+    def __init__(self, ctx: Context, nseq: int, max_steps: int, slot_base: int = 0, submap_scan_size: int = 3,
+                 use_guess: bool = True, use_keyframe: bool = True, min_keyframe_dist: float = 1.5, min_keyframe_rot_deg: float = 5.0):
+        self.ctx, self.nseq, self.max_steps = ctx, nseq, max_steps
+        sp = SeqParams(submap_scan_size, int(use_guess), int(use_keyframe), 0, min_keyframe_dist, min_keyframe_rot_deg)
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.cfear_seq_create(ctx.h, nseq, slot_base, max_steps, C.byref(sp), C.byref(h)), "cfear_seq_create")
+        self.h = h
+
+    def step(self, polar):
+        """polar: host (nseq, A, R) uint8."""
+        if polar.dtype != np.uint8 or not polar.flags["C_CONTIGUOUS"]:
+            polar = np.ascontiguousarray(polar, dtype=np.uint8)
+        self._keep = polar          # the copy is asynchronous: keep the buffer alive until the next call
+        self.ctx._ck(self.ctx.lib.cfear_seq_step(self.h, _ptr(polar)), "cfear_seq_step")
+
+    def step_dev(self, d_polar_ptr):
+        self.ctx._ck(self.ctx.lib.cfear_seq_step_dev(self.h, d_polar_ptr), "cfear_seq_step_dev")
+
+    def read(self, step_from, nsteps):
+        poses = np.zeros((self.nseq, nsteps, 3)); kf = np.zeros((self.nseq, nsteps), np.int32)
+        st = np.zeros((self.nseq, nsteps), STATS_DTYPE)
+        self.ctx._ck(self.ctx.lib.cfear_seq_read(self.h, step_from, nsteps, _ptr(poses), _ptr(kf), _ptr(st)), "cfear_seq_read")
+        return poses, kf, st
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.cfear_seq_destroy(self.h)
+            self.h = None

@@ -17,6 +17,7 @@
 #include "k1_kstrongest.cuh"
 #include "k3_surface.cuh"
 #include "k5_register.cuh"
+#include "k6_fuser.cuh"
 
 using namespace cfear;
 
@@ -380,9 +381,9 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
 }
 
 static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
-                     cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0) {
+                     cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0, const int32_t* d_nscans_pp = nullptr) {
   RegParams p;
-  p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
+  p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.nscans_pp = d_nscans_pp; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
   p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
   p.cost = c->cfg.cost; p.loss = c->cfg.loss; p.weight_opt = c->cfg.weight_opt; p.solver_mode = c->cfg.solver_mode;
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
@@ -748,6 +749,101 @@ int cfear_last_counts(cfear_ctx* c, int nprob, const int32_t* cur_slots, int32_t
     CK(cudaMemcpyAsync(all.data(), c->pool.ncells, all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < nprob; ++i) { RC(check_slot(c, cur_slots[i])); ncells_out[i] = all[cur_slots[i]]; }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+
+// ---- lock-step replay of many independent sequences (OdometryKeyframeFuser semantics on the device) ---------------
+struct cfear_seq {
+  cfear_ctx* ctx;
+  SeqParams p;
+  int slot_base;
+  std::vector<void*> allocs;
+};
+
+void cfear_seq_destroy(cfear_seq* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->cfg.device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (void* q : s->allocs) cudaFree(q);
+  delete s;
+}
+
+int cfear_seq_create(cfear_ctx* c, int nseq, int slot_base, int max_steps, const cfear_seq_params* sp, cfear_seq** out) {
+  ENTER(c);
+  if (!sp || !out || nseq < 1 || max_steps < 1) { g_err = "bad argument"; return CFEAR_ERR_ARG; }
+  *out = nullptr;
+  if (nseq > c->cfg.max_batch) { g_err = "nseq exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (sp->submap_scan_size < 1 || sp->submap_scan_size > c->cfg.max_keyframes) { g_err = "submap_scan_size must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
+  const int kmax = c->cfg.max_keyframes;
+  if (slot_base < 0 || slot_base + nseq * (kmax + 1) > c->cfg.max_cellsets) { g_err = "sequences need nseq*(max_keyframes+1) cell-set slots from slot_base"; return CFEAR_ERR_CAPACITY; }
+  cfear_seq* s = new (std::nothrow) cfear_seq();
+  if (!s) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
+  s->ctx = c; s->slot_base = slot_base;
+  SeqParams& P = s->p;
+  P.nseq = nseq; P.submap = sp->submap_scan_size; P.kmax = kmax; P.use_guess = sp->use_guess; P.use_keyframe = sp->use_keyframe;
+  P.max_steps = max_steps; P.min_keyframe_dist = sp->min_keyframe_dist; P.min_keyframe_rot_deg = sp->min_keyframe_rot_deg;
+  auto al = [&](void** q, size_t bytes) { if (cudaMalloc(q, bytes) != cudaSuccess) return false; s->allocs.push_back(*q); return true; };
+  bool ok = al((void**)&P.state, sizeof(SeqState) * nseq) && al((void**)&P.kf_pose, sizeof(T2) * (size_t)nseq * kmax) &&
+            al((void**)&P.kf_slot, 4 * (size_t)nseq * kmax) && al((void**)&P.nscans_pp, 4 * (size_t)nseq) &&
+            al((void**)&P.traj, 24 * (size_t)nseq * max_steps) && al((void**)&P.kf_flag, 4 * (size_t)nseq * max_steps) &&
+            al((void**)&P.traj_stats, sizeof(cfear_reg_stats) * (size_t)nseq * max_steps);
+  if (!ok) { g_err = "cudaMalloc failed"; cfear_seq_destroy(s); return CFEAR_ERR_CUDA; }
+  P.mot = c->d_mot; P.cur_slots = c->d_curslots; P.slots = c->d_slots; P.poses = c->d_poses; P.stats = c->d_stats;
+  k6_init<<<(nseq + 127) / 128, 128, 0, c->stream>>>(P, slot_base);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(P.traj, 0, 24 * (size_t)nseq * max_steps, c->stream));
+  CK(cudaMemsetAsync(P.kf_flag, 0, 4 * (size_t)nseq * max_steps, c->stream));
+  CK(cudaMemsetAsync(P.traj_stats, 0, sizeof(cfear_reg_stats) * (size_t)nseq * max_steps, c->stream));
+  *out = s;
+  return CFEAR_OK;
+}
+
+static int seq_step_common(cfear_seq* s, const uint8_t* d_polar) {
+  cfear_ctx* c = s->ctx;
+  const SeqParams& P = s->p;
+  const int B = P.nseq;
+  k6_pre<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
+  c->launches++;
+  CK(cudaGetLastError());
+  RC(launch_k1(c, d_polar, B));
+  RC(launch_k3(c, 0, B, c->d_mot, c->d_curslots, false));
+  RC(launch_k5(c, B, P.kmax + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, P.nscans_pp));
+  k6_post<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
+  c->launches++;
+  CK(cudaGetLastError());
+  return CFEAR_OK;
+}
+
+int cfear_seq_step_dev(cfear_seq* s, const uint8_t* d_polar) {
+  if (!s || !d_polar) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  ENTER(s->ctx);
+  return seq_step_common(s, d_polar);
+}
+
+int cfear_seq_step(cfear_seq* s, const uint8_t* polar) {
+  if (!s || !polar) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  cfear_ctx* c = s->ctx;
+  ENTER(c);
+  const size_t bytes = (size_t)s->p.nseq * c->cfg.azimuths * c->cfg.range_bins;
+  CK(cudaMemcpyAsync(c->d_polar, polar, bytes, cudaMemcpyHostToDevice, c->stream));   // stream-ordered: the previous step's K1 is done
+  return seq_step_common(s, c->d_polar);
+}
+
+int cfear_seq_read(cfear_seq* s, int step_from, int nsteps, double* poses_out, int32_t* keyframe_out, cfear_reg_stats* stats_out) {
+  if (!s) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  cfear_ctx* c = s->ctx;
+  ENTER(c);
+  const SeqParams& P = s->p;
+  if (step_from < 0 || nsteps < 0 || step_from + nsteps > P.max_steps) { g_err = "step range outside [0, max_steps)"; return CFEAR_ERR_ARG; }
+  for (int b = 0; b < P.nseq; ++b) {
+    const size_t src = (size_t)b * P.max_steps + step_from, dst = (size_t)b * nsteps;
+    if (poses_out) CK(cudaMemcpyAsync(poses_out + dst * 3, P.traj + src * 3, 24 * (size_t)nsteps, cudaMemcpyDeviceToHost, c->stream));
+    if (keyframe_out) CK(cudaMemcpyAsync(keyframe_out + dst, P.kf_flag + src, 4 * (size_t)nsteps, cudaMemcpyDeviceToHost, c->stream));
+    if (stats_out) CK(cudaMemcpyAsync(stats_out + dst, reinterpret_cast<cfear_reg_stats*>(P.traj_stats) + src, sizeof(cfear_reg_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
   return CFEAR_OK;

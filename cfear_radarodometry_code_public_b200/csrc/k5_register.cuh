@@ -27,7 +27,8 @@ constexpr int K5_SMEM_BYTES = 100 * 1024;   // dynamic smem per CTA: keyframe NN
 
 struct RegParams {
   CellPool pool;
-  int nprob, nscans;             // nscans = K+1 cell sets per problem, last = current scan
+  int nprob, nscans;             // nscans = K+1 cell sets per problem, last = current scan (row stride of slots / poses)
+  const int32_t* nscans_pp;      // optional [nprob]: cell sets actually used by problem b (<= nscans); the current scan is entry nscans_pp[b]-1
   const int32_t* slots;          // [nprob][nscans]
   double* poses;                 // [nprob][nscans][3] in/out
   double* cov36;                 // [nprob][36]
@@ -343,8 +344,7 @@ __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmi
 template <int COST>
 __device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
                                              const NNGrid* s_grid, const GridView* s_view, const double x[3], int itr,
-                                             const ResList& res, int32_t* assoc, int* s_warp PROF_PARAM) {
-  const int ns = P.nscans, K = ns - 1;
+                                             const ResList& res, int32_t* assoc, int* s_warp, int K PROF_PARAM) {
   const int src_slot = slots[K];
   const int n_src = P.pool.ncells[src_slot];
   const size_t sbase = (size_t)src_slot * P.pool.max_cells;
@@ -447,11 +447,21 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   __shared__ uint32_t s_misc_off;
 
   const int prob = blockIdx.x;
-  const int ns = P.nscans, K = ns - 1;
+  const int stride = P.nscans;
+  const int ns = P.nscans_pp ? P.nscans_pp[prob] : P.nscans, K = ns - 1;
   const int tid = threadIdx.x;
-  double* poses = P.poses + (size_t)prob * ns * 3;
+  double* poses = P.poses + (size_t)prob * stride * 3;
+  if (ns < 2) {                      // nothing to register against (first scan of a sequence): Register() would assert
+    if (tid == 0) {
+      RegStatsDev st; st.success = 0; st.outer_iterations = 0; st.inner_iterations = 0; st.num_residuals = 0; st.num_blocks = 0;
+      st.usable = 0; st.final_cost = 0.0; st.score = 0.0;
+      reinterpret_cast<RegStatsDev*>(P.stats)[prob] = st;
+      for (int i = 0; i < 36; ++i) P.cov36[(size_t)prob * 36 + i] = 0.0;
+    }
+    return;
+  }
   if (tid < ns) {
-    const int sl = P.slots[(size_t)prob * ns + tid];
+    const int sl = P.slots[(size_t)prob * stride + tid];
     s_slots[tid] = sl;
     s_grid[tid] = P.pool.grid[sl];
     const double yaw = poses[3 * tid + 2];
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   res.g = P.res + (size_t)prob * P.res_cap * 4; res.cap_g = P.res_cap;
   res.s = reinterpret_cast<double2*>(dyn_smem + s_misc_off);
   res.cap_s = min(((int)P.smem_bytes - (int)s_misc_off) / 64, P.res_cap);
-  int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * K * P.pool.max_cells : nullptr;
+  int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
   int parity = 0;
 
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp PROF_ARG);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp, K PROF_ARG);
       if (nres * per_block <= 1) { success = false; break; }
       EvalOut ev;
       block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     int itr;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
       PROF_T(tb0);
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp PROF_ARG);
+      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp, K PROF_ARG);
       PROF_T(tb1);
       PROF_ADD(prof[4], tb0, tb1);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114

@@ -190,6 +190,31 @@ int cfear_stage_timing(cfear_ctx* ctx, int enable, float ms_out[3]);
 int cfear_last_counts(cfear_ctx* ctx, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out);
 
 
+/* ---- lock-step replay of many independent sequences ------------------------------------------------------------- */
+/* OdometryKeyframeFuser::processFrame (odometrykeyframefuser.cpp:143-259) for nseq sequences advancing together:
+ * Compensate with the previous motion, constant-velocity guess, Register against the sliding window of keyframes,
+ * AccelerationVelocitySanityCheck (:76-94), KeyFrameBasedFuse (:62-73), AddToReference (:470-476).  Poses, motion, the
+ * keyframe window (a ring of cell-set slots) and the trajectory table stay on the device; a step is enqueued with no
+ * host synchronisation.  Parameters: OdometryKeyframeFuser::Parameters (odometrykeyframefuser.h:92-107). */
+typedef struct cfear_seq_params {
+  int32_t submap_scan_size;      /* 3 */
+  int32_t use_guess;             /* 1 (forced true by offline_odometry.cpp:273) */
+  int32_t use_keyframe;          /* 1 */
+  int32_t reserved;
+  double  min_keyframe_dist;     /* 1.5 */
+  double  min_keyframe_rot_deg;  /* 5 */
+} cfear_seq_params;
+typedef struct cfear_seq cfear_seq;
+/* Sequence b owns the cell-set slots [slot_base + b*(max_keyframes+1), +max_keyframes+1). */
+int  cfear_seq_create(cfear_ctx* ctx, int nseq, int slot_base, int max_steps, const cfear_seq_params* params, cfear_seq** out);
+void cfear_seq_destroy(cfear_seq* seq);
+/* One time step for every sequence: polar [nseq][A][R] (HOST / DEVICE).  Asynchronous on the context stream. */
+int  cfear_seq_step(cfear_seq* seq, const uint8_t* polar);
+int  cfear_seq_step_dev(cfear_seq* seq, const uint8_t* d_polar);
+/* Waits for the enqueued steps and copies out steps [step_from, step_from+nsteps): poses_out [nseq][nsteps][3],
+ * keyframe_out [nseq][nsteps] (1 = scan became a keyframe), stats_out [nseq][nsteps] (any may be NULL). */
+int  cfear_seq_read(cfear_seq* seq, int step_from, int nsteps, double* poses_out, int32_t* keyframe_out, cfear_reg_stats* stats_out);
+
 /* ---- memory helpers for callers that keep buffers resident (bench / replay harness) ------------------------------- */
 /* Page-locked host memory (fast host<->device copies for the host-buffer entry points). */
 void* cfear_alloc_pinned(size_t bytes);

@@ -253,3 +253,28 @@ def test_odometry_step_batch_matches_oracle_pipeline(orc):
         assert out["stats"]["outer_iterations"][b] == ref["stats"][b].outer_iterations
         assert out["stats"]["num_residuals"][b] == ref["stats"][b].num_residuals
     c.close()
+
+
+@pytest.mark.parametrize("cost,wopt,submap,wint,radius", [("P2L", 0, 3, True, 3.5), ("P2D", 4, 4, True, 3.0)])
+def test_sequences_lockstep_match_oracle_replay(orc, cost, wopt, submap, wint, radius):
+    """cfear_seq_*: OdometryKeyframeFuser bookkeeping on the device, 3 sequences advancing together, no host sync per
+    step.  Every sequence must reproduce the oracle's sequential replay: keyframe decisions, iteration counts, poses."""
+    from cfear_radarodometry_code_public_b200 import synth
+    nseq, nsteps, kmax = 3, 10, 4
+    seqs = [synth.make_sequence(40 + b, nsteps)[0] for b in range(nseq)]
+    reg = 0.1 if cost == "P2D" else 0.0
+    c = capi.Context(max_batch=nseq, max_cellsets=nseq * (kmax + 1), max_keyframes=kmax, cost=cost, weight_opt=wopt,
+                     regularization=reg, radius=radius, weight_intensity=int(wint))
+    S = capi.Sequences(c, nseq, nsteps, submap_scan_size=submap)
+    for t in range(nsteps):
+        S.step(np.stack([seqs[b][t] for b in range(nseq)]))
+    poses, kf, st = S.read(0, nsteps)
+    for b in range(nseq):
+        ref = orc.odometry_sequence(seqs[b], orc.reg_cfg(cost=cost, weight_opt=wopt, regularization=reg), radius=radius,
+                                    weight_intensity=wint, submap_scan_size=submap)
+        assert np.array_equal(kf[b], ref["keyframe"])
+        assert np.array_equal(st[b]["outer_iterations"], [s.outer_iterations for s in ref["stats"]])
+        assert np.array_equal(st[b]["num_residuals"], [s.num_residuals for s in ref["stats"]])
+        d = poses[b] - ref["poses"]
+        assert np.hypot(d[:, 0], d[:, 1]).max() < POS_TOL and np.abs(d[:, 2]).max() < ROT_TOL, (b, d)
+    S.close(); c.close()
