@@ -278,3 +278,54 @@ def test_sequences_lockstep_match_oracle_replay(orc, cost, wopt, submap, wint, r
         d = poses[b] - ref["poses"]
         assert np.hypot(d[:, 0], d[:, 1]).max() < POS_TOL and np.abs(d[:, 2]).max() < ROT_TOL, (b, d)
     S.close(); c.close()
+
+
+def test_large_k_global_fallback_paths(orc):
+    """k=40 (the reference's CFEAR-3 preset): 16000-point clouds do not fit shared memory, so K3 runs on its global
+    scratch buffers; r=1.0 makes the voxel grid exceed the shared histogram (global histogram fallback)."""
+    im = helpers.scan_images(8, 1)[0]
+    c = capi.Context(max_batch=2, k_strongest=40, max_cellsets=4, max_keyframes=2, radius=3.0)
+    out = c.filter(im)
+    sets = []
+    for i in range(2):
+        oi, oc = orc.kstrongest(im[i], 60, 40)
+        assert np.array_equal(out["idx"][i], oi)
+        ocl = orc.cloud(im[i], oi, oc)
+        assert np.array_equal(out["clouds"][i].view(np.uint32), ocl.view(np.uint32))
+        o = orc.surface_points(ocl, 3.0, True)
+        assert c.surface_points(ocl, i) == o["mean"].shape[0] > 100
+        _assert_cells_close(c.cells_download(i), o)
+        sets.append(o)
+    P = np.array([[0, 0, 0], [0.5, 0.1, 0.01]], np.float64)
+    gp, gcov, gst = c.register([0, 1], P)
+    ok, op, ocov, ost, _ = orc.register(sets, P, orc.reg_cfg())
+    assert bool(gst["success"]) == ok and gst["outer_iterations"] == ost.outer_iterations
+    assert np.hypot(*(gp[1, :2] - op[1, :2])) < POS_TOL and abs(gp[1, 2] - op[1, 2]) < ROT_TOL
+    # whole path with the fused kernel chain (mode 0 of K3 on global scratch)
+    npts, nc = c.scans_to_cells_batch(im, None, [2, 3])
+    assert nc[0] == sets[0]["mean"].shape[0] and nc[1] == sets[1]["mean"].shape[0]
+    c.close()
+    c = capi.Context(max_batch=1, max_cellsets=2, radius=1.0)
+    oi, oc = orc.kstrongest(im[0], 60, 12)
+    ocl = orc.cloud(im[0], oi, oc)
+    o = orc.surface_points(ocl, 1.0, True)
+    assert c.surface_points(ocl, 0) == o["mean"].shape[0]
+    _assert_cells_close(c.cells_download(0), o)
+    c.close()
+
+
+def test_small_max_cells_and_capacity_errors(orc):
+    im = helpers.scan_images(8, 0)[0]
+    oi, oc = orc.kstrongest(im[0], 60, 12)
+    ocl = orc.cloud(im[0], oi, oc)
+    o = orc.surface_points(ocl, 3.5, True)
+    n = o["mean"].shape[0]
+    c = capi.Context(max_batch=1, max_cellsets=2, max_cells=100)          # fewer cells than the scan produces: truncated, in order
+    assert c.surface_points(ocl, 0) == 100 < n
+    g = c.cells_download(0)
+    np.testing.assert_allclose(g["mean"], o["mean"][:100], atol=1e-9)
+    with pytest.raises(capi.CfearError):
+        c.cells_upload(1, o)                                              # exceeds max_cells
+    with pytest.raises(capi.CfearError):
+        c.filter(np.zeros((2, 400, 3360), np.uint8))                      # exceeds max_batch
+    c.close()
