@@ -66,6 +66,8 @@ __device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc, bo
          (ge_flags(d.w, addc, zhi) >> 3);
 }
 
+// ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
+template <bool ALIGNED>
 __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params p) {
   __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
   __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
 #pragma unroll
     for (int i = 0; i < K1_TILES; ++i) {
       const int v = v0 + i * 32 + lane;
-      d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
+      if (ALIGNED) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
+      else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
     }
     uint32_t g[K1_TILES];
     int nl = 0;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
       uint32_t m = ge_flags16(d[i], addc, zhi);
       const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
       if (v >= nvec) m = 0;
-      else if (b0 < 0 || b0 + 16 > R) {        // row head / tail: drop bytes of neighbouring rows
+      else if (!ALIGNED && (b0 < 0 || b0 + 16 > R)) {        // row head / tail: drop bytes of neighbouring rows
         uint32_t keep = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -120,15 +123,19 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
       int pos = C + incl - nl;
 #pragma unroll
       for (int i = 0; i < K1_TILES; ++i) {
-        uint32_t m = g[i];
+        const uint32_t m = g[i];
+        if (m == 0) continue;
         const int rb = (v0 + i * 32 + lane) * 16 - off;
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int b = bit >> 3, w = 7 - (bit & 7);
-          const uint32_t word = (w == 0) ? d[i].x : (w == 1) ? d[i].y : (w == 2) ? d[i].z : d[i].w;
-          const uint32_t inten = (word >> (8 * b)) & 0xffu;
-          cand[pos++] = (inten << 16) | (uint32_t)(rb + 4 * w + b);
+        const uint32_t words[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t mw = (m << w) & 0x80808080u;             // byte b of word w -> bit 8b+7
+          while (mw) {
+            const int sh = __ffs(mw) - 8;                   // 8b
+            mw &= mw - 1;
+            const uint32_t inten = (words[w] >> sh) & 0xffu;
+            cand[pos++] = (inten << 16) | (uint32_t)(rb + 4 * w + (sh >> 3));
+          }
         }
       }
     }
