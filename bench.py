@@ -56,7 +56,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -140,7 +140,7 @@ def cpu_leg(batch, nsample, min_seconds, steps=None, warmup=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nprob", type=int, default=NPROB)
@@ -241,7 +241,6 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - l0
     nst, stage_ms = ctx.stage_timing(False)
-    clocks = sampler.stop(tw0, tw1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,6 +299,8 @@ def main():
         e2e = {"value": world * nprob * args.steps / el, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / args.steps}
         assert np.allclose(h_out["poses"], poses_dev, atol=1e-12), "e2e and device-resident arms disagree"
+
+    clocks = sampler.stop(tw0, time.time())      # samples taken during the device-resident and end-to-end timed regions
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
     cpu = None
