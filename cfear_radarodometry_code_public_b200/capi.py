@@ -37,6 +37,10 @@ class RegStats(C.Structure):
                 ("final_cost", C.c_double), ("score", C.c_double)]
 
 
+class CfarParams(C.Structure):
+    _fields_ = [("window_size", C.c_int32), ("nb_guard_cells", C.c_int32), ("false_alarm_rate", C.c_double), ("max_distance", C.c_double)]
+
+
 class SeqParams(C.Structure):
     _fields_ = [("submap_scan_size", C.c_int32), ("use_guess", C.c_int32), ("use_keyframe", C.c_int32), ("reserved", C.c_int32),
                 ("min_keyframe_dist", C.c_double), ("min_keyframe_rot_deg", C.c_double)]
@@ -56,7 +60,7 @@ SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_updat
            "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_dev", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
-           "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
+           "cfear_cfar_filter", "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
 
 _lib = None
 
@@ -107,6 +111,7 @@ def load():
         lib.cfear_odometry_step_batch_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         lib.cfear_stage_timing.argtypes = [vp, i32, vp]
         lib.cfear_last_counts.argtypes = [vp, i32, vp, vp, vp]
+        lib.cfear_cfar_filter.argtypes = [vp, vp, i32, C.POINTER(CfarParams), vp, i32, vp]
         lib.cfear_seq_create.argtypes = [vp, i32, i32, i32, C.POINTER(SeqParams), C.POINTER(C.c_void_p)]
         lib.cfear_seq_destroy.argtypes = [vp]
         lib.cfear_seq_step.argtypes = [vp, vp]
@@ -231,6 +236,15 @@ class Context:
         if peaks:
             out["peaks"] = [pk[i, :npk[i]].copy() for i in range(n)]
         return out
+
+    def cfar_filter(self, polar, window_size=10, nb_guard_cells=20, false_alarm_rate=0.01, max_distance=400.0, capacity=None):
+        polar = np.ascontiguousarray(polar, dtype=np.uint8).reshape(-1, self.A, self.R)
+        n = polar.shape[0]
+        cap = capacity if capacity is not None else 8 * self.cap_pts
+        cp = CfarParams(window_size, nb_guard_cells, false_alarm_rate, max_distance)
+        cloud = np.zeros((n, cap, 4), np.float32); npts = np.zeros(n, np.int32)
+        self._ck(self.lib.cfear_cfar_filter(self.h, _ptr(polar), n, C.byref(cp), _ptr(cloud), cap, _ptr(npts)), "cfear_cfar_filter")
+        return [cloud[i, :npts[i]].copy() for i in range(n)]
 
     def compensate(self, cloud, mot, ccw=False):
         out = np.ascontiguousarray(cloud, dtype=np.float32).copy()

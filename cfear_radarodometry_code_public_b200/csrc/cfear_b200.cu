@@ -18,6 +18,7 @@
 #include "k3_surface.cuh"
 #include "k5_register.cuh"
 #include "k6_fuser.cuh"
+#include "k7_cfar.cuh"
 
 using namespace cfear;
 
@@ -217,6 +218,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
   CK(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+  CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cfg->range_bins + 1) * 4)));
   c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
 #define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
   K5_ATTR(0, 0) K5_ATTR(0, 1) K5_ATTR(0, 2) K5_ATTR(0, 3) K5_ATTR(0, 4) K5_ATTR(0, 5)
@@ -756,6 +758,50 @@ int cfear_last_counts(cfear_ctx* c, int nprob, const int32_t* cur_slots, int32_t
   return CFEAR_OK;
 }
 
+
+// ---- CA-CFAR (alternative filter) ---------------------------------------------------------------------------------
+int cfear_cfar_filter(cfear_ctx* c, const uint8_t* polar, int nscans, const cfear_cfar_params* cp, cfear_point* cloud_out,
+                      int capacity_per_scan, int32_t* npts_out) {
+  ENTER(c);
+  if (!polar || !cp || !npts_out || nscans < 0 || capacity_per_scan < 0) { g_err = "bad argument"; return CFEAR_ERR_ARG; }
+  if (nscans > c->cfg.max_batch) { g_err = "nscans exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (cp->window_size < 1 || cp->nb_guard_cells < 0 || !(cp->false_alarm_rate > 0.0)) { g_err = "bad CFAR parameters"; return CFEAR_ERR_ARG; }
+  if (nscans == 0) return CFEAR_OK;
+  const int A = c->cfg.azimuths, R = c->cfg.range_bins;
+  const size_t rows = (size_t)nscans * A;
+  int32_t *d_cnt = nullptr, *d_off = nullptr, *d_n = nullptr; float4* d_out = nullptr;
+  CK(cudaMallocAsync(&d_cnt, rows * 4, c->stream));
+  CK(cudaMallocAsync(&d_off, rows * 4, c->stream));
+  CK(cudaMallocAsync(&d_n, (size_t)nscans * 4, c->stream));
+  CK(cudaMallocAsync(&d_out, std::max<size_t>((size_t)nscans * capacity_per_scan, 1) * sizeof(float4), c->stream));
+  CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
+  CfarParams p;
+  p.polar = c->d_polar; p.nrows = (int)rows; p.A = A; p.R = R; p.window = cp->window_size; p.guard = cp->nb_guard_cells;
+  const double N = (double)(2 * cp->window_size);
+  p.scaling = N * (pow(cp->false_alarm_rate, -1. / N) - 1.);                 // cfar.cpp:12-16, 31
+  p.range_res = (double)c->cfg.range_res; p.static_threshold = (double)c->cfg.z_min;   // radar_driver.cpp:54 passes the float parameters
+  p.min_distance = (double)c->cfg.min_distance; p.max_distance = cp->max_distance;
+  p.cs = c->d_cs; p.rowcnt = d_cnt; p.rowoff = d_off; p.cloud = d_out; p.cap = capacity_per_scan; p.pass = 0;
+  const size_t smem = (size_t)(R + 1) * 4;
+  k7_cfar<<<(int)rows, K7_THREADS, smem, c->stream>>>(p);
+  k7_offsets<<<nscans, 512, A * sizeof(int), c->stream>>>(d_cnt, A, d_off, d_n);
+  p.pass = 1;
+  k7_cfar<<<(int)rows, K7_THREADS, smem, c->stream>>>(p);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(npts_out, d_n, (size_t)nscans * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int rc = CFEAR_OK;
+  for (int i = 0; i < nscans; ++i)
+    if (npts_out[i] > capacity_per_scan) { g_err = "CFAR cloud exceeds capacity_per_scan (npts_out holds the required sizes)"; rc = CFEAR_ERR_CAPACITY; }
+  if (rc == CFEAR_OK && cloud_out)
+    for (int i = 0; i < nscans; ++i)
+      CK(cudaMemcpyAsync(cloud_out + (size_t)i * capacity_per_scan, d_out + (size_t)i * capacity_per_scan,
+                         (size_t)npts_out[i] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaFreeAsync(d_cnt, c->stream)); CK(cudaFreeAsync(d_off, c->stream)); CK(cudaFreeAsync(d_n, c->stream)); CK(cudaFreeAsync(d_out, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return rc;
+}
 
 // ---- lock-step replay of many independent sequences (OdometryKeyframeFuser semantics on the device) ---------------
 struct cfear_seq {

@@ -190,6 +190,21 @@ int cfear_stage_timing(cfear_ctx* ctx, int enable, float ms_out[3]);
 int cfear_last_counts(cfear_ctx* ctx, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out);
 
 
+/* ---- CA-CFAR (alternative filter, --filter-type CA-CFAR) ------------------------------------------------------------ */
+/* AzimuthCACFAR::getFilteredPointCloud (src/cfear_radarodometry/cfar.cpp:35-83) as dispatched by radarDriver::Process
+ * (radar_driver.cpp:52-56): window / guard cells / false-alarm rate from radarDriver::Parameters (radar_driver.h:43-44);
+ * static threshold = z_min, range_res and min_distance come from the context configuration; max_distance is 400 in the
+ * reference's call.  cloud_out [nscans][capacity_per_scan] in (azimuth, bin) order, npts_out [nscans].  Returns
+ * CFEAR_ERR_CAPACITY (npts_out filled with the needed sizes) if a cloud does not fit. */
+typedef struct cfear_cfar_params {
+  int32_t window_size;        /* 10 */
+  int32_t nb_guard_cells;     /* 20 */
+  double  false_alarm_rate;   /* 0.01 */
+  double  max_distance;       /* 400.0 */
+} cfear_cfar_params;
+int cfear_cfar_filter(cfear_ctx* ctx, const uint8_t* polar, int nscans, const cfear_cfar_params* params,
+                      cfear_point* cloud_out, int capacity_per_scan, int32_t* npts_out);
+
 /* ---- lock-step replay of many independent sequences ------------------------------------------------------------- */
 /* OdometryKeyframeFuser::processFrame (odometrykeyframefuser.cpp:143-259) for nseq sequences advancing together:
  * Compensate with the previous motion, constant-velocity guess, Register against the sliding window of keyframes,

@@ -165,6 +165,8 @@ class Backend {
 };
 
 // ---- radarDriver (radar_driver.h:30-118) ---------------------------------------------------------------------
+typedef enum filter_type { kstrong, CACFAR } filtertype;   // radar_driver.h:24
+
 class radarDriver {
  public:
   class Parameters {
@@ -172,8 +174,11 @@ class radarDriver {
     float z_min = 60;
     float range_res = 0.0438f;
     int azimuths = 400, k_strongest = 12;
+    int nb_guard_cells = 20, window_size = 10;
+    float false_alarm_rate = 0.01f;
     float min_distance = 2.5f, max_distance = 200;
     std::string dataset = "oxford";
+    filtertype filter_type_ = kstrong;
     std::string ToString() {
       std::ostringstream s;
       s << "range res, " << range_res << std::endl << "z min, " << z_min << std::endl << "min distance, " << min_distance << std::endl
@@ -201,6 +206,23 @@ class radarDriver {
     const int cap = cfg.azimuths * cfg.k_strongest;
     cloud_filtered_ = std::make_shared<PointCloud>();
     cloud_filtered_peaks_ = std::make_shared<PointCloud>();
+    if (par.filter_type_ == CACFAR) {                                   // radar_driver.cpp:52-56 (the peaks cloud stays empty)
+      cfear_cfar_params cp; cp.window_size = par.window_size; cp.nb_guard_cells = par.nb_guard_cells;
+      cp.false_alarm_rate = par.false_alarm_rate; cp.max_distance = 400.0;
+      int32_t n = 0;
+      int capacity = 4 * cap;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        cloud_filtered_->points.resize(capacity);
+        const int rc = cfear_cfar_filter(b.ctx(), radar_image_polar.data, 1, &cp, cloud_filtered_->points.data(), capacity, &n);
+        if (rc == CFEAR_OK) break;
+        if (rc != CFEAR_ERR_CAPACITY || attempt == 1) throw std::runtime_error(std::string("cfear_cfar_filter: ") + cfear_last_error());
+        capacity = n;
+      }
+      cloud_filtered_->points.resize(n);
+      cloud_filtered_->stamp = radar_image_polar.stamp;
+      cloud = cloud_filtered_; cloud_peaks = cloud_filtered_peaks_;
+      return;
+    }
     cloud_filtered_->points.resize(cap); cloud_filtered_peaks_->points.resize(cap);
     int32_t n = 0, np = 0;
     if (cfear_filter(b.ctx(), radar_image_polar.data, 1, nullptr, nullptr, cloud_filtered_->points.data(), &n,

@@ -198,3 +198,13 @@ def odometry_sequence(polar, cfg, *, k=12, z_min=60, min_distance=2.5, range_res
     stats = (RegStats * n)()
     lib().orc_odometry_sequence(n, _p(pipe_i), _p(pipe_f), _p(kf_d), _p(ci), _p(cd), _p(polar), _p(poses), _p(kf), C.byref(stats), _p(ncells))
     return dict(poses=poses, keyframe=kf, stats=list(stats), ncells=ncells)
+
+
+def cfar(img, window_size=10, false_alarm_rate=0.01, nb_guard_cells=20, range_res=0.0438, z_min=60.0, min_distance=2.5,
+         max_distance=400.0):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    A, R = img.shape
+    out = np.zeros((A * R, 4), np.float32)
+    n = lib().orc_cfar(_p(img), A, R, int(window_size), C.c_double(false_alarm_rate), int(nb_guard_cells), C.c_float(range_res),
+                       C.c_float(z_min), C.c_float(min_distance), C.c_double(max_distance), _p(out), out.shape[0])
+    return out[:n].copy()

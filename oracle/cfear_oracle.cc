@@ -1074,3 +1074,45 @@ int orc_odometry_sequence(int nscans, const int32_t* pipe_i, const float* pipe_f
   return 0;
 }
 }  // extern "C"
+
+// ----------------------------------------------------------------------------
+// CA-CFAR: AzimuthCACFAR::getFilteredPointCloud (cfar.cpp:35-83), getMean (:73-83),
+// getCAScalingFactor (:12-16), constructed as in radar_driver.cpp:54.
+// ----------------------------------------------------------------------------
+extern "C" int orc_cfar(const uint8_t* img, int A, int R, int window_size, double false_alarm_rate, int nb_guard_cells,
+                        float range_res_f, float static_threshold_f, float min_distance_f, double max_distance,
+                        float* xyzi_out, int capacity) {
+  const double range_resolution = (double)range_res_f, static_threshold = (double)static_threshold_f, min_distance = (double)min_distance_f;
+  const double N = (double)(window_size * 2);
+  const double scaling_factor = N * (std::pow(false_alarm_rate, -1. / N) - 1.);
+  auto get_mean = [&](const uint8_t* az, int start_idx, int end_idx) {
+    double sum = 0., n = 0.;
+    for (int i = start_idx; i < end_idx; i++) { sum += std::pow(double(az[i]), 2.); n += 1.; }
+    return sum / n;
+  };
+  int n = 0;
+  for (int azimuth_nb = 0; azimuth_nb < A; azimuth_nb++) {
+    const uint8_t* az = img + (size_t)azimuth_nb * R;
+    const double theta = (double(azimuth_nb + 1) / A) * 2. * M_PI;
+    for (int range_bin = 0; range_bin < R; range_bin++) {
+      const double range = range_resolution * double(range_bin);
+      const double intensity = double(az[range_bin]);
+      if (range > min_distance && range < max_distance && intensity > static_threshold) {
+        const int ts = std::max(0, range_bin - nb_guard_cells - window_size), te = range_bin - nb_guard_cells;
+        const double trailing_mean = get_mean(az, ts, te);
+        const int fs = range_bin + nb_guard_cells, fe = std::min(R, range_bin + nb_guard_cells + window_size);
+        const double forwarding_mean = get_mean(az, fs, fe);
+        const double mean = (trailing_mean + forwarding_mean) / 2.0;
+        const double threshold = scaling_factor * mean;
+        if (std::pow(intensity, 2.) > threshold) {
+          if (n < capacity) {
+            float* p = xyzi_out + 4 * (size_t)n;
+            p[0] = (float)(range * std::cos(theta)); p[1] = (float)(range * std::sin(theta)); p[2] = 0.f; p[3] = (float)intensity;
+          }
+          ++n;
+        }
+      }
+    }
+  }
+  return n;
+}

@@ -239,3 +239,25 @@ def test_synth_is_seeded():
     b = synth.make_problem_images(11, 1)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert a[0].shape == (2, 400, 3360) and a[0].dtype == np.uint8
+
+
+def test_png_ingestion_conventions(tmp_path):
+    import cv2
+    from cfear_radarodometry_code_public_b200 import io as cio
+    rng = np.random.Generator(np.random.PCG64(1))
+    polar = rng.integers(0, 256, (400, 3768), dtype=np.uint8)
+    ts = (1547120000000000 + np.arange(400) * 625).astype(np.int64)
+    sweep = ((np.arange(400) * 14) % 5600).astype(np.uint16)
+    raw = np.concatenate([ts.view(np.uint8).reshape(400, 8), sweep.view(np.uint8).reshape(400, 2),
+                          np.full((400, 1), 255, np.uint8), polar], 1)
+    p = str(tmp_path / "oxford.png"); cv2.imwrite(p, raw)
+    got, gts, az, valid = cio.load_oxford_png(p)
+    assert np.array_equal(got, polar) and np.array_equal(gts, ts) and valid.all()
+    np.testing.assert_allclose(az, sweep * 2 * np.pi / 5600)
+    ra = rng.integers(0, 256, (3360, 400), dtype=np.uint8)          # MulRan layout: range x azimuth
+    p2 = str(tmp_path / "mulran.png"); cv2.imwrite(p2, ra)
+    rot = cio.load_range_azimuth_png(p2)
+    assert rot.shape == (400, 3360) and rot.flags["C_CONTIGUOUS"]
+    assert np.array_equal(rot, cv2.rotate(ra, cv2.ROTATE_90_COUNTERCLOCKWISE))
+    with pytest.raises(FileNotFoundError):
+        cio.load_oxford_png(str(tmp_path / "missing.png"))

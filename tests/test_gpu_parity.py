@@ -329,3 +329,17 @@ def test_small_max_cells_and_capacity_errors(orc):
     with pytest.raises(capi.CfearError):
         c.filter(np.zeros((2, 400, 3360), np.uint8))                      # exceeds max_batch
     c.close()
+
+
+@pytest.mark.parametrize("window,guard,far", [(10, 20, 0.01), (40, 5, 0.01), (3, 0, 0.2), (10, 70, 0.001)])
+def test_cfar_filter_bit_exact(ctx, orc, imgs, window, guard, far):
+    """CA-CFAR (the reference's alternative filter): detections and fp32 cloud identical to the oracle."""
+    im, _ = imgs
+    both = np.stack([im[0], helpers.adversarial_image(5)])
+    got = ctx.cfar_filter(both, window_size=window, nb_guard_cells=guard, false_alarm_rate=far, capacity=400 * 3360 // 4)
+    for i in range(2):
+        ref = orc.cfar(both[i], window_size=window, nb_guard_cells=guard, false_alarm_rate=far)
+        assert got[i].shape == ref.shape and ref.shape[0] > 0
+        assert np.array_equal(got[i].view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(capi.CfearError):
+        ctx.cfar_filter(both[:1], window_size=3, nb_guard_cells=0, false_alarm_rate=0.2, capacity=5)
