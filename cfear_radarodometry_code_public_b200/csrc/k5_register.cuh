@@ -20,7 +20,7 @@
 
 namespace cfear {
 
-constexpr int K5_THREADS = 256;      // 8 warps per problem, 2 problems resident per SM
+constexpr int K5_THREADS = 192;      // 6 warps per problem, 2 problems resident per SM, 168 registers (spill-free; 256 threads spill and run slower)
 constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
 constexpr int K5_SMEM_BYTES = 100 * 1024;   // dynamic smem per CTA: keyframe NN grids staged by TMA bulk copies
@@ -326,6 +326,7 @@ __device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, doub
   if (bx0 > bx1) return -1;
   for (int by = by0; by <= by1; ++by) {
     const int s = V.gs[bx0 + by * G.nx], e = V.gs[bx1 + by * G.nx + 1];
+#pragma unroll 4
     for (int a = s; a < e; ++a) {
       const float4 m = V.gp[a];
       const float dx = qx - m.x, dy = qy - m.y;
