@@ -24,6 +24,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <memory>
 #include <mutex>
@@ -551,6 +553,61 @@ inline std::string MatToString(const Affine3d& T) {
     for (int c = 0; c < 4; ++c) { s << T(r, c); if (!(r == 2 && c == 3)) s << " "; }
   return s.str();
 }
+
+// ---- trajectory files (eval_trajectory.cpp:169-233): est/NN.txt (KITTI), tum_NN.txt, cov_NN.txt ---------------------
+struct PoseStamped { Affine3d pose; Matrix6d cov; uint32_t sec = 0, nsec = 0; };
+typedef std::vector<PoseStamped> poseStampedVector;
+
+// Eigen::Quaterniond(rotation matrix) -- QuaternionBase::operator=(MatrixBase), same branch structure
+inline void RotationToQuaternion(const Affine3d& T, double& qx, double& qy, double& qz, double& qw) {
+  double q[3];
+  double t = T(0, 0) + T(1, 1) + T(2, 2);
+  if (t > 0) {
+    t = std::sqrt(t + 1.0); qw = 0.5 * t; t = 0.5 / t;
+    q[0] = (T(2, 1) - T(1, 2)) * t; q[1] = (T(0, 2) - T(2, 0)) * t; q[2] = (T(1, 0) - T(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (T(1, 1) > T(0, 0)) i = 1;
+    if (T(2, 2) > T(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(T(i, i) - T(j, j) - T(k, k) + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    qw = (T(k, j) - T(j, k)) * t; q[j] = (T(j, i) + T(i, j)) * t; q[k] = (T(k, i) + T(i, k)) * t;
+  }
+  qx = q[0]; qy = q[1]; qz = q[2];
+}
+
+class EvalTrajectory {
+ public:
+  void CallbackESTEigen(const Affine3d& pose, const Matrix6d& cov, uint32_t sec, uint32_t nsec) {   // eval_trajectory.cpp:56-62
+    PoseStamped p; p.pose = pose; p.cov = cov; p.sec = sec; p.nsec = nsec; est_vek.push_back(p);
+  }
+  static void Write(const std::string& path, const poseStampedVector& v) {                          // :169-183
+    std::ofstream f(path);
+    for (size_t i = 0; i < v.size(); ++i) f << MatToString(v[i].pose) << std::endl;
+  }
+  static void WriteTUM(const std::string& path, const poseStampedVector& v) {                        // :185-212
+    std::ofstream f(path);
+    for (size_t i = 0; i < v.size(); ++i) {
+      f << v[i].sec << "." << std::setfill('0') << std::setw(9) << v[i].nsec << " " << std::setw(0);
+      f << std::fixed << std::setprecision(4);
+      f << v[i].pose(0, 3) << " " << v[i].pose(1, 3) << " " << v[i].pose(2, 3) << " ";
+      double qx, qy, qz, qw; RotationToQuaternion(v[i].pose, qx, qy, qz, qw);
+      f << std::defaultfloat;
+      f << qx << " " << qy << " " << qz << " " << qw;
+      f << std::endl;
+    }
+  }
+  static void WriteCov(const std::string& path, const poseStampedVector& v) {                        // :214-233
+    std::ofstream f(path);
+    for (size_t i = 0; i < v.size(); ++i) {
+      f << v[i].sec << "." << std::setfill('0') << std::setw(9) << v[i].nsec << " " << std::setw(0);
+      for (int k = 0; k < 36; ++k) { f << v[i].cov.m[k]; if (k != 35) f << " "; }   // Eigen IOFormat(StreamPrecision, DontAlignCols, " ", " ")
+      f << std::endl;
+    }
+  }
+  poseStampedVector est_vek;
+};
 
 }  // namespace CFEAR_Radarodometry
 #endif  // CFEAR_B200_HPP_

@@ -261,3 +261,28 @@ def test_png_ingestion_conventions(tmp_path):
     assert np.array_equal(rot, cv2.rotate(ra, cv2.ROTATE_90_COUNTERCLOCKWISE))
     with pytest.raises(FileNotFoundError):
         cio.load_oxford_png(str(tmp_path / "missing.png"))
+
+
+def test_trajectory_writers_match_reference_formats(tmp_path):
+    """est (KITTI, fixed 6 decimals), tum (sec.nsec9 x y z [fixed 4] qx qy qz qw [defaultfloat, precision 4]) and
+    cov (36 numbers, stream precision 6) rows as EvalTrajectory::Write / WriteTUM / WriteCov produce them."""
+    import subprocess
+    exe = str(tmp_path / "writer_test")
+    pkg = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "writer_test.cpp"),
+                           "-o", exe, "-L" + pkg, "-lcfear_b200", "-Wl,-rpath," + pkg])
+    est, tum, cov = (str(tmp_path / n) for n in ("est.txt", "tum.txt", "cov.txt"))
+    subprocess.check_call([exe, est, tum, cov])
+    rows = open(est).read().strip().split("\n")
+    c, s = np.cos(0.3), np.sin(0.3)
+    assert rows[0] == "%.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f" % (c, -s, 0, 1.23456789, s, c, 0, -2.5, 0, 0, 1, 0)
+    t = open(tum).read().strip().split("\n")
+    assert t[0] == "1547120000.000000625 1.2346 -2.5000 0.0000 0 0 %.4g %.4g" % (np.sin(0.15), np.cos(0.15))
+    # yaw = -2.9: trace <= 0 -> Eigen's largest-diagonal branch: qz > 0, qw < 0
+    f = t[1].split(" ")
+    assert f[0] == "1547120001.250000000" and f[1:4] == ["100.0000", "0.0000", "0.0000"]
+    assert float(f[6]) > 0 and float(f[7]) < 0
+    np.testing.assert_allclose([float(f[6]), float(f[7])], [-np.sin(-1.45), -np.cos(-1.45)], rtol=2e-4)
+    cr = open(cov).read().strip().split("\n")[0].split(" ")
+    assert cr[0] == "1547120000.000000625" and len(cr) == 37
+    assert cr[1] == "0.0123457" and cr[6] == "-1.5e-07" and cr[36] == "0.0001" and cr[2] == "0"
