@@ -279,6 +279,7 @@ def main():
     # ---- end-to-end arm: host buffers through the public C-ABI call ----
     e2e = None
     if not args.no_e2e:
+        numa = capi.bind_to_device_numa(local) if world > 1 else {"numa_node": None, "reason": "single GPU"}
         h_polar = capi.pinned_array(batch["polar"].shape, np.uint8); h_polar[...] = batch["polar"]
         h_out = dict(poses=capi.pinned_array((nprob, K + 1, 3), np.float64), cov=capi.pinned_array((nprob, 36), np.float64),
                      stats=capi.pinned_array((nprob,), capi.STATS_DTYPE), npts=capi.pinned_array((nprob,), np.int32))
@@ -297,7 +298,7 @@ def main():
         h2d = h_polar.nbytes + batch["mot"].nbytes + kf_slots.nbytes + cur_slots.nbytes + batch["poses"].nbytes
         d2h = h_out["poses"].nbytes + h_out["cov"].nbytes + h_out["stats"].nbytes + h_out["npts"].nbytes
         e2e = {"value": world * nprob * args.steps / el, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / args.steps}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / args.steps, "host_numa_binding": numa}
         assert np.allclose(h_out["poses"], poses_dev, atol=1e-12), "e2e and device-resident arms disagree"
 
     clocks = sampler.stop(tw0, time.time())      # samples taken during the device-resident and end-to-end timed regions

@@ -141,6 +141,30 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def bind_to_device_numa(device: int) -> dict:
+    """Pin the calling process to the CPU cores of the NUMA node the GPU hangs off, so that page-locked host buffers
+    allocated afterwards (first touch) sit next to the GPU's PCIe root port.  Plumbing for multi-GPU hosts where eight
+    ranks stream images host->device at once; a no-op (returns the reason) when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "reason": "single node"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "reason": "no allowed cpu on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "reason": repr(e)[:80]}
+
+
 def pinned_array(shape, dtype):
     """numpy array over page-locked host memory (freed when the array is garbage collected)."""
     lib = load()
