@@ -343,3 +343,35 @@ def test_cfar_filter_bit_exact(ctx, orc, imgs, window, guard, far):
         assert np.array_equal(got[i].view(np.uint32), ref.view(np.uint32))
     with pytest.raises(capi.CfearError):
         ctx.cfar_filter(both[:1], window_size=3, nb_guard_cells=0, false_alarm_rate=0.2, capacity=5)
+
+
+def test_degenerate_images_through_the_whole_path(orc):
+    """Empty, saturated and pure-noise images must neither crash nor diverge from the oracle: empty clouds give empty
+    cell sets and a failed registration that leaves the guess untouched (the fuser then keeps the guess)."""
+    K, radius = 2, 3.0
+    base = helpers.scan_images(9, K)[0]
+    rng = np.random.Generator(np.random.PCG64(3))
+    cur_imgs = np.stack([np.zeros((400, 3360), np.uint8), np.full((400, 3360), 255, np.uint8),
+                         rng.integers(0, 256, (400, 3360), dtype=np.uint8), base[K]])
+    n = cur_imgs.shape[0]
+    c = capi.Context(max_batch=n, max_cellsets=K + n, max_keyframes=K, radius=radius, cost="P2L")
+    kf_sets = []
+    for i in range(K):
+        c.scans_to_cells_batch(base[i][None], None, [i])
+        kf_sets.append(helpers.oracle_cells(orc, base[i], radius=radius)[1])
+    kf = np.tile(np.arange(K, dtype=np.int32), (n, 1)); cur = (K + np.arange(n)).astype(np.int32)
+    poses = np.tile(np.array([[0, 0, 0], [2.5, 0, 0.02], [5.0, 0.1, 0.04]], np.float64), (n, 1, 1))
+    mot = np.tile(np.array([2.5, 0.0, 0.02]), (n, 1))
+    out = c.odometry_step_batch(cur_imgs, mot, kf, cur, poses)
+    ref = orc.pipeline_batch(cur_imgs, mot, kf_sets, np.tile(np.arange(K, dtype=np.int32), (n, 1)), poses, orc.reg_cfg(cost="P2L"), radius=radius)
+    npts, ncells = c.last_counts(cur)
+    assert np.array_equal(npts, ref["npts"]) and np.array_equal(ncells, ref["ncells"])
+    assert npts[0] == 0 and ncells[0] == 0 and npts[1] == 400 * 12
+    for b in range(n):
+        assert out["stats"]["success"][b] == ref["stats"][b].success
+        assert out["stats"]["num_residuals"][b] == ref["stats"][b].num_residuals
+        d = out["poses"][b, K] - ref["poses"][b, K]
+        assert np.hypot(d[0], d[1]) < POS_TOL and abs(d[2]) < ROT_TOL
+    assert out["stats"]["success"][0] == 0 and np.array_equal(out["poses"][0], poses[0])     # nothing to register: guess untouched
+    assert out["stats"]["success"][3] == 1
+    c.close()
