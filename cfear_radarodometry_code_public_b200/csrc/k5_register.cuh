@@ -139,19 +139,28 @@ __device__ __forceinline__ void accumulate(double loss_limit, double cs, double 
   }
 }
 
-// Block-wide evaluation over the residual list at x.  Loads of two residual blocks are issued before either
-// is consumed (the list lives in L2).  s_part: [2][K5_WARPS][10]; parity toggles per call -> one
-// __syncthreads per evaluation.  Deterministic: fixed per-thread order, xor-butterfly, fixed cross-warp order.
-template <int COST, int LOSS, bool JAC>
-__device__ __forceinline__ void block_evaluate(double loss_limit, const ResList& res,
-                                               int nres, const double x[3], EvalOut& ev, double* s_part, int& parity
-#ifdef CFEAR_K5_PROFILE
-                                               , long long* prof
-#endif
-                                               ) {
-  PROF_T(t0);
-  double cs, sn; sincos(x[2], &sn, &cs);
-  PROF_T(t1);
+// ---- evaluation service -------------------------------------------------------------------------------------------
+// The scalar trust-region arithmetic (a few hundred dependent fp64 instructions per LM iteration: a 3x3 Cholesky,
+// divisions, square roots, sincos of the candidate yaw) runs in WARP 0 ONLY; replicated in every warp it saturates the
+// FP64 pipe shared by the two resident problems and becomes the longest part of an iteration.  Warp 0 publishes the
+// point to evaluate (x, cos psi, sin psi) in shared memory and raises barrier A; every warp (warp 0 included) then
+// accumulates its share of the residual list, reduces it by xor-butterfly, lane 0 stores the 10 partial sums, barrier B;
+// warp 0 adds the K5_WARPS partials in fixed order.  Bit-reproducible: fixed per-thread order, fixed tree, fixed order.
+struct LMShared {
+  double bc[5];            // x0, x1, psi, cos psi, sin psi of the requested evaluation
+  int ctl, pad;            // 1 = evaluate, 0 = done
+  double out_x[3];         // results broadcast at the end of a solve
+  double out_final_cost, out_last_rel;
+  int out_niter, out_usable, out_success, out_inner;
+};
+
+__device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+
+// every warp: this thread's share of the list at (x, cs, sn) -> per-warp partial sums in s_part[warp][10]
+template <int COST, int LOSS>
+__device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& res, int nres, const double x[3], double cs,
+                                             double sn, double* s_part) {
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
@@ -160,41 +169,54 @@ __device__ __forceinline__ void block_evaluate(double loss_limit, const ResList&
     const int r2 = r + K5_THREADS;
     const double2 p0 = res.ld(0, r), q0 = res.ld(1, r), ab0 = res.ld(2, r), cw0 = res.ld(3, r);
     const double2 p1 = res.ld(0, r2), q1 = res.ld(1, r2), ab1 = res.ld(2, r2), cw1 = res.ld(3, r2);
-    accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
-    accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
+    accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
+    accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
   }
-  if (r < nres) accumulate<COST, LOSS, JAC>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
-  PROF_T(t2);
-  constexpr int nv = JAC ? 10 : 1;
-  double* part = s_part + parity * (K5_WARPS * 10);
-  parity ^= 1;
+  if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
 #pragma unroll
-  for (int i = 0; i < nv; ++i) {
+  for (int i = 0; i < 10; ++i) {
     const double v = warp_sum(acc[i]);
-    if (lane_id() == 0) part[warp_id() * 10 + i] = v;
+    if (lane_id() == 0) s_part[warp_id() * 10 + i] = v;
   }
-  __syncthreads();
-  // cross-warp sum in fixed order: lane i (< nv) of every warp adds the K5_WARPS partials of value i, then the
-  // totals are broadcast inside the warp (every warp computes the same bits)
+}
+
+// warp 0 only: evaluate cost + normal equations at y
+template <int COST, int LOSS>
+__device__ __forceinline__ void request_eval(double loss_limit, const ResList& res, int nres, const double y[3], EvalOut& ev,
+                                             LMShared* sh, double* s_part) {
+  double cs, sn; sincos(y[2], &sn, &cs);
+  if (lane_id() == 0) { sh->bc[0] = y[0]; sh->bc[1] = y[1]; sh->bc[2] = y[2]; sh->bc[3] = cs; sh->bc[4] = sn; sh->ctl = 1; }
+  bar_a();
+  eval_contrib<COST, LOSS>(loss_limit, res, nres, y, cs, sn, s_part);
+  bar_b();
   double mine = 0.0;
-  if (lane_id() < nv) {
+  if (lane_id() < 10) {
 #pragma unroll
-    for (int w = 0; w < K5_WARPS; ++w) mine += part[w * 10 + lane_id()];
+    for (int w = 0; w < K5_WARPS; ++w) mine += s_part[w * 10 + lane_id()];
   }
-  double tot[10];
+  ev.cost = __shfl_sync(FULL, mine, 0);
 #pragma unroll
-  for (int i = 0; i < nv; ++i) tot[i] = __shfl_sync(FULL, mine, i);
-  PROF_T(t3);
-#ifdef CFEAR_K5_PROFILE
-  PROF_ADD(prof[0], t0, t1); PROF_ADD(prof[1], t1, t2); PROF_ADD(prof[2], t2, t3); prof[3] += 1;
-#endif
-  ev.cost = tot[0];
-  if constexpr (JAC) {
+  for (int i = 0; i < 6; ++i) ev.H[i] = __shfl_sync(FULL, mine, 1 + i);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
+  for (int i = 0; i < 3; ++i) ev.g[i] = __shfl_sync(FULL, mine, 7 + i);
+}
+
+// warps 1..: serve evaluations until warp 0 signals completion
+template <int COST, int LOSS>
+__device__ __forceinline__ void serve_evals(double loss_limit, const ResList& res, int nres, LMShared* sh, double* s_part) {
+  for (;;) {
+    bar_a();
+    if (sh->ctl == 0) break;
+    const double y[3] = {sh->bc[0], sh->bc[1], sh->bc[2]};
+    eval_contrib<COST, LOSS>(loss_limit, res, nres, y, sh->bc[3], sh->bc[4], s_part);
+    bar_b();
   }
+}
+
+// warp 0 only: end of a serving episode
+__device__ __forceinline__ void finish_evals(LMShared* sh) {
+  if (lane_id() == 0) sh->ctl = 0;
+  bar_a();
 }
 
 // Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal square root per pivot.
@@ -220,12 +242,13 @@ __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3]
 
 struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usable; };
 
-// Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc),
-// block-uniform control flow.  The candidate point is evaluated with its Jacobian in the same pass, so an
-// accepted step needs no second pass over the residuals (the sums are the ones a re-evaluation would give).
+// Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc); executed by
+// warp 0 (all lanes redundantly), evaluations through request_eval.  The candidate point is evaluated with its
+// Jacobian in the same pass, so an accepted step needs no second pass over the residuals (the sums are the ones a
+// re-evaluation would give).
 template <int COST, int LOSS>
 __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                         double* s_part, int& parity PROF_PARAM) {
+                                         LMShared* sh, double* s_part) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -235,7 +258,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
   EvalOut ev;
-  block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
+  request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -282,7 +305,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     EvalOut evc;
-    block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, xc, evc, s_part, parity PROF_ARG);
+    request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part);
     const double cand_cost = evc.cost;
     const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
@@ -439,7 +462,8 @@ template <int COST, int LOSS>
 __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
-  __shared__ double s_part[2 * K5_WARPS * 10];
+  __shared__ double s_part[K5_WARPS * 10];
+  __shared__ LMShared s_lm;
   __shared__ double s_pose[K5_MAXSCANS * 5];
   __shared__ NNGrid s_grid[K5_MAXSCANS];
   __shared__ GridView s_view[K5_MAXSCANS];
@@ -522,7 +546,8 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   res.cap_s = min(((int)P.smem_bytes - (int)s_misc_off) / 64, P.res_cap);
   int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
-  int parity = 0;
+  const bool w0 = warp_id() == 0;              // the warp that runs the scalar solver logic (see "evaluation service")
+  LMShared* sh = &s_lm;
 
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
   bool success = true;
@@ -533,19 +558,38 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     for (it = 1; it <= P.gn_iters; ++it) {
       nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp, K PROF_ARG);
       if (nres * per_block <= 1) { success = false; break; }
-      EvalOut ev;
-      block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
-      double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
-      if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
-      x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
-      sum.final_cost = ev.cost;
+      if (w0) {
+        EvalOut ev;
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+        double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
+        const bool ok = chol3_solve(ev.H, nb, y);
+        if (lane_id() == 0) {
+          sh->out_success = ok ? 1 : 0; sh->out_final_cost = ev.cost;
+          sh->out_x[0] = x[0] + (ok ? y[0] : 0.0); sh->out_x[1] = x[1] + (ok ? y[1] : 0.0); sh->out_x[2] = x[2] + (ok ? y[2] : 0.0);
+        }
+        finish_evals(sh);
+      } else {
+        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+      }
+      const bool ok = sh->out_success != 0;
+      x[0] = sh->out_x[0]; x[1] = sh->out_x[1]; x[2] = sh->out_x[2];
+      sum.final_cost = sh->out_final_cost;
+      __syncthreads();                           // outputs consumed before the next episode rewrites them
+      if (!ok) { success = false; break; }
       inner_total++;
     }
     outer = it;
     if (success) {
-      EvalOut ev;
-      block_evaluate<COST, LOSS, false>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
-      sum.final_cost = ev.cost;
+      if (w0) {
+        EvalOut ev;
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+        if (lane_id() == 0) sh->out_final_cost = ev.cost;
+        finish_evals(sh);
+      } else {
+        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+      }
+      sum.final_cost = sh->out_final_cost;
+      __syncthreads();
     }
   } else {
     double prev_par[3] = {x[0], x[1], x[2]};
@@ -557,7 +601,21 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
       PROF_T(tb1);
       PROF_ADD(prof[4], tb0, tb1);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
-      lm_solve<COST, LOSS>(P, res, nres, x, sum, s_part, parity PROF_ARG);               // :117
+      if (w0) {
+        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part);                 // :117
+        if (lane_id() == 0) {
+          sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
+          sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
+          sh->out_niter = sum.n_iterations; sh->out_usable = sum.usable ? 1 : 0;
+        }
+        finish_evals(sh);
+      } else {
+        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+      }
+      x[0] = sh->out_x[0]; x[1] = sh->out_x[1]; x[2] = sh->out_x[2];
+      sum.final_cost = sh->out_final_cost; sum.last_rel = sh->out_last_rel;
+      sum.n_iterations = sh->out_niter; sum.usable = sh->out_usable != 0;
+      __syncthreads();                           // outputs consumed before the next episode rewrites them
       success = sum.usable;
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
@@ -583,22 +641,27 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   if (success) {
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
-    EvalOut ev;                                                                 // GetCovariance :392-433
-    block_evaluate<COST, LOSS, true>(P.loss_limit, res, nres, x, ev, s_part, parity PROF_ARG);
-    double inv[9]; bool ok = true;
-    for (int c = 0; c < 3 && ok; ++c) {
-      double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
-      ok = chol3_solve(ev.H, e, y);
-      inv[0 + c] = y[0]; inv[3 + c] = y[1]; inv[6 + c] = y[2];
-    }
-    if (ok && st.num_residuals - 3 != 0) {
-      const double f = 30 * (sum.final_cost / (st.num_residuals - 3));          // :418
+    if (w0) {
+      EvalOut ev;                                                               // GetCovariance :392-433
+      request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+      finish_evals(sh);
+      double inv[9]; bool ok = true;
+      for (int c = 0; c < 3 && ok; ++c) {
+        double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
+        ok = chol3_solve(ev.H, e, y);
+        inv[0 + c] = y[0]; inv[3 + c] = y[1]; inv[6 + c] = y[2];
+      }
+      if (ok && st.num_residuals - 3 != 0) {
+        const double f = 30 * (sum.final_cost / (st.num_residuals - 3));        // :418
 #pragma unroll
-      for (int i = 0; i < 36; ++i) cov[i] = 0.0;
-      for (int i = 0; i < 6; ++i) cov[i * 6 + i] = 1.0;
-      cov[0] = f * inv[0]; cov[1] = f * inv[1]; cov[6] = f * inv[3]; cov[7] = f * inv[4];
-      cov[35] = f * inv[8]; cov[5] = f * inv[2]; cov[30] = f * inv[6];
-      st.success = 1;
+        for (int i = 0; i < 36; ++i) cov[i] = 0.0;
+        for (int i = 0; i < 6; ++i) cov[i * 6 + i] = 1.0;
+        cov[0] = f * inv[0]; cov[1] = f * inv[1]; cov[6] = f * inv[3]; cov[7] = f * inv[4];
+        cov[35] = f * inv[8]; cov[5] = f * inv[2]; cov[30] = f * inv[6];
+        st.success = 1;
+      }
+    } else {
+      serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
     }
   }
   if (tid == 0) {
@@ -607,7 +670,6 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     double* c36 = P.cov36 + (size_t)prob * 36;
     for (int i = 0; i < 36; ++i) c36[i] = cov[i];
 #ifdef CFEAR_K5_PROFILE
-    c36[8] = (double)prof[0]; c36[9] = (double)prof[1]; c36[10] = (double)prof[2]; c36[11] = (double)prof[3];
     c36[13] = (double)prof[4]; c36[15] = (double)(clock64() - tk0);
     c36[14] = (double)prof[5]; c36[16] = (double)prof[6]; c36[17] = (double)prof[7];
 #endif
