@@ -25,13 +25,30 @@ def _one(args):
     return imgs, poses
 
 
+def _cuda_live() -> bool:
+    import sys
+    t = sys.modules.get("torch")
+    try:
+        if t is not None and t.cuda.is_initialized():
+            return True
+    except Exception:
+        pass
+    from . import capi
+    return capi._lib is not None          # the C-ABI library (and with it a CUDA context) has been loaded
+
+
 def make_batch(nprob: int, K: int = 4, seed0: int = 0, workers: int | None = None):
     """Returns dict(kf_polar [nprob,K,A,R] u8, polar [nprob,A,R] u8, poses [nprob,K+1,3] (last = guess),
     truth [nprob,3], mot [nprob,3])."""
     if workers is None:
         workers = min(nprob, max(1, (os.cpu_count() or 1)))
     jobs = [(seed0 + b, K) for b in range(nprob)]
-    if workers > 1:
+    if workers > 1 and _cuda_live():
+        # forking a process that already holds CUDA / its helper threads is unsafe: use threads (numpy releases the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(workers) as ex:
+            res = list(ex.map(_one, jobs))
+    elif workers > 1:
         with mp.get_context("fork").Pool(workers) as pool:
             res = pool.map(_one, jobs, chunksize=max(1, nprob // (4 * workers)))
     else:
