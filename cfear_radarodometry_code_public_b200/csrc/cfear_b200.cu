@@ -221,9 +221,13 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cfg->range_bins + 1) * 4)));
   c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
 #define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
+#ifdef CFEAR_K5_MINIMAL      /* experiment builds (profiles/ab): only the bench's P2D / Huber instantiation */
+  K5_ATTR(2, 1)
+#else
   K5_ATTR(0, 0) K5_ATTR(0, 1) K5_ATTR(0, 2) K5_ATTR(0, 3) K5_ATTR(0, 4) K5_ATTR(0, 5)
   K5_ATTR(1, 0) K5_ATTR(1, 1) K5_ATTR(1, 2) K5_ATTR(1, 3) K5_ATTR(1, 4) K5_ATTR(1, 5)
   K5_ATTR(2, 0) K5_ATTR(2, 1) K5_ATTR(2, 2) K5_ATTR(2, 3) K5_ATTR(2, 4) K5_ATTR(2, 5)
+#endif
 #undef K5_ATTR
 
   const size_t rows = (size_t)B * A;
@@ -396,9 +400,14 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   p.smem_bytes = c->k5_smem;
 #define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); break;
   switch (p.cost * 6 + p.loss) {
+#ifdef CFEAR_K5_MINIMAL
+    K5_CASE(2, 1)
+    default: g_err = "experiment build: only P2D / Huber is instantiated"; return CFEAR_ERR_ARG;
+#else
     K5_CASE(0, 0) K5_CASE(0, 1) K5_CASE(0, 2) K5_CASE(0, 3) K5_CASE(0, 4) K5_CASE(0, 5)
     K5_CASE(1, 0) K5_CASE(1, 1) K5_CASE(1, 2) K5_CASE(1, 3) K5_CASE(1, 4) K5_CASE(1, 5)
     K5_CASE(2, 0) K5_CASE(2, 1) K5_CASE(2, 2) K5_CASE(2, 3) K5_CASE(2, 4) K5_CASE(2, 5)
+#endif
   }
 #undef K5_CASE
   c->launches++;

@@ -20,10 +20,13 @@
 
 namespace cfear {
 
-constexpr int K5_THREADS = 192;      // 6 warps per problem, 2 problems resident per SM, 168 registers (spill-free; 256 threads spill and run slower)
+#ifndef CFEAR_K5_THREADS
+#define CFEAR_K5_THREADS 192
+#endif
+constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 6 warps per problem, 2 problems resident per SM, 168 registers
 constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
-constexpr int K5_SMEM_BYTES = 100 * 1024;   // dynamic smem per CTA: keyframe NN grids staged by TMA bulk copies
+constexpr int K5_SMEM_BYTES = 106 * 1024;   // dynamic smem per CTA (2 CTAs + 6 KB static each fit the 228 KB of an SM)
 
 struct RegParams {
   CellPool pool;
@@ -52,7 +55,9 @@ template <int LOSS>
 __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
   if constexpr (LOSS == 1) {            // HuberLoss
     const double b = a * a;
-    if (s > b) { const double r = sqrt(s); rho[0] = 2.0 * a * r - b; rho[1] = fmax(2.2250738585072014e-308, a / r); rho[2] = -rho[1] / (2.0 * s); }
+    // sqrt(s) = s * rsqrt(s), a / sqrt(s) = a * rsqrt(s): one reciprocal square root instead of a square root and a
+    // division per outlier (each within an ulp of the library forms; the unused rho[2] is dead code)
+    if (s > b) { const double ri = rsqrt(s); rho[0] = fma(2.0 * a, s * ri, -b); rho[1] = fmax(2.2250738585072014e-308, a * ri); rho[2] = -rho[1] / (2.0 * s); }
     else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
   } else if constexpr (LOSS == 2) {     // CauchyLoss
     const double b = a * a, c = 1.0 / b;
@@ -85,8 +90,8 @@ struct ResList {
   __device__ __forceinline__ double2 ld(int f, int r) const { return r < cap_s ? s[f * cap_s + r] : g[(size_t)f * cap_g + r]; }
   __device__ __forceinline__ void st(int f, int r, double2 v) const { if (r < cap_s) s[f * cap_s + r] = v; else g[(size_t)f * cap_g + r] = v; }
 };
+// -DCFEAR_K5_PROFILE: clock64 probes (thread 0's view), reported through unused covariance slots; profiles/ab_stage.py --prof
 #ifdef CFEAR_K5_PROFILE
-__device__ long long g_prof_dummy;
 #define PROF_T(v) const long long v = clock64()
 #define PROF_ADD(acc, a, b) (acc) += (b) - (a)
 #define PROF_ARG , prof
@@ -99,42 +104,59 @@ __device__ long long g_prof_dummy;
 #endif
 
 
+// Row j of a residual block, loss-corrected weight wr = w rho'(s): adds wr j^T j to the packed upper triangle
+// acc[1..6] = (xx, xy, xt, yy, yt, tt) and wr j r to acc[7..9].  Z0 / Z1: the row's d/dx / d/dy entry is the constant 0
+// (its products are not formed at all).  Explicit FMAs: the file is compiled with -fmad=false for the fp32 / point
+// arithmetic that has to round like the reference's x86 build, but these sums have no such contract (their order
+// already differs from a sequential CPU sum) and the FP64 pipe (64 lanes per SM) is what bounds an evaluation pass.
+template <bool Z0, bool Z1>
+__device__ __forceinline__ void add_row(double wr, double j0, double j1, double j2, double r, double acc[10]) {
+  if constexpr (!Z0) {
+    const double u0 = wr * j0;
+    acc[1] = fma(u0, j0, acc[1]);
+    if constexpr (!Z1) acc[2] = fma(u0, j1, acc[2]);
+    acc[3] = fma(u0, j2, acc[3]);
+    acc[7] = fma(u0, r, acc[7]);
+  }
+  if constexpr (!Z1) {
+    const double u1 = wr * j1;
+    acc[4] = fma(u1, j1, acc[4]);
+    acc[5] = fma(u1, j2, acc[5]);
+    acc[8] = fma(u1, r, acc[8]);
+  }
+  const double u2 = wr * j2;
+  acc[6] = fma(u2, j2, acc[6]);
+  acc[9] = fma(u2, r, acc[9]);
+}
+
 // One residual block's contribution at x (cs = cos psi, sn = sin psi): cost and (optionally) normal equations.
 // Residuals / Jacobians: n_scan_normal.h:180-255, 330-361; loss: ScaledLoss(w) around the base loss with
 // Ceres' corrector in its rho'' <= 0 form (rows scaled by sqrt(w rho')).
 template <int COST, int LOSS, bool JAC>
 __device__ __forceinline__ void accumulate(double loss_limit, double cs, double sn, const double x[3], double2 p, double2 q,
                                            double2 ab, double2 cw, double acc[10]) {
-  const double rx = cs * p.x - sn * p.y, ry = sn * p.x + cs * p.y;
+  const double rx = fma(cs, p.x, -(sn * p.y)), ry = fma(sn, p.x, cs * p.y);
   const double ex = rx + x[0] - q.x, ey = ry + x[1] - q.y;
-  const double dpx = -ry, dpy = rx;
+  // d(R p)/d psi = (-ry, rx)
   const double a = ab.x, b = ab.y, c = cw.x, w = cw.y;
-  double r0, r1 = 0.0, J0[3], J1[3] = {0, 0, 0};
-  if constexpr (COST == 1) {
-    r0 = ex * a + ey * b;
-    J0[0] = a; J0[1] = b; J0[2] = dpx * a + dpy * b;
-  } else if constexpr (COST == 2) {
-    r0 = a * ex; r1 = b * ex + c * ey;
-    J0[0] = a; J0[1] = 0.0; J0[2] = a * dpx;
-    J1[0] = b; J1[1] = c; J1[2] = b * dpx + c * dpy;
-  } else {
-    r0 = -ex; r1 = -ey;
-    J0[0] = -1.0; J0[1] = 0.0; J0[2] = -dpx;
-    J1[0] = 0.0; J1[1] = -1.0; J1[2] = -dpy;
-  }
-  const double s = r0 * r0 + r1 * r1;
+  double r0, r1 = 0.0;
+  if constexpr (COST == 1) r0 = fma(ex, a, ey * b);
+  else if constexpr (COST == 2) { r0 = a * ex; r1 = fma(b, ex, c * ey); }
+  else { r0 = -ex; r1 = -ey; }
+  const double s = fma(r0, r0, r1 * r1);
   double rho[3];
   loss_eval<LOSS>(loss_limit, s, rho);
-  acc[0] += 0.5 * w * rho[0];
+  acc[0] = fma(0.5 * w, rho[0], acc[0]);
   if constexpr (JAC) {
     const double wr = w * rho[1];
-    acc[1] += wr * J0[0] * J0[0]; acc[2] += wr * J0[0] * J0[1]; acc[3] += wr * J0[0] * J0[2];
-    acc[4] += wr * J0[1] * J0[1]; acc[5] += wr * J0[1] * J0[2]; acc[6] += wr * J0[2] * J0[2];
-    acc[7] += wr * J0[0] * r0; acc[8] += wr * J0[1] * r0; acc[9] += wr * J0[2] * r0;
-    if constexpr (COST != 1) {
-      acc[1] += wr * J1[0] * J1[0]; acc[2] += wr * J1[0] * J1[1]; acc[3] += wr * J1[0] * J1[2];
-      acc[4] += wr * J1[1] * J1[1]; acc[5] += wr * J1[1] * J1[2]; acc[6] += wr * J1[2] * J1[2];
-      acc[7] += wr * J1[0] * r1; acc[8] += wr * J1[1] * r1; acc[9] += wr * J1[2] * r1;
+    if constexpr (COST == 1) {
+      add_row<false, false>(wr, a, b, fma(rx, b, -(ry * a)), r0, acc);                  // J = (a, b, dpx a + dpy b)
+    } else if constexpr (COST == 2) {
+      add_row<false, true>(wr, a, 0.0, -(a * ry), r0, acc);                             // J0 = (a, 0, a dpx)
+      add_row<false, false>(wr, b, c, fma(c, rx, -(b * ry)), r1, acc);                  // J1 = (b, c, b dpx + c dpy)
+    } else {
+      add_row<false, true>(wr, -1.0, 0.0, ry, r0, acc);                                 // J0 = (-1, 0, -dpx)
+      add_row<true, false>(wr, 0.0, -1.0, -rx, r1, acc);                                // J1 = (0, -1, -dpy)
     }
   }
 }
@@ -157,6 +179,26 @@ struct LMShared {
 __device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
 __device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
 
+// Warp reduction of the 10 sums by recursive halving: at each step a lane hands the half of its values its partner
+// keeps to that partner, so 5+3+2+1+1 = 12 exchanges replace the 50 of ten separate butterflies.  Ends with sum i in the
+// even lane whose bits (16,8,4,2) encode i; fixed tree, so the result is bit-reproducible.
+__device__ __forceinline__ double xchg_add(bool upper, double lo, double hi, int d) {
+  const double send = upper ? lo : hi, keep = upper ? hi : lo;
+  return keep + __shfl_xor_sync(FULL, send, d);
+}
+__device__ __forceinline__ void warp_reduce10(const double acc[10], double* s_part_warp) {
+  const int l = lane_id();
+  const bool b4 = l & 16, b3 = l & 8, b2 = l & 4, b1 = l & 2;
+  const double v0 = xchg_add(b4, acc[0], acc[5], 16), v1 = xchg_add(b4, acc[1], acc[6], 16), v2 = xchg_add(b4, acc[2], acc[7], 16),
+               v3 = xchg_add(b4, acc[3], acc[8], 16), v4 = xchg_add(b4, acc[4], acc[9], 16);
+  const double w0 = xchg_add(b3, v0, v3, 8), w1 = xchg_add(b3, v1, v4, 8), w2 = xchg_add(b3, v2, 0.0, 8);   // (v0 v1 v2 | v3 v4 -)
+  const double u0 = xchg_add(b2, w0, w2, 4), u1 = xchg_add(b2, w1, 0.0, 4);                                 // (w0 w1 | w2 -)
+  double t = xchg_add(b1, u0, u1, 2);                                                                       // (u0 | u1)
+  t += __shfl_xor_sync(FULL, t, 1);
+  const bool pad = b2 && (b1 || b3);
+  if (!(l & 1) && !pad) s_part_warp[(b4 ? 5 : 0) + (b3 ? 3 + (b1 ? 1 : 0) : (b2 ? 2 : 0) + (b1 ? 1 : 0))] = t;
+}
+
 // every warp: this thread's share of the list at (x, cs, sn) -> per-warp partial sums in s_part[warp][10]
 template <int COST, int LOSS>
 __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& res, int nres, const double x[3], double cs,
@@ -173,32 +215,37 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
     accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
   }
   if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const double v = warp_sum(acc[i]);
-    if (lane_id() == 0) s_part[warp_id() * 10 + i] = v;
-  }
+  warp_reduce10(acc, s_part + warp_id() * 10);
 }
 
 // warp 0 only: evaluate cost + normal equations at y
 template <int COST, int LOSS>
 __device__ __forceinline__ void request_eval(double loss_limit, const ResList& res, int nres, const double y[3], EvalOut& ev,
-                                             LMShared* sh, double* s_part) {
+                                             LMShared* sh, double* s_part PROF_PARAM) {
+  PROF_T(te0);
   double cs, sn; sincos(y[2], &sn, &cs);
   if (lane_id() == 0) { sh->bc[0] = y[0]; sh->bc[1] = y[1]; sh->bc[2] = y[2]; sh->bc[3] = cs; sh->bc[4] = sn; sh->ctl = 1; }
+  PROF_T(te1);
   bar_a();
   eval_contrib<COST, LOSS>(loss_limit, res, nres, y, cs, sn, s_part);
+  PROF_T(te2);
   bar_b();
-  double mine = 0.0;
-  if (lane_id() < 10) {
+  PROF_T(te3);
+  PROF_ADD(prof[4], te0, te1); PROF_ADD(prof[5], te1, te2); PROF_ADD(prof[6], te2, te3); prof[7] += 1;
+  // every lane adds the K5_WARPS partials of every sum in warp order (broadcast shared-memory reads, no shuffles)
+  double tot[10];
 #pragma unroll
-    for (int w = 0; w < K5_WARPS; ++w) mine += s_part[w * 10 + lane_id()];
+  for (int i = 0; i < 10; ++i) tot[i] = s_part[i];
+#pragma unroll
+  for (int w = 1; w < K5_WARPS; ++w) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) tot[i] += s_part[w * 10 + i];
   }
-  ev.cost = __shfl_sync(FULL, mine, 0);
+  ev.cost = tot[0];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) ev.H[i] = __shfl_sync(FULL, mine, 1 + i);
+  for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ev.g[i] = __shfl_sync(FULL, mine, 7 + i);
+  for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
 }
 
 // warps 1..: serve evaluations until warp 0 signals completion
@@ -248,7 +295,7 @@ struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usa
 // re-evaluation would give).
 template <int COST, int LOSS>
 __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                         LMShared* sh, double* s_part) {
+                                         LMShared* sh, double* s_part PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -258,7 +305,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
   EvalOut ev;
-  request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+  request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -305,7 +352,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     EvalOut evc;
-    request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part);
+    request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
     const double cand_cost = evc.cost;
     const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
@@ -364,99 +411,229 @@ __device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, doub
 
 __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) / (x + y); }
 
-// One outer iteration's association pass.  Returns the number of residual blocks (block-uniform).
+constexpr int K5_TILE_MAX = 4096;     // (keyframe, source cell) pairs associated per tile (2 x u16 of shared memory each)
+constexpr uint16_t K5_NONE = 0xffffu;
+
+// Everything one association pass needs, block-uniform.
+struct AssocCtx {
+  const int32_t* slots;       // s_slots
+  const double* pose;         // s_pose [nscans][5]: x y yaw cos sin
+  const NNGrid* grid;         // s_grid
+  const GridView* view;       // s_view
+  int K, n_src;
+  size_t sbase;               // first cell of the source set in the pool
+  double x[3], cs_s, sn_s;    // pose of the current scan
+  double radius;              // association radius of this outer iteration
+};
+
+// Relative transform Ttar^-1 * Tsrc of pair (keyframe i): rotation (rc, rs) and translation (tx, ty).   n_scan_normal.cpp:224
+struct RelT { double rc, rs, tx, ty, ct, st, px, py; };
+__device__ __forceinline__ RelT rel_transform(const AssocCtx& C, int i) {
+  const double* pt = C.pose + 5 * i;
+  RelT T; T.ct = pt[3]; T.st = pt[4]; T.px = pt[0]; T.py = pt[1];
+  T.rc = T.ct * C.cs_s + T.st * C.sn_s; T.rs = T.ct * C.sn_s - T.st * C.cs_s;
+  const double dx = C.x[0] - pt[0], dy = C.x[1] - pt[1];
+  T.tx = T.ct * dx + T.st * dy; T.ty = -T.st * dx + T.ct * dy;
+  return T;
+}
+
+// The residual record of an accepted pair: source mean p, world-frame target q, the cost's constants (a, b, c)
+// and the weight w.   n_scan_normal.cpp:262-311, registration.cpp:67-76
 template <int COST>
-__device__ __forceinline__ int build_problem(const RegParams& P, const int32_t* slots, const double* s_pose /*[nscans][5]: x y yaw cos sin*/,
-                                             const NNGrid* s_grid, const GridView* s_view, const double x[3], int itr,
-                                             const ResList& res, int32_t* assoc, int* s_warp, int K PROF_PARAM) {
-  const int src_slot = slots[K];
-  const int n_src = P.pool.ncells[src_slot];
-  const size_t sbase = (size_t)src_slot * P.pool.max_cells;
-  double cs_s, sn_s; sincos(x[2], &sn_s, &cs_s);
+__device__ __forceinline__ void make_record(const RegParams& P, const RelT& T, double sim, double2 mu, double2 tm, double2 ntar,
+                                            double4 Cv, double n1, double n2, double p1, double p2, double2& rp, double2& rq,
+                                            double2& rab, double2& rcw) {
+  double w = 1.0;
+  if (P.weight_opt == 1) w = sim_ratio(n1, n2);
+  else if (P.weight_opt == 2) w = sim;
+  else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
+  else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
+  const double ct = T.ct, st = T.st;
+  rp = mu;
+  rq = make_double2(ct * tm.x - st * tm.y + T.px, st * tm.x + ct * tm.y + T.py);
+  rab = make_double2(0, 0); rcw = make_double2(0, w);
+  if constexpr (COST == 1) {                                                   // :279-289
+    rab = make_double2(ct * ntar.x - st * ntar.y, st * ntar.x + ct * ntar.y);
+  } else if constexpr (COST == 2) {                                            // :290-300
+    const double a00 = ct * Cv.x - st * Cv.z, a01 = ct * Cv.y - st * Cv.w;
+    const double a10 = st * Cv.x + ct * Cv.z, a11 = st * Cv.y + ct * Cv.w;
+    double s00 = a00 * ct - a01 * st, s01 = a00 * st + a01 * ct;
+    double s10 = a10 * ct - a11 * st, s11 = a10 * st + a11 * ct;
+    s00 = (P.regularization + s00) * P.cov_scale; s11 = (P.regularization + s11) * P.cov_scale;
+    s01 = s01 * P.cov_scale; s10 = s10 * P.cov_scale;
+    // inverse and its lower Cholesky factor with one reciprocal, one reciprocal square root and one square root
+    const double idet = 1.0 / (s00 * s11 - s01 * s10);
+    const double i00 = s11 * idet, i10 = -(s10 * idet), i11 = s00 * idet;
+    const double rl = rsqrt(i00);
+    const double l00 = i00 * rl, l10 = i10 * rl;
+    const double l11 = sqrt(i11 - l10 * l10);
+    rab = make_double2(l00, l10); rcw.x = l11;
+  }
+}
+
+// One outer iteration's association pass (n_scan_normal.cpp:215-326), two phases per tile of pairs:
+//   1. every (keyframe i, source cell j) pair: transform, exact NN through the keyframe's bucket grid, 30 degree normal
+//      gate -> s_nn[pair] = target cell or NONE.  No block-wide synchronisation inside; two pairs per thread in flight so
+//      the target-normal loads (L2) of one overlap the grid walk of the other.
+//   2. one block scan gives every accepted pair its position, in (keyframe, cell) order; the residual records are then
+//      built position by position (two in flight per thread) and stored straight into the residual list.
+// Returns the number of residual blocks (block-uniform).
+template <int COST>
+__device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx& C, const ResList& res, int32_t* assoc,
+                                             int* s_warp, uint16_t* s_nn, uint16_t* s_list, int tile PROF_PARAM) {
+  const int T = K5_THREADS, tid = threadIdx.x;
+  const int n_src = C.n_src, npairs = C.K * n_src;
   const double angle_outlier = cos(M_PI / 6.0);
-  const double curr_radius = (itr == 1) ? 2 * P.radius : P.radius;       // n_scan_normal.cpp:222
-  const int npairs = K * n_src;
   const int cap = res.cap_g;
   int nres = 0;
-  for (int t0 = 0; t0 < npairs; t0 += blockDim.x) {
-    const int t = t0 + threadIdx.x;
-    bool valid = false;
-    double2 rp = make_double2(0, 0), rq = rp, rab = rp, rcw = rp;
-    PROF_T(tq0);
-#ifdef CFEAR_K5_PROFILE
-    long long tq1 = tq0;
-#endif
-    if (t < npairs) {
-      const int i = t / n_src, j = t - i * n_src;
-      const double* pt = s_pose + 5 * i;
-      const double ct = pt[3], st = pt[4];
-      const double rc = ct * cs_s + st * sn_s, rs = ct * sn_s - st * cs_s;     // Ttar^-1 * Tsrc   :224
-      const double dx = x[0] - pt[0], dy = x[1] - pt[1];
-      const double tx = ct * dx + st * dy, ty = -st * dx + ct * dy;
-      const double2 mu = P.pool.mean[sbase + j];
-      const double2 nsrc = P.pool.normal[sbase + j];
-      const double qx = rc * mu.x - rs * mu.y + tx, qy = rs * mu.x + rc * mu.y + ty;   // :240
-      const int tslot = slots[i];
-      const int m = nn_query(s_view[i], s_grid[i], qx, qy, curr_radius);              // :241
-#ifdef CFEAR_K5_PROFILE
-      tq1 = clock64();
-#endif
-      if (m >= 0) {
-        // everything the residual may need from the target cell is requested at once (one L2 round trip),
-        // before the normal gate decides whether it is used
-        const size_t tb = (size_t)tslot * P.pool.max_cells + m;
-        const double2 ntar = P.pool.normal[tb];
-        const double2 tm = P.pool.mean[tb];
-        double4 C = make_double4(0, 0, 0, 0);
-        if constexpr (COST == 2) C = P.pool.cov[tb];
-        double n1 = 0, n2 = 0, p1 = 0, p2 = 0;
-        if (P.weight_opt == 1 || P.weight_opt == 4) { n1 = (double)P.pool.nsamples[sbase + j]; n2 = (double)P.pool.nsamples[tb]; }
-        if (P.weight_opt == 3 || P.weight_opt == 4) { p1 = P.pool.planarity[sbase + j]; p2 = P.pool.planarity[tb]; }
-        const double ntx = rc * nsrc.x - rs * nsrc.y, nty = rs * nsrc.x + rc * nsrc.y;  // :244
-        const double sim = fmax(ntx * ntar.x + nty * ntar.y, 0.0);                      // :246
-        if (sim > angle_outlier) {                                                      // :247
-          valid = true;
-          double w = 1.0;                                                              // registration.cpp:67-76
-          if (P.weight_opt == 1) w = sim_ratio(n1, n2);
-          else if (P.weight_opt == 2) w = sim;
-          else if (P.weight_opt == 3) w = sim_ratio(p1, p2);
-          else if (P.weight_opt == 4) w = sim_ratio(n1, n2) + sim + sim_ratio(p1, p2);
-          rp = mu;
-          rq = make_double2(ct * tm.x - st * tm.y + pt[0], st * tm.x + ct * tm.y + pt[1]);
-          rcw.y = w;
-          if constexpr (COST == 1) {                                                   // :279-289
-            rab = make_double2(ct * ntar.x - st * ntar.y, st * ntar.x + ct * ntar.y);
-          } else if constexpr (COST == 2) {                                            // :290-300
-            const double a00 = ct * C.x - st * C.z, a01 = ct * C.y - st * C.w;
-            const double a10 = st * C.x + ct * C.z, a11 = st * C.y + ct * C.w;
-            double s00 = a00 * ct - a01 * st, s01 = a00 * st + a01 * ct;
-            double s10 = a10 * ct - a11 * st, s11 = a10 * st + a11 * ct;
-            s00 = (P.regularization + s00) * P.cov_scale; s11 = (P.regularization + s11) * P.cov_scale;
-            s01 = s01 * P.cov_scale; s10 = s10 * P.cov_scale;
-            const double det = s00 * s11 - s01 * s10;
-            const double i00 = s11 / det, i10 = -s10 / det, i11 = s00 / det;
-            const double l00 = sqrt(i00);
-            const double l10 = i10 / l00;
-            const double l11 = sqrt(i11 - l10 * l10);
-            rab = make_double2(l00, l10); rcw.x = l11;
-          }
+  for (int t0 = 0; t0 < npairs; t0 += tile) {
+    const int nt = min(tile, npairs - t0);
+    PROF_T(tp0);
+    // ---- phase 1 ----
+    for (int u0 = tid; u0 < nt; u0 += 2 * T) {
+      int m[2] = {-1, -1}, ii[2] = {0, 0}, jj[2] = {0, 0};
+      double ntx[2] = {0, 0}, nty[2] = {0, 0};
+      size_t tb[2] = {0, 0};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int u = u0 + h * T;
+        if (u < nt) {
+          const int t = t0 + u, i = t / n_src, j = t - i * n_src;
+          ii[h] = i; jj[h] = j;
+          const RelT R = rel_transform(C, i);
+          const double2 mu = P.pool.mean[C.sbase + j];
+          const double2 nsrc = P.pool.normal[C.sbase + j];
+          const double qx = R.rc * mu.x - R.rs * mu.y + R.tx, qy = R.rs * mu.x + R.rc * mu.y + R.ty;   // :240
+          m[h] = nn_query(C.view[i], C.grid[i], qx, qy, C.radius);                                      // :241
+          ntx[h] = R.rc * nsrc.x - R.rs * nsrc.y; nty[h] = R.rs * nsrc.x + R.rc * nsrc.y;               // :244
+          tb[h] = (size_t)C.slots[i] * P.pool.max_cells + (m[h] >= 0 ? m[h] : 0);
         }
       }
-      if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
+      double2 ntar[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) ntar[h] = (m[h] >= 0) ? P.pool.normal[tb[h]] : make_double2(0, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int u = u0 + h * T;
+        if (u < nt) {
+          const double sim = fmax(ntx[h] * ntar[h].x + nty[h] * ntar[h].y, 0.0);                        // :246
+          const bool valid = m[h] >= 0 && sim > angle_outlier;                                          // :247
+          s_nn[u] = valid ? (uint16_t)m[h] : K5_NONE;
+          if (assoc) assoc[(size_t)ii[h] * P.pool.max_cells + jj[h]] = valid ? m[h] : -1;
+        }
+      }
     }
-    PROF_T(tq2);
+    PROF_T(tp1);
+    __syncthreads();
+    PROF_T(tp2);
+    // ---- positions: contiguous chunk per thread, one block scan ----
+    const int chunk = (nt + T - 1) / T;
+    const int lo = min(tid * chunk, nt), hi = min(lo + chunk, nt);
+    int cnt = 0;
+    for (int u = lo; u < hi; ++u) cnt += (s_nn[u] != K5_NONE);
     int total;
-    const int pos = nres + block_excl_scan(valid ? 1 : 0, s_warp, &total);
-    PROF_T(tq3);
-#ifdef CFEAR_K5_PROFILE
-    prof[5] += tq1 - tq0; prof[6] += tq2 - tq1; prof[7] += tq3 - tq2;
-#endif
-    if (valid && pos < cap) { res.st(0, pos, rp); res.st(1, pos, rq); res.st(2, pos, rab); res.st(3, pos, rcw); }
+    int base = block_excl_scan(cnt, s_warp, &total);
+    for (int u = lo; u < hi; ++u) if (s_nn[u] != K5_NONE) s_list[base++] = (uint16_t)u;
+    __syncthreads();
+    PROF_T(tp3);
+    // ---- phase 2 ----
+    for (int r0 = tid; r0 < total; r0 += 2 * T) {
+      int ii[2] = {0, 0};
+      bool have[2];
+      double2 mu[2], nsrc[2], tm[2], ntar[2];
+      double4 Cv[2];
+      double n1[2] = {0, 0}, n2[2] = {0, 0}, p1[2] = {0, 0}, p2[2] = {0, 0};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r0 + h * T;
+        have[h] = r < total;
+        const int u = have[h] ? s_list[r] : s_list[r0];
+        const int t = t0 + u, i = t / n_src, j = t - i * n_src;
+        ii[h] = i;
+        const size_t sb = C.sbase + j;
+        const size_t tb = (size_t)C.slots[i] * P.pool.max_cells + s_nn[u];
+        // everything the record may need is requested at once: one L2 round trip for both pairs
+        mu[h] = P.pool.mean[sb]; nsrc[h] = P.pool.normal[sb];
+        tm[h] = P.pool.mean[tb]; ntar[h] = P.pool.normal[tb];
+        Cv[h] = make_double4(0, 0, 0, 0);
+        if constexpr (COST == 2) Cv[h] = P.pool.cov[tb];
+        if (P.weight_opt == 1 || P.weight_opt == 4) { n1[h] = (double)P.pool.nsamples[sb]; n2[h] = (double)P.pool.nsamples[tb]; }
+        if (P.weight_opt == 3 || P.weight_opt == 4) { p1[h] = P.pool.planarity[sb]; p2[h] = P.pool.planarity[tb]; }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r0 + h * T;
+        if (have[h]) {
+          const RelT R = rel_transform(C, ii[h]);
+          const double ntx = R.rc * nsrc[h].x - R.rs * nsrc[h].y, nty = R.rs * nsrc[h].x + R.rc * nsrc[h].y;
+          const double sim = fmax(ntx * ntar[h].x + nty * ntar[h].y, 0.0);
+          double2 rp, rq, rab, rcw;
+          make_record<COST>(P, R, sim, mu[h], tm[h], ntar[h], Cv[h], n1[h], n2[h], p1[h], p2[h], rp, rq, rab, rcw);
+          const int pos = nres + r;
+          if (pos < cap) { res.st(0, pos, rp); res.st(1, pos, rq); res.st(2, pos, rab); res.st(3, pos, rcw); }
+        }
+      }
+    }
     nres += total;
+    PROF_T(tp4);
+    __syncthreads();                 // s_nn / s_list are reused by the next tile; residual list visible to the block
+    PROF_T(tp5);
+    PROF_ADD(prof[8], tp0, tp1); PROF_ADD(prof[9], tp1, tp2); PROF_ADD(prof[10], tp2, tp3); PROF_ADD(prof[11], tp3, tp4); PROF_ADD(prof[12], tp4, tp5);
   }
-  __syncthreads();                 // residual list visible to the whole block
   return min(nres, cap);
 }
+
+// Keyframe NN indices (bucket starts + packed fp32 means) -> shared memory by TMA bulk copies, keyframe by keyframe
+// while they fit in [base, base + room); the rest is read through L1/L2.  Thread 0 plans the views once (plan = true)
+// and issues the copies; every thread then waits on the mbarrier's current phase.
+__device__ __forceinline__ void stage_grids(const RegParams& P, const int32_t* s_slots, const NNGrid* s_grid, GridView* s_view,
+                                            unsigned char* base, uint32_t room, int K, uint64_t* bar, uint32_t phase,
+                                            bool plan, uint32_t* used) {
+  if (threadIdx.x == 0) {
+    uint32_t off = 0, tx = 0;
+    for (int i = 0; i < K; ++i) {
+      const int sl = s_slots[i];
+      const NNGrid G = s_grid[i];
+      const int n = P.pool.ncells[sl];
+      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
+      const uint32_t gp_bytes = (uint32_t)n * 16u;
+      if (off + gs_bytes + gp_bytes <= room) {
+        if (plan) {
+          GridView V;
+          V.gs = reinterpret_cast<const uint16_t*>(base + off);
+          V.gp = reinterpret_cast<const float4*>(base + off + gs_bytes);
+          s_view[i] = V;
+        }
+        off += gs_bytes + gp_bytes; tx += gs_bytes + gp_bytes;
+      } else if (plan) {
+        GridView V;
+        V.gs = P.pool.gstart + (size_t)sl * P.pool.grid_stride;
+        V.gp = P.pool.gpt + (size_t)sl * P.pool.max_cells;
+        s_view[i] = V;
+      }
+    }
+    if (plan) *used = off;
+    mbar_expect_tx(bar, tx);
+    off = 0;
+    for (int i = 0; i < K; ++i) {
+      const int sl = s_slots[i];
+      const NNGrid G = s_grid[i];
+      const int n = P.pool.ncells[sl];
+      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
+      const uint32_t gp_bytes = (uint32_t)n * 16u;
+      if (off + gs_bytes + gp_bytes <= room) {
+        tma_bulk_g2s(base + off, P.pool.gstart + (size_t)sl * P.pool.grid_stride, gs_bytes, bar);
+        if (gp_bytes) tma_bulk_g2s(base + off + gs_bytes, P.pool.gpt + (size_t)sl * P.pool.max_cells, gp_bytes, bar);
+        off += gs_bytes + gp_bytes;
+      }
+    }
+  }
+  __syncthreads();
+  mbar_wait(bar, phase);
+}
+
+// Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes to it.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int COST, int LOSS>
 __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) {
@@ -469,7 +646,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   __shared__ GridView s_view[K5_MAXSCANS];
   __shared__ int32_t s_slots[K5_MAXSCANS];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_misc_off;
+  __shared__ uint32_t s_grid_bytes;
 
   const int prob = blockIdx.x;
   const int stride = P.nscans;
@@ -496,58 +673,71 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   }
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  // Stage the keyframes' NN indices (bucket starts + packed fp32 means) into shared memory with TMA bulk
-  // copies, keyframe by keyframe while they fit; the rest is read through L2.
-  if (tid == 0) {
-    uint32_t off = 0, tx = 0;
-    s_misc_off = 0;
-    for (int i = 0; i < K; ++i) {
-      const int sl = s_slots[i];
-      const NNGrid G = s_grid[i];
-      const int n = P.pool.ncells[sl];
-      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
-      const uint32_t gp_bytes = (uint32_t)n * 16u;
-      const uint16_t* g_gs = P.pool.gstart + (size_t)sl * P.pool.grid_stride;
-      const float4* g_gp = P.pool.gpt + (size_t)sl * P.pool.max_cells;
-      GridView V; V.gs = g_gs; V.gp = g_gp;
-      if (off + gs_bytes + gp_bytes <= (uint32_t)P.smem_bytes) {
-        V.gs = reinterpret_cast<const uint16_t*>(dyn_smem + off);
-        V.gp = reinterpret_cast<const float4*>(dyn_smem + off + gs_bytes);
-        off += gs_bytes + gp_bytes; tx += gs_bytes + gp_bytes;
-      }
-      s_view[i] = V;
-    }
-    s_misc_off = off;
-    mbar_expect_tx(&s_bar, tx);
-    for (int i = 0; i < K; ++i) {
-      const int sl = s_slots[i];
-      const NNGrid G = s_grid[i];
-      const int n = P.pool.ncells[sl];
-      const uint32_t gs_bytes = (uint32_t)(((G.nx * G.ny + 1) * 2 + 15) & ~15);
-      const uint32_t gp_bytes = (uint32_t)n * 16u;
-      const uint16_t* g_gs = P.pool.gstart + (size_t)sl * P.pool.grid_stride;
-      if (s_view[i].gs != g_gs) {
-        tma_bulk_g2s(const_cast<uint16_t*>(s_view[i].gs), g_gs, gs_bytes, &s_bar);
-        if (gp_bytes) tma_bulk_g2s(const_cast<float4*>(s_view[i].gp), P.pool.gpt + (size_t)sl * P.pool.max_cells, gp_bytes, &s_bar);
-      }
-    }
-  }
-  __syncthreads();
-  mbar_wait(&s_bar, 0);
+
+  // Shared-memory plan:  [ s_nn | s_list | U ]  with U = the rest of the dynamic allocation.
+  //  * problems whose pairs fit one tile (the normal case) OVERLAY U: during association it holds the keyframes' NN
+  //    grids, during the LM solve the residual list (written there directly by phase 2 of the association); the grids
+  //    are re-staged from L2 by TMA at the start of the next outer iteration.  Every evaluation of the solve -- the
+  //    inner loop of the whole kernel -- then reads shared memory only.
+  //  * larger problems keep the grids resident in U and put the residual list in what is left, overflowing to the
+  //    problem's global scratch.
+  AssocCtx C;
+  C.slots = s_slots; C.pose = s_pose; C.grid = s_grid; C.view = s_view; C.K = K;
+  const int src_slot = s_slots[K];
+  C.n_src = P.pool.ncells[src_slot];
+  C.sbase = (size_t)src_slot * P.pool.max_cells;
+  const int npairs = K * C.n_src;
+  const int tile = min(max((npairs + 7) & ~7, 8), K5_TILE_MAX);
+  const bool overlay = npairs <= K5_TILE_MAX;
+  uint16_t* s_nn = reinterpret_cast<uint16_t*>(dyn_smem);
+  uint16_t* s_list = s_nn + tile;
+  const uint32_t u_off = (uint32_t)((tile * 4 + 127) & ~127);
+  unsigned char* U = dyn_smem + u_off;
+  const uint32_t u_room = (uint32_t)P.smem_bytes - u_off;
+  uint32_t bar_phase = 0;
+  stage_grids(P, s_slots, s_grid, s_view, U, u_room, K, &s_bar, bar_phase, true, &s_grid_bytes);
+  bar_phase ^= 1;
+  bool grids_resident = true;
 
 #ifdef CFEAR_K5_PROFILE
-  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // 0 association 1 solve 2 grid staging | warp 0, per evaluation: 4 sincos+publish 5 own share 6 wait for the others 7 count |
+  // association: 8 phase 1 (own work) 9 wait 10 scan + list 11 phase 2 (own work) 12 wait
   const long long tk0 = clock64();
 #endif
   double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
   ResList res;
   res.g = P.res + (size_t)prob * P.res_cap * 4; res.cap_g = P.res_cap;
-  res.s = reinterpret_cast<double2*>(dyn_smem + s_misc_off);
-  res.cap_s = min(((int)P.smem_bytes - (int)s_misc_off) / 64, P.res_cap);
+  if (overlay) { res.s = reinterpret_cast<double2*>(U); res.cap_s = min((int)(u_room / 64), P.res_cap); }
+  else {
+    const uint32_t g_end = (s_grid_bytes + 127) & ~127u;
+    res.s = reinterpret_cast<double2*>(U + g_end); res.cap_s = min(((int)u_room - (int)g_end) / 64, P.res_cap);
+    if (res.cap_s < 0) res.cap_s = 0;
+  }
   int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
   const bool w0 = warp_id() == 0;              // the warp that runs the scalar solver logic (see "evaluation service")
   LMShared* sh = &s_lm;
+
+  // association at pose x for outer iteration itr (radius doubled on the first, n_scan_normal.cpp:222)
+  auto associate = [&](int itr) -> int {
+    PROF_T(ta0);
+    if (overlay && !grids_resident) {
+      fence_proxy_async_smem();                // our reads of the residual list precede the TMA writes over it
+      __syncthreads();
+      stage_grids(P, s_slots, s_grid, s_view, U, u_room, K, &s_bar, bar_phase, false, nullptr);
+      bar_phase ^= 1;
+    }
+    PROF_T(ta1);
+    C.x[0] = x[0]; C.x[1] = x[1]; C.x[2] = x[2];
+    sincos(x[2], &C.sn_s, &C.cs_s);
+    C.radius = (itr == 1) ? 2 * P.radius : P.radius;
+    const int n = build_problem<COST>(P, C, res, assoc, s_warp, s_nn, s_list, tile PROF_ARG);
+    if (overlay) grids_resident = false;
+    PROF_T(ta2);
+    PROF_ADD(prof[2], ta0, ta1); PROF_ADD(prof[0], ta1, ta2);
+    return n;
+  };
 
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
   bool success = true;
@@ -556,11 +746,11 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, it, res, assoc, s_warp, K PROF_ARG);
+      nres = associate(it);
       if (nres * per_block <= 1) { success = false; break; }
       if (w0) {
         EvalOut ev;
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
         double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
         const bool ok = chol3_solve(ev.H, nb, y);
         if (lane_id() == 0) {
@@ -582,7 +772,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     if (success) {
       if (w0) {
         EvalOut ev;
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
         if (lane_id() == 0) sh->out_final_cost = ev.cost;
         finish_evals(sh);
       } else {
@@ -596,13 +786,11 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     double prev_score = 1.7976931348623157e308;
     int itr;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
-      PROF_T(tb0);
-      nres = build_problem<COST>(P, s_slots, s_pose, s_grid, s_view, x, itr, res, assoc, s_warp, K PROF_ARG);
-      PROF_T(tb1);
-      PROF_ADD(prof[4], tb0, tb1);
+      nres = associate(itr);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
+      PROF_T(ts0);
       if (w0) {
-        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part);                 // :117
+        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part PROF_ARG);                 // :117
         if (lane_id() == 0) {
           sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
           sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
@@ -616,6 +804,8 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
       sum.final_cost = sh->out_final_cost; sum.last_rel = sh->out_last_rel;
       sum.n_iterations = sh->out_niter; sum.usable = sh->out_usable != 0;
       __syncthreads();                           // outputs consumed before the next episode rewrites them
+      PROF_T(ts1);
+      PROF_ADD(prof[1], ts0, ts1);
       success = sum.usable;
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
@@ -643,7 +833,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     if (w0) {
       EvalOut ev;                                                               // GetCovariance :392-433
-      request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part);
+      request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
       finish_evals(sh);
       double inv[9]; bool ok = true;
       for (int c = 0; c < 3 && ok; ++c) {
@@ -670,8 +860,9 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
     double* c36 = P.cov36 + (size_t)prob * 36;
     for (int i = 0; i < 36; ++i) c36[i] = cov[i];
 #ifdef CFEAR_K5_PROFILE
-    c36[13] = (double)prof[4]; c36[15] = (double)(clock64() - tk0);
-    c36[14] = (double)prof[5]; c36[16] = (double)prof[6]; c36[17] = (double)prof[7];
+    c36[13] = (double)prof[0]; c36[14] = (double)prof[1]; c36[16] = (double)prof[2]; c36[15] = (double)(clock64() - tk0);
+    c36[8] = (double)prof[4]; c36[9] = (double)prof[5]; c36[10] = (double)prof[6]; c36[11] = (double)prof[7];
+    c36[17] = (double)prof[8]; c36[18] = (double)prof[9]; c36[19] = (double)prof[10]; c36[20] = (double)prof[11]; c36[22] = (double)prof[12];
 #endif
   }
 }
