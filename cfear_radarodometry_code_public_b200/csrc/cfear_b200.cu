@@ -78,7 +78,7 @@ __global__ void k4b_nearest(CellPool pool, int slot, const double* q, int nq, do
   if (i >= nq) return;
   const NNGrid G = pool.grid[slot];
   GridView V; V.gs = pool.gstart + (size_t)slot * pool.grid_stride; V.gp = pool.gpt + (size_t)slot * pool.max_cells;
-  out[i] = nn_query(V, G, q[2 * i], q[2 * i + 1], radius);
+  uint32_t n16; out[i] = nn_query(V, G, q[2 * i], q[2 * i + 1], radius, &n16);
 }
 
 // AoS cfear_cell <-> pool SoA

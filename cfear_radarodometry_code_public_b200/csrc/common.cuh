@@ -30,7 +30,7 @@ struct CellPool {
   // NN index: uniform bucket grid over the fp32 means
   NNGrid* grid;            // [slots]
   uint16_t* gstart;        // [slots][grid_stride]  bucket start offsets (nx*ny+1 used); u16: max_cells <= 65535
-  float4* gpt;             // [slots][max_cells]    (x, y, cell index as int bits, 0) sorted by bucket
+  float4* gpt;             // [slots][max_cells]    (x, y, cell index as int bits, normal as 2 x fp16) sorted by bucket
   float2* fm_scratch;      // [slots][max_cells]    fp32 means staging for the index build of uploaded sets
   int grid_stride;         // u16 entries per slot (grid_cap + 8: keeps every slot 16-byte aligned for bulk copies)
 };

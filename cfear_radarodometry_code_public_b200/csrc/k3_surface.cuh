@@ -19,6 +19,8 @@
 //   mean / covariance / closed-form 2x2 eigen -> validity -> ordered compaction into the cell slot
 //   fp32 means -> bucket grid (counting sort through hist) -> gstart / gxy / gidx of the slot
 #pragma once
+#include <cstdio>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace cfear {
@@ -154,7 +156,11 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
     int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
     bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
     const int pos = atomicAdd(&hist[bx + by * nx], 1);
-    gpt[pos] = make_float4(p.x, p.y, __int_as_float(i), 0.f);
+    // .w: the cell's normal as two fp16 -- lets the registration's 30 degree normal gate decide from shared memory in
+    // all but the borderline cases (k5_register.cuh, normal_gate)
+    const double2 nrm = pool.normal[(size_t)slot * pool.max_cells + i];
+    const __half2 h = __floats2half2_rn((float)nrm.x, (float)nrm.y);
+    gpt[pos] = make_float4(p.x, p.y, __int_as_float(i), __uint_as_float(*reinterpret_cast<const unsigned*>(&h)));
   }
   if (tid == 0) {
     NNGrid G; G.ox = mnx; G.oy = mny; G.inv_g = inv; G.g = g; G.nx = nx; G.ny = ny;
@@ -163,7 +169,18 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
   __syncthreads();
 }
 
+// -DCFEAR_K3_PROFILE: clock64 phase probes, printed by thread 0 of a few scans
+#ifdef CFEAR_K3_PROFILE
+#define K3P(i) if (threadIdx.x == 0) { k3t[i] = clock64(); }
+#else
+#define K3P(i)
+#endif
+
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Params p) {
+#ifdef CFEAR_K3_PROFILE
+  long long k3t[16];
+#endif
+  K3P(0)
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ float s_red[32];
@@ -234,6 +251,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
       if (have) { bufA[dst] = pt; if (outc) outc[dst] = pt; }
     }
     __syncthreads();
+    K3P(1)
     if (tid == 0 && p.npts) p.npts[scan] = n;
   } else {
     n = p.npts[scan];
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   }
   mnx = block_min_f(mnx, s_red); mny = block_min_f(mny, s_red);
   mxx = block_max_f(mxx, s_red); mxy = block_max_f(mxy, s_red);
+  K3P(2)
   const float inv = 1.0f / p.leaf;
   const int minbx = (int)floorf(mnx * inv), maxbx = (int)floorf(mxx * inv);
   const int minby = (int)floorf(mny * inv), maxby = (int)floorf(mxy * inv);
@@ -298,7 +317,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     atomicAdd(&hist[i0 + i1 * divx], 1);
   }
   __syncthreads();
+  K3P(3)
   block_array_excl_scan(hist, nbins + 1, s_warp);          // hist[v] = start of voxel v
+  K3P(4)
   for (int i = tid; i < n; i += T) {
     float4 q = bufA[i];
     const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
@@ -307,6 +328,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     bufB[pos] = q;
   }
   __syncthreads();
+  K3P(5)
   // restore input order inside every voxel (VoxelGrid sums a voxel's points in a fixed order; the oracle's is
   // ascending input index): rank by counting, one thread per point, neighbours in a warp share the segment
   for (int a = tid; a < n; a += T) {
@@ -320,6 +342,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     bufA[s + rank] = q;
   }
   __syncthreads();
+  K3P(6)
   float4* pts = bufA;                                      // points bucketed by voxel, input order inside a voxel
 
   // ---- ordered list of non-empty voxels, sequential fp32 centroid per voxel ---------------------------
@@ -337,6 +360,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     if (tid == 0) s_misc[0] = total;
     __syncthreads();
   }
+  K3P(7)
   const int nvox = s_misc[0];
   for (int c = tid; c < nvox; c += T) {
     const int v = vlist[c];
@@ -354,6 +378,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   // (exact in fp64: q and the points are fp32), from which the weighted mean and the central covariance of
   // pointnormal.cpp:21-33 follow.  Cells land in a per-scan scratch at their centroid index; an ordered
   // compaction of the valid ones follows. ---------------------------------------------------------------
+  K3P(8)
   const float r = p.radius;
   const float r2 = (float)((double)r * (double)r);
   const float rq = r * 1.0001f + 1e-4f;                    // bin-range margin (the d2 test itself is exact)
@@ -405,6 +430,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     }
   }
   __syncthreads();
+  K3P(9)
   int ncells = 0;                                          // block-uniform running count
   for (int c0 = 0; c0 < nvox; c0 += T) {
     const int c = c0 + tid;
@@ -445,12 +471,20 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     ncells += total;
     __syncthreads();
   }
+  K3P(10)
   ncells = min(ncells, p.pool.max_cells);
   if (tid == 0) p.pool.ncells[slot] = ncells;
   __syncthreads();
 
   // ---- NN index over the fp32 means --------------------------------------------------------------
   build_nn_grid(p.pool, slot, cxy, ncells, p.nn_cell, s_hist, min(K3_HIST_CAP, p.pool.grid_cap) - 1, s_warp, s_red);
+#ifdef CFEAR_K3_PROFILE
+  K3P(11)
+  if (tid == 0 && (scan & 63) == 5)
+    printf("K3 scan %d n=%d nvox=%d ncells=%d nbins=%d | stage+compact %lld bounds %lld hist %lld scan %lld scatter %lld reorder %lld voxlist %lld centroids %lld moments %lld finalise %lld nngrid %lld | total %lld\n",
+           scan, n, nvox, ncells, nbins, k3t[1] - k3t[0], k3t[2] - k3t[1], k3t[3] - k3t[2], k3t[4] - k3t[3], k3t[5] - k3t[4], k3t[6] - k3t[5],
+           k3t[7] - k3t[6], k3t[8] - k3t[7], k3t[9] - k3t[8], k3t[10] - k3t[9], k3t[11] - k3t[10], k3t[11] - k3t[0]);
+#endif
 }
 
 // NN index for an uploaded cell set (cfear_cells_upload): one CTA per slot.

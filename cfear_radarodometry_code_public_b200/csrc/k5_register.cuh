@@ -15,6 +15,7 @@
 // + cost sums reduced by warp shuffles and a fixed-order cross-warp sum (bit-reproducible), while the
 // scalar trust-region logic is executed redundantly by every thread on identical inputs.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "k3_surface.cuh"   // mbarrier / TMA bulk-copy helpers
 
@@ -231,7 +232,7 @@ __device__ __forceinline__ void request_eval(double loss_limit, const ResList& r
   PROF_T(te2);
   bar_b();
   PROF_T(te3);
-  PROF_ADD(prof[4], te0, te1); PROF_ADD(prof[5], te1, te2); PROF_ADD(prof[6], te2, te3); prof[7] += 1;
+  PROF_ADD(prof[4], te0, te1); PROF_ADD(prof[5], te1, te2); PROF_ADD(prof[6], te2, te3); PROF_ADD(prof[7], 0, 1);
   // every lane adds the K5_WARPS partials of every sum in warp order (broadcast shared-memory reads, no shuffles)
   double tot[10];
 #pragma unroll
@@ -300,6 +301,9 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
   double radius = 1e4, decrease_factor = 2.0;
+  // 1 / radius is carried along multiplicatively (the oracle divides the diagonal by the radius; both are the same damping
+  // to an ulp) so that no division sits between an accepted step and the next linear solve
+  double inv_radius = 1e-4;
   bool reuse_diagonal = false;
   int invalid_in_a_row = 0;
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
@@ -311,7 +315,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
   scale[1] = 1.0 / (1.0 + sqrt(ev.H[3]));
   scale[2] = 1.0 / (1.0 + sqrt(ev.H[5]));
-  double x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  double x_n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
   double min_cost = x_cost;
   double gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
   sum.final_cost = min_cost;
@@ -326,7 +330,6 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
       diag[1] = fmin(fmax(Hs[3], kMinDiag), kMaxDiag);
       diag[2] = fmin(fmax(Hs[5], kMinDiag), kMaxDiag);
     }
-    const double inv_radius = 1.0 / radius;
     const double A[6] = {Hs[0] + diag[0] * inv_radius, Hs[1], Hs[2], Hs[3] + diag[1] * inv_radius, Hs[4], Hs[5] + diag[2] * inv_radius};
     double y[3];
     const double nb[3] = {-gs[0], -gs[1], -gs[2]};
@@ -341,7 +344,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
     }
     if (!ok || !(model_change > 0.0)) {
       if (++invalid_in_a_row >= 5) { sum.usable = false; return; }
-      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
       sum.n_iterations++; sum.last_rel = 0.0;
       min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
       if (it >= P.max_inner) return;
@@ -354,27 +357,33 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
     EvalOut evc;
     request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
     const double cand_cost = evc.cost;
-    const double step_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
-    if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return;
+    // parameter tolerance |delta| <= tol (|x| + tol): the square roots are only taken when the squares come close
+    const double step_n2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
+    if (step_n2 <= 4.0 * kParameterTol * kParameterTol * (x_n2 + kParameterTol * kParameterTol)) {      // (a+b)^2 <= 2a^2+2b^2, doubled again
+      if (sqrt(step_n2) <= kParameterTol * (sqrt(x_n2) + kParameterTol)) return;
+    }
     const double cost_change = x_cost - cand_cost;
     if (fabs(cost_change) <= kFunctionTol * x_cost) return;
     const double rel = cost_change / model_change;
     sum.n_iterations++; sum.last_rel = rel;
     if (rel > kMinRelDecrease) {
       x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
-      x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+      x_n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
       ev = evc;
       x_cost = ev.cost;
       gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
-      const double t = 2.0 * rel - 1.0;
-      radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
-      radius = fmin(kMaxRadius, radius);
+      // radius /= max(1/3, 1 - (2 rel - 1)^3).  A step with rel >= 0.94 has (2 rel - 1)^3 > 2/3, i.e. the maximum picks
+      // 1/3 whatever the last bits of rel are: that case needs neither the quotient nor the cube.
+      double f = 1.0 / 3.0;
+      if (!(cost_change >= 0.94 * model_change)) { const double t = 2.0 * rel - 1.0; f = fmax(1.0 / 3.0, 1.0 - t * t * t); }
+      radius = fmin(kMaxRadius, radius / f);
+      inv_radius = fmax(1.0 / kMaxRadius, inv_radius * f);
       decrease_factor = 2.0; reuse_diagonal = false;
       min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
       if (it >= P.max_inner) return;
       if (gmax <= kGradientTol) return;
     } else {
-      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
       min_cost = fmin(min_cost, cand_cost); sum.final_cost = min_cost;
       if (it >= P.max_inner) return;
       if (radius <= kMinRadius) return;
@@ -385,14 +394,15 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
 // One keyframe's NN index as seen by the block: bucket starts + packed points, in shared memory when staged.
 struct GridView { const uint16_t* gs; const float4* gp; };
 
-// GetClosestIdx: exact fp32 nearest neighbour through the bucket grid; ties -> smallest cell index.
-__device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, double radius) {
+// GetClosestIdx: exact fp32 nearest neighbour through the bucket grid; ties -> smallest cell index.  *nrm16 receives
+// the winner's normal as packed fp16 pair (the .w of its grid point).
+__device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, double radius, uint32_t* nrm16) {
   const float qx = (float)pxd, qy = (float)pyd;             // pointnormal.cpp:241-242
   const float rq = (float)radius * 1.0001f + 1e-3f;         // bucket-range margin only
   int bx0 = (int)floorf((qx - rq - G.ox) * G.inv_g), bx1 = (int)floorf((qx + rq - G.ox) * G.inv_g);
   int by0 = (int)floorf((qy - rq - G.oy) * G.inv_g), by1 = (int)floorf((qy + rq - G.oy) * G.inv_g);
   bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, G.nx - 1); by1 = min(by1, G.ny - 1);
-  float best = 3.4028234e38f; int besti = -1;
+  float best = 3.4028234e38f; int besti = -1; uint32_t bestn = 0;
   if (bx0 > bx1) return -1;
   for (int by = by0; by <= by1; ++by) {
     const int s = V.gs[bx0 + by * G.nx], e = V.gs[bx1 + by * G.nx + 1];
@@ -402,11 +412,27 @@ __device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, doub
       const float dx = qx - m.x, dy = qy - m.y;
       float d2 = dx * dx; d2 += dy * dy;
       const int i = __float_as_int(m.z);
-      if (d2 < best || (d2 == best && i < besti)) { best = d2; besti = i; }
+      if (d2 < best || (d2 == best && i < besti)) { best = d2; besti = i; bestn = __float_as_uint(m.w); }
     }
   }
+  *nrm16 = bestn;
   if (besti >= 0 && (double)best < radius * radius) return besti;   // pointnormal.cpp:250
   return -1;
+}
+
+// The normal gate of n_scan_normal.cpp:244-247, max(n_src' . n_tar, 0) > cos(30 deg) in fp64, decided from the fp16 copy
+// of the target normal whenever the fp32 dot product is further from the threshold than the copy's rounding error can
+// explain; only the borderline pairs fetch the fp64 normal.  Same decisions as the fp64 test, by construction.
+__device__ __forceinline__ bool normal_gate(double ntx, double nty, uint32_t nrm16, const double2* tar_normal, double thr) {
+  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&nrm16));
+  const float sx = (float)ntx, sy = (float)nty;
+  const float dot = sx * t.x + sy * t.y;
+  const float band = (fabsf(sx) + fabsf(sy)) * (6e-4f * (fabsf(t.x) + fabsf(t.y)) + 1e-4f);
+  const float th = (float)thr;
+  if (dot > th + band) return true;
+  if (dot < th - band) return false;
+  const double2 n = *tar_normal;                                        // borderline (or non-finite): exact test
+  return fmax(ntx * n.x + nty * n.y, 0.0) > thr;
 }
 
 __device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) / (x + y); }
@@ -422,6 +448,8 @@ struct AssocCtx {
   const GridView* view;       // s_view
   int K, n_src;
   size_t sbase;               // first cell of the source set in the pool
+  const double2* src_mean;    // [n_src] means / normals of the source cells: shared-memory copies when they fit,
+  const double2* src_normal;  //         else the pool's arrays
   double x[3], cs_s, sn_s;    // pose of the current scan
   double radius;              // association radius of this outer iteration
 };
@@ -473,8 +501,8 @@ __device__ __forceinline__ void make_record(const RegParams& P, const RelT& T, d
 
 // One outer iteration's association pass (n_scan_normal.cpp:215-326), two phases per tile of pairs:
 //   1. every (keyframe i, source cell j) pair: transform, exact NN through the keyframe's bucket grid, 30 degree normal
-//      gate -> s_nn[pair] = target cell or NONE.  No block-wide synchronisation inside; two pairs per thread in flight so
-//      the target-normal loads (L2) of one overlap the grid walk of the other.
+//      gate -> s_nn[pair] = target cell or NONE.  Shared memory only (source cells, grids, fp16 target normals) except
+//      for borderline gate decisions; no block-wide synchronisation inside.
 //   2. one block scan gives every accepted pair its position, in (keyframe, cell) order; the residual records are then
 //      built position by position (two in flight per thread) and stored straight into the residual list.
 // Returns the number of residual blocks (block-uniform).
@@ -490,38 +518,21 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
     const int nt = min(tile, npairs - t0);
     PROF_T(tp0);
     // ---- phase 1 ----
-    for (int u0 = tid; u0 < nt; u0 += 2 * T) {
-      int m[2] = {-1, -1}, ii[2] = {0, 0}, jj[2] = {0, 0};
-      double ntx[2] = {0, 0}, nty[2] = {0, 0};
-      size_t tb[2] = {0, 0};
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int u = u0 + h * T;
-        if (u < nt) {
-          const int t = t0 + u, i = t / n_src, j = t - i * n_src;
-          ii[h] = i; jj[h] = j;
-          const RelT R = rel_transform(C, i);
-          const double2 mu = P.pool.mean[C.sbase + j];
-          const double2 nsrc = P.pool.normal[C.sbase + j];
-          const double qx = R.rc * mu.x - R.rs * mu.y + R.tx, qy = R.rs * mu.x + R.rc * mu.y + R.ty;   // :240
-          m[h] = nn_query(C.view[i], C.grid[i], qx, qy, C.radius);                                      // :241
-          ntx[h] = R.rc * nsrc.x - R.rs * nsrc.y; nty[h] = R.rs * nsrc.x + R.rc * nsrc.y;               // :244
-          tb[h] = (size_t)C.slots[i] * P.pool.max_cells + (m[h] >= 0 ? m[h] : 0);
-        }
+    for (int u = tid; u < nt; u += T) {
+      const int t = t0 + u, i = t / n_src, j = t - i * n_src;
+      const RelT R = rel_transform(C, i);
+      const double2 mu = C.src_mean[j];
+      const double2 nsrc = C.src_normal[j];
+      const double qx = R.rc * mu.x - R.rs * mu.y + R.tx, qy = R.rs * mu.x + R.rc * mu.y + R.ty;   // :240
+      uint32_t n16;
+      const int m = nn_query(C.view[i], C.grid[i], qx, qy, C.radius, &n16);                       // :241
+      bool valid = false;
+      if (m >= 0) {
+        const double ntx = R.rc * nsrc.x - R.rs * nsrc.y, nty = R.rs * nsrc.x + R.rc * nsrc.y;    // :244
+        valid = normal_gate(ntx, nty, n16, P.pool.normal + (size_t)C.slots[i] * P.pool.max_cells + m, angle_outlier);   // :246-247
       }
-      double2 ntar[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) ntar[h] = (m[h] >= 0) ? P.pool.normal[tb[h]] : make_double2(0, 0);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int u = u0 + h * T;
-        if (u < nt) {
-          const double sim = fmax(ntx[h] * ntar[h].x + nty[h] * ntar[h].y, 0.0);                        // :246
-          const bool valid = m[h] >= 0 && sim > angle_outlier;                                          // :247
-          s_nn[u] = valid ? (uint16_t)m[h] : K5_NONE;
-          if (assoc) assoc[(size_t)ii[h] * P.pool.max_cells + jj[h]] = valid ? m[h] : -1;
-        }
-      }
+      s_nn[u] = valid ? (uint16_t)m : K5_NONE;
+      if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
     }
     PROF_T(tp1);
     __syncthreads();
@@ -553,7 +564,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
         const size_t sb = C.sbase + j;
         const size_t tb = (size_t)C.slots[i] * P.pool.max_cells + s_nn[u];
         // everything the record may need is requested at once: one L2 round trip for both pairs
-        mu[h] = P.pool.mean[sb]; nsrc[h] = P.pool.normal[sb];
+        mu[h] = C.src_mean[j]; nsrc[h] = C.src_normal[j];
         tm[h] = P.pool.mean[tb]; ntar[h] = P.pool.normal[tb];
         Cv[h] = make_double4(0, 0, 0, 0);
         if constexpr (COST == 2) Cv[h] = P.pool.cov[tb];
@@ -636,7 +647,7 @@ __device__ __forceinline__ void stage_grids(const RegParams& P, const int32_t* s
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int COST, int LOSS>
-__global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) {
+__global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ double s_part[K5_WARPS * 10];
@@ -674,7 +685,7 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
 
-  // Shared-memory plan:  [ s_nn | s_list | U ]  with U = the rest of the dynamic allocation.
+  // Shared-memory plan:  [ s_nn | s_list | source means, normals | U ]  with U = the rest of the dynamic allocation.
   //  * problems whose pairs fit one tile (the normal case) OVERLAY U: during association it holds the keyframes' NN
   //    grids, during the LM solve the residual list (written there directly by phase 2 of the association); the grids
   //    are re-staged from L2 by TMA at the start of the next outer iteration.  Every evaluation of the solve -- the
@@ -691,7 +702,17 @@ __global__ void __launch_bounds__(K5_THREADS, 2) k5_register(const RegParams P) 
   const bool overlay = npairs <= K5_TILE_MAX;
   uint16_t* s_nn = reinterpret_cast<uint16_t*>(dyn_smem);
   uint16_t* s_list = s_nn + tile;
-  const uint32_t u_off = (uint32_t)((tile * 4 + 127) & ~127);
+  uint32_t u_off = (uint32_t)((tile * 4 + 127) & ~127);
+  // the source cells' means and normals (read by every pair of every association pass) are copied to shared memory
+  // once when they take at most a quarter of the allocation
+  C.src_mean = P.pool.mean + C.sbase; C.src_normal = P.pool.normal + C.sbase;
+  if ((uint32_t)C.n_src * 32u <= (uint32_t)P.smem_bytes / 4) {
+    double2* sm = reinterpret_cast<double2*>(dyn_smem + u_off);
+    double2* sn = sm + C.n_src;
+    for (int j = tid; j < C.n_src; j += K5_THREADS) { sm[j] = C.src_mean[j]; sn[j] = C.src_normal[j]; }
+    C.src_mean = sm; C.src_normal = sn;
+    u_off += (uint32_t)((C.n_src * 32 + 127) & ~127);
+  }
   unsigned char* U = dyn_smem + u_off;
   const uint32_t u_room = (uint32_t)P.smem_bytes - u_off;
   uint32_t bar_phase = 0;
