@@ -339,9 +339,7 @@ static int launch_k1(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
   p.min_range_bin = (int)ceil(min_distance / range_res);                      // radar_filters.cpp:315
   p.range_res = range_res; p.cs = c->d_cs;
   p.kidx = c->d_kidx; p.kcnt = c->d_kcnt; p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
-  const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
-  if (((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0) k1_kstrongest<true><<<grid, K1_WARPS * 32, 0, c->stream>>>(p);
-  else k1_kstrongest<false><<<grid, K1_WARPS * 32, 0, c->stream>>>(p);
+  k1_launch(p, c->stream);
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;
@@ -713,8 +711,7 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     p.min_range_bin = (int)ceil(min_distance / range_res); p.range_res = range_res; p.cs = c->d_cs;
     const size_t r0 = (size_t)b0 * A;
     p.kidx = c->d_kidx + r0 * p.k; p.kcnt = c->d_kcnt + r0; p.rowcloud = c->d_rowcloud + r0 * p.k; p.rowcnt = c->d_rowcnt + r0;
-    if (((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0) k1_kstrongest<true><<<(p.nrows + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, c->stream>>>(p);
-    else k1_kstrongest<false><<<(p.nrows + K1_WARPS - 1) / K1_WARPS, K1_WARPS * 32, 0, c->stream>>>(p);
+    k1_launch(p, c->stream);
     c->launches++;
     CK(cudaGetLastError());
     RC(launch_k3(c, 0, nb, have_mot ? c->d_mot + 3 * (size_t)b0 : nullptr, c->d_curslots + b0, false, b0));

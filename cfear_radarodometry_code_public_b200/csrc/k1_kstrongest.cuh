@@ -3,9 +3,9 @@
 // getPeaksFilteredPointCloud (radar_filters.cpp:309-337) of the reference.
 //
 // One warp per azimuth row.  The row (R uint8, 3360 B on Navtech data) is streamed once from HBM
-// with 16-byte non-allocating loads (8 in flight per lane), tested against z_min with SWAR byte
-// compares, the (sparse) candidates are packed as keys (intensity<<16 | range) into a per-warp
-// shared-memory list, and the k largest keys are selected exactly:
+// with 16-byte non-allocating loads (7 in flight per lane), tested against z_min with SWAR byte
+// compares, the (sparse) candidates are emitted warp-cooperatively as keys (intensity<<16 | range) into
+// a per-warp shared-memory list, and the k largest keys are selected exactly:
 //   lexicographic (intensity, range) order == integer order of the key, so ties go to the larger
 //   range bin exactly like the reference's sorted-insert / erase-front loop.
 // Algorithmic HBM bytes per row: R (read) + 4k+4 (indices) + 16k+4 (cloud row).
@@ -14,9 +14,12 @@
 
 namespace cfear {
 
+#ifndef CFEAR_K1_MINBLOCKS
+#define CFEAR_K1_MINBLOCKS 6   // resident CTAs per SM the register budget is set for (40 registers, no spills; 4 -> 6: 0.115 -> 0.109 ms)
+#endif
 constexpr int K1_WARPS = 8;       // warps (rows) per CTA
 constexpr int K1_CAP = 256;       // candidate keys per warp kept in shared memory
-constexpr int K1_TILES = 8;       // uint4 per lane per super-tile (8*512 B = 4096 B of row in registers)
+constexpr int K1_TILES = 7;       // uint4 per lane per super-tile (7*512 B = 3584 B >= one 3360-bin Navtech row in registers)
 constexpr int K1_MAXK = 64;       // k_strongest <= 64
 
 struct K1Params {
@@ -54,21 +57,23 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t*
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// bit7 of each byte set iff byte >= z_min.  addc = (0x80 - (zmin&0x7f)) * 0x01010101.
-__device__ __forceinline__ uint32_t ge_flags(uint32_t x, uint32_t addc, bool zhi) {
+// bit7 of each byte set iff byte >= z_min.  addc = (0x80 - (zmin&0x7f)) * 0x01010101.  ZHI: z_min >= 128.
+template <bool ZHI>
+__device__ __forceinline__ uint32_t ge_flags(uint32_t x, uint32_t addc) {
   const uint32_t a = (x & 0x7f7f7f7fu) + addc;     // bit7: low 7 bits >= low 7 bits of zmin; no cross-byte carry
-  return zhi ? (x & a & 0x80808080u) : ((x | a) & 0x80808080u);
+  return ZHI ? (x & a & 0x80808080u) : ((x | a) & 0x80808080u);
 }
 
 // flags of a uint4 packed in one word: byte b of word w -> bit 8b + 7 - w
-__device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc, bool zhi) {
-  return ge_flags(d.x, addc, zhi) | (ge_flags(d.y, addc, zhi) >> 1) | (ge_flags(d.z, addc, zhi) >> 2) |
-         (ge_flags(d.w, addc, zhi) >> 3);
+template <bool ZHI>
+__device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc) {
+  return ge_flags<ZHI>(d.x, addc) | (ge_flags<ZHI>(d.y, addc) >> 1) | (ge_flags<ZHI>(d.z, addc) >> 2) |
+         (ge_flags<ZHI>(d.w, addc) >> 3);
 }
 
 // ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
-template <bool ALIGNED>
-__global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params p) {
+template <bool ALIGNED, bool ZHI>
+__global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstrongest(const K1Params p) {
   __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
   __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
   __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
@@ -85,61 +90,68 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
   const uint8_t* base = row - off;
   const int nvec = (off + R + 15) >> 4;
   const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
-  const bool zhi = p.zmin >= 128;
 
-  // ---- pass 1: stream the row, collect candidate keys ------------------------------------------
+  // ---- pass 1: stream the row, collect the candidates ---------------------------------------------
+  // Candidates are sparse (a few vectors per row hold any), so they are emitted cooperatively: the warp walks the
+  // vectors that have flags set (ballot), two at a time, and lane l handles byte (l & 15) of the first (l < 16) or second
+  // (l >= 16) of them.  Only range bins are emitted here; the intensities are re-read (L2) once the list is complete.
+  const int jb = lane & 15, jw = jb >> 2;
+  const uint32_t mybit = 1u << (8 * (jb & 3) + 7 - jw);                          // flag bit of byte jb (see ge_flags16)
+  const uint32_t lowmask = 0x01010101u * (0x100u - (0x100u >> jw)) |             // flag bits of the bytes before jb
+                           ((0x80808080u >> jw) & ((1u << (8 * (jb & 3))) - 1u));
+  const bool hi = lane >= 16;
   int C = 0;                                   // warp-uniform candidate count
   for (int v0 = 0; v0 < nvec; v0 += 32 * K1_TILES) {
-    uint4 d[K1_TILES];
-#pragma unroll
-    for (int i = 0; i < K1_TILES; ++i) {
-      const int v = v0 + i * 32 + lane;
-      if (ALIGNED) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
-      else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
-    }
     uint32_t g[K1_TILES];
-    int nl = 0;
-#pragma unroll
-    for (int i = 0; i < K1_TILES; ++i) {
-      const int v = v0 + i * 32 + lane;
-      uint32_t m = ge_flags16(d[i], addc, zhi);
-      const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
-      if (v >= nvec) m = 0;
-      else if (!ALIGNED && (b0 < 0 || b0 + 16 > R)) {        // row head / tail: drop bytes of neighbouring rows
-        uint32_t keep = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = b0 + j;
-          if (r >= 0 && r < R) keep |= 1u << (8 * (j & 3) + 7 - (j >> 2));
-        }
-        m &= keep;
-      }
-      g[i] = m;
-      nl += __popc(m);
-    }
-    const int incl = warp_incl_scan(nl);
-    const int tot = __shfl_sync(FULL, incl, 31);
-    if (C + tot <= K1_CAP) {
-      int pos = C + incl - nl;
+    {
+      uint4 d[K1_TILES];
 #pragma unroll
       for (int i = 0; i < K1_TILES; ++i) {
-        const uint32_t m = g[i];
-        if (m == 0) continue;
-        const int rb = (v0 + i * 32 + lane) * 16 - off;
-        const uint32_t words[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+        const int v = v0 + i * 32 + lane;
+        if (ALIGNED) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
+        else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          uint32_t mw = (m << w) & 0x80808080u;             // byte b of word w -> bit 8b+7
-          while (mw) {
-            const int sh = __ffs(mw) - 8;                   // 8b
-            mw &= mw - 1;
-            const uint32_t inten = (words[w] >> sh) & 0xffu;
-            cand[pos++] = (inten << 16) | (uint32_t)(rb + 4 * w + (sh >> 3));
+      for (int i = 0; i < K1_TILES; ++i) {
+        const int v = v0 + i * 32 + lane;
+        uint32_t m = ge_flags16<ZHI>(d[i], addc);
+        const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
+        if (v >= nvec) m = 0;
+        else if (!ALIGNED && (b0 < 0 || b0 + 16 > R)) {        // row head / tail: drop bytes of neighbouring rows
+          uint32_t keep = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int r = b0 + j;
+            if (r >= 0 && r < R) keep |= 1u << (8 * (j & 3) + 7 - (j >> 2));
           }
+          m &= keep;
         }
+        g[i] = m;
       }
     }
-    C += tot;
+#pragma unroll
+    for (int i = 0; i < K1_TILES; ++i) {
+      uint32_t bal = __ballot_sync(FULL, g[i] != 0);
+      while (bal) {                              // warp-uniform
+        const int l1 = __ffs(bal) - 1; bal &= bal - 1;
+        const bool two = bal != 0;
+        const int l2 = two ? __ffs(bal) - 1 : l1;
+        if (two) bal &= bal - 1;
+        const uint32_t m1 = __shfl_sync(FULL, g[i], l1);
+        uint32_t m2 = __shfl_sync(FULL, g[i], l2);
+        if (!two) m2 = 0;
+        const uint32_t mm = hi ? m2 : m1;
+        if (mm & mybit) {
+          const int pos = C + (hi ? __popc(m1) : 0) + __popc(mm & lowmask);
+          if (pos < K1_CAP) cand[pos] = (uint32_t)((v0 + i * 32 + (hi ? l2 : l1)) * 16 - off + jb);
+        }
+        C += __popc(m1) + __popc(m2);
+      }
+    }
+  }
+  __syncwarp();
+  if (C <= K1_CAP) {                             // range bins -> keys (intensity << 16 | range)
+    for (int j = lane; j < C; j += 32) { const uint32_t r = cand[j]; cand[j] = ((uint32_t)row[r] << 16) | r; }
   }
   __syncwarp();
 
@@ -177,12 +189,18 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
     work = sel;
     nwork = k;
   }
-  // rank by counting among <= 64 keys; ascending output position = kk-1-rank_desc
-  for (int j = lane; j < nwork; j += 32) {
-    const uint32_t key = work[j];
-    int rank = 0;
-    for (int m = 0; m < nwork; ++m) rank += (work[m] > key);
-    if (rank < kk) outk[kk - 1 - rank] = key;
+  // <= 64 distinct keys, at most two per lane: the kk largest, one warp-wide max reduction (REDUX) each, written in
+  // ascending order (position kk-1-t for the t-th largest)
+  {
+    uint32_t k0 = (lane < nwork) ? work[lane] + 1u : 0u;           // +1: 0 is the "taken / absent" mark
+    uint32_t k1 = (lane + 32 < nwork) ? work[lane + 32] + 1u : 0u;
+    __syncwarp();
+    for (int t = 0; t < kk; ++t) {
+      const uint32_t mx = __reduce_max_sync(FULL, max(k0, k1));
+      if (k0 == mx) k0 = 0u;
+      if (k1 == mx) k1 = 0u;
+      if (lane == 0) outk[kk - 1 - t] = mx - 1u;
+    }
   }
   __syncwarp();
 
@@ -212,6 +230,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_kstrongest(const K1Params
     ncloud += __popc(bal);
   }
   if (lane == 0) { p.kcnt[grow] = kk; p.rowcnt[grow] = ncloud; }
+}
+
+// Launch with the instantiation the data allows: aligned rows (every row on a 16-byte boundary, no vector straddles a
+// row) and the z_min half (>= 128 or not) are compile-time.
+inline void k1_launch(const K1Params& p, cudaStream_t stream) {
+  const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
+  const bool aligned = ((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0;
+  const bool zhi = p.zmin >= 128;
+  if (aligned) { if (zhi) k1_kstrongest<true, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<true, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
+  else { if (zhi) k1_kstrongest<false, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<false, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -51,6 +51,19 @@ struct RegStatsDev {             // == cfear_reg_stats
   double final_cost, score;
 };
 
+// 1 / sqrt(s) for s in the normal range (callers guarantee s > loss_limit^2 > 0): the 22-bit hardware seed and two
+// Newton steps, 9 FP64-pipe instructions instead of the ~25 (plus special-case branches) of the library rsqrt().
+// Within 2 ulp of the exact value.
+__device__ __forceinline__ double rsqrt_normal(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double h = 0.5 * s;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+
 // ceres/loss_function.cc (rho[2] is only needed by Ceres' corrector when rho'' > 0, which none of these have)
 template <int LOSS>
 __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
@@ -58,7 +71,7 @@ __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
     const double b = a * a;
     // sqrt(s) = s * rsqrt(s), a / sqrt(s) = a * rsqrt(s): one reciprocal square root instead of a square root and a
     // division per outlier (each within an ulp of the library forms; the unused rho[2] is dead code)
-    if (s > b) { const double ri = rsqrt(s); rho[0] = fma(2.0 * a, s * ri, -b); rho[1] = fmax(2.2250738585072014e-308, a * ri); rho[2] = -rho[1] / (2.0 * s); }
+    if (s > b) { const double ri = rsqrt_normal(s); rho[0] = fma(2.0 * a, s * ri, -b); rho[1] = fmax(2.2250738585072014e-308, a * ri); rho[2] = -rho[1] / (2.0 * s); }
     else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
   } else if constexpr (LOSS == 2) {     // CauchyLoss
     const double b = a * a, c = 1.0 / b;
@@ -208,14 +221,26 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
   int r = threadIdx.x;
-  for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
-    const int r2 = r + K5_THREADS;
-    const double2 p0 = res.ld(0, r), q0 = res.ld(1, r), ab0 = res.ld(2, r), cw0 = res.ld(3, r);
-    const double2 p1 = res.ld(0, r2), q1 = res.ld(1, r2), ab1 = res.ld(2, r2), cw1 = res.ld(3, r2);
-    accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
-    accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
+  if (nres <= res.cap_s) {                   // the whole list is in shared memory (the normal case): no per-load path select
+    const double2* f0 = res.s, * f1 = res.s + res.cap_s, * f2 = res.s + 2 * res.cap_s, * f3 = res.s + 3 * res.cap_s;
+    for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
+      const int r2 = r + K5_THREADS;
+      const double2 p0 = f0[r], q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
+      const double2 p1 = f0[r2], q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
+      accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
+      accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
+    }
+    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, f0[r], f1[r], f2[r], f3[r], acc);
+  } else {
+    for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
+      const int r2 = r + K5_THREADS;
+      const double2 p0 = res.ld(0, r), q0 = res.ld(1, r), ab0 = res.ld(2, r), cw0 = res.ld(3, r);
+      const double2 p1 = res.ld(0, r2), q1 = res.ld(1, r2), ab1 = res.ld(2, r2), cw1 = res.ld(3, r2);
+      accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
+      accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
+    }
+    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
   }
-  if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
   warp_reduce10(acc, s_part + warp_id() * 10);
 }
 
@@ -295,8 +320,23 @@ struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usa
 // Jacobian in the same pass, so an accepted step needs no second pass over the residuals (the sums are the ones a
 // re-evaluation would give).
 template <int COST, int LOSS>
+__device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
+                                              LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM);
+
+// Hout: J^T J (loss-corrected, unscaled) at the returned x -- what GetCovariance needs, so the caller does not have to
+// evaluate the final point again.
+template <int COST, int LOSS>
 __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                         LMShared* sh, double* s_part PROF_PARAM) {
+                                         LMShared* sh, double* s_part, double Hout[6] PROF_PARAM) {
+  EvalOut ev;
+  lm_solve_impl<COST, LOSS>(P, res, nres, x, sum, sh, s_part, ev PROF_ARG);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) Hout[i] = ev.H[i];
+}
+
+template <int COST, int LOSS>
+__device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
+                                              LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -308,7 +348,6 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   int invalid_in_a_row = 0;
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
-  EvalOut ev;
   request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
   double x_cost = ev.cost;
   double scale[3];
@@ -761,6 +800,8 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   };
 
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
+  double lastH[6] = {0, 0, 0, 0, 0, 0};        // warp 0: J^T J at x from the last solve; valid while have_H (block-uniform)
+  bool have_H = false;
   bool success = true;
   int inner_total = 0, nres = 0, outer = 0;
   if (P.solver_mode == 1) {
@@ -806,12 +847,13 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     double prev_par[3] = {x[0], x[1], x[2]};
     double prev_score = 1.7976931348623157e308;
     int itr;
+    have_H = true;
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
       nres = associate(itr);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
       PROF_T(ts0);
       if (w0) {
-        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part PROF_ARG);                 // :117
+        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part, lastH PROF_ARG);         // :117
         if (lane_id() == 0) {
           sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
           sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
@@ -832,7 +874,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
       const double current_score = sum.final_cost;
       const double rel_improvement = (prev_score - current_score) / prev_score;
       if (itr > P.min_outer) {                                                  // :134-149
-        if (prev_score < current_score) { x[0] = prev_par[0]; x[1] = prev_par[1]; x[2] = prev_par[2]; break; }
+        if (prev_score < current_score) { x[0] = prev_par[0]; x[1] = prev_par[1]; x[2] = prev_par[2]; have_H = false; break; }
         else if (rel_improvement < 0.00001) break;
         else if (sum.last_rel < 0.00001 || sum.n_iterations == 1) break;
       }
@@ -854,8 +896,13 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     if (w0) {
       EvalOut ev;                                                               // GetCovariance :392-433
-      request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-      finish_evals(sh);
+      if (have_H) {                            // the last solve ended at x: its normal equations are the ones wanted
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ev.H[i] = lastH[i];
+      } else {
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
+        finish_evals(sh);
+      }
       double inv[9]; bool ok = true;
       for (int c = 0; c < 3 && ok; ++c) {
         double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
@@ -871,7 +918,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
         cov[35] = f * inv[8]; cov[5] = f * inv[2]; cov[30] = f * inv[6];
         st.success = 1;
       }
-    } else {
+    } else if (!have_H) {
       serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
     }
   }
