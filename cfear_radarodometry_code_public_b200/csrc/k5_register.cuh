@@ -435,27 +435,49 @@ struct GridView { const uint16_t* gs; const float4* gp; };
 
 // GetClosestIdx: exact fp32 nearest neighbour through the bucket grid; ties -> smallest cell index.  *nrm16 receives
 // the winner's normal as packed fp16 pair (the .w of its grid point).
+// A query sees only a handful of candidates (2-3 on the bench workload) spread over 2-3 bucket rows, so the walk is
+// organised for latency rather than throughput: the row ranges of three rows are fetched together, their candidates
+// are taken four at a time through one flattened index (four independent loads in flight), and the running minimum
+// is a single 64-bit key  d2 bits : cell index : position  whose unsigned order is exactly "smaller distance, then
+// smaller cell index" (d2 >= 0, so its bit pattern is monotonic).
 __device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, double radius, uint32_t* nrm16) {
   const float qx = (float)pxd, qy = (float)pyd;             // pointnormal.cpp:241-242
   const float rq = (float)radius * 1.0001f + 1e-3f;         // bucket-range margin only
   int bx0 = (int)floorf((qx - rq - G.ox) * G.inv_g), bx1 = (int)floorf((qx + rq - G.ox) * G.inv_g);
   int by0 = (int)floorf((qy - rq - G.oy) * G.inv_g), by1 = (int)floorf((qy + rq - G.oy) * G.inv_g);
   bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, G.nx - 1); by1 = min(by1, G.ny - 1);
-  float best = 3.4028234e38f; int besti = -1; uint32_t bestn = 0;
+  *nrm16 = 0;
   if (bx0 > bx1) return -1;
-  for (int by = by0; by <= by1; ++by) {
-    const int s = V.gs[bx0 + by * G.nx], e = V.gs[bx1 + by * G.nx + 1];
-#pragma unroll 4
-    for (int a = s; a < e; ++a) {
-      const float4 m = V.gp[a];
-      const float dx = qx - m.x, dy = qy - m.y;
-      float d2 = dx * dx; d2 += dy * dy;
-      const int i = __float_as_int(m.z);
-      if (d2 < best || (d2 == best && i < besti)) { best = d2; besti = i; bestn = __float_as_uint(m.w); }
+  unsigned long long best = ~0ull;
+  for (int byb = by0; byb <= by1; byb += 3) {
+    const bool h1 = byb + 1 <= by1, h2 = byb + 2 <= by1;
+    const int o0 = byb * G.nx, o1 = o0 + G.nx, o2 = o1 + G.nx;
+    const int s0 = V.gs[bx0 + o0], e0 = V.gs[bx1 + o0 + 1];
+    const int s1 = h1 ? V.gs[bx0 + o1] : 0, e1 = h1 ? V.gs[bx1 + o1 + 1] : 0;
+    const int s2 = h2 ? V.gs[bx0 + o2] : 0, e2 = h2 ? V.gs[bx1 + o2 + 1] : 0;
+    const int n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
+    for (int c0 = 0; c0 < total; c0 += 4) {
+      unsigned long long key[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        const int a = c < n0 ? s0 + c : (c < n01 ? s1 + (c - n0) : s2 + (c - n01));
+        key[k] = ~0ull;
+        if (c < total) {
+          const float4 m = V.gp[a];
+          const float dx = qx - m.x, dy = qy - m.y;
+          float d2 = dx * dx; d2 += dy * dy;
+          key[k] = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)(__float_as_uint(m.z) & 0xffffu) << 16) | (unsigned)a;
+        }
+      }
+      best = min(best, min(min(key[0], key[1]), min(key[2], key[3])));
     }
   }
-  *nrm16 = bestn;
-  if (besti >= 0 && (double)best < radius * radius) return besti;   // pointnormal.cpp:250
+  if (best == ~0ull) return -1;
+  const float bd2 = __uint_as_float((uint32_t)(best >> 32));
+  const int besti = (int)((best >> 16) & 0xffffu);
+  *nrm16 = __float_as_uint(V.gp[(int)(best & 0xffffu)].w);
+  if ((double)bd2 < radius * radius) return besti;          // pointnormal.cpp:250
   return -1;
 }
 
@@ -558,13 +580,21 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
     PROF_T(tp0);
     // ---- phase 1 ----
     for (int u = tid; u < nt; u += T) {
+      PROF_T(tq0);
       const int t = t0 + u, i = t / n_src, j = t - i * n_src;
       const RelT R = rel_transform(C, i);
       const double2 mu = C.src_mean[j];
       const double2 nsrc = C.src_normal[j];
       const double qx = R.rc * mu.x - R.rs * mu.y + R.tx, qy = R.rs * mu.x + R.rc * mu.y + R.ty;   // :240
       uint32_t n16;
+#ifdef CFEAR_K5_PROFILE
+      const long long tq1 = clock64() + (long long)(__double_as_longlong(qx) & 0);               // after the transform
+#endif
       const int m = nn_query(C.view[i], C.grid[i], qx, qy, C.radius, &n16);                       // :241
+#ifdef CFEAR_K5_PROFILE
+      const long long tq2 = clock64() + (long long)(m & 0);
+      prof[13] += tq1 - tq0; prof[14] += tq2 - tq1; prof[16] += 1;
+#endif
       bool valid = false;
       if (m >= 0) {
         const double ntx = R.rc * nsrc.x - R.rs * nsrc.y, nty = R.rs * nsrc.x + R.rc * nsrc.y;    // :244
@@ -572,6 +602,9 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
       }
       s_nn[u] = valid ? (uint16_t)m : K5_NONE;
       if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
+#ifdef CFEAR_K5_PROFILE
+      prof[15] += clock64() - tq2;
+#endif
     }
     PROF_T(tp1);
     __syncthreads();
@@ -760,7 +793,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   bool grids_resident = true;
 
 #ifdef CFEAR_K5_PROFILE
-  long long prof[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // 0 association 1 solve 2 grid staging | warp 0, per evaluation: 4 sincos+publish 5 own share 6 wait for the others 7 count |
   // association: 8 phase 1 (own work) 9 wait 10 scan + list 11 phase 2 (own work) 12 wait
   const long long tk0 = clock64();
@@ -930,6 +963,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
 #ifdef CFEAR_K5_PROFILE
     c36[13] = (double)prof[0]; c36[14] = (double)prof[1]; c36[16] = (double)prof[2]; c36[15] = (double)(clock64() - tk0);
     c36[8] = (double)prof[4]; c36[9] = (double)prof[5]; c36[10] = (double)prof[6]; c36[11] = (double)prof[7];
+    c36[23] = (double)prof[13]; c36[24] = (double)prof[14]; c36[25] = (double)prof[15]; c36[26] = (double)prof[16];
     c36[17] = (double)prof[8]; c36[18] = (double)prof[9]; c36[19] = (double)prof[10]; c36[20] = (double)prof[11]; c36[22] = (double)prof[12];
 #endif
   }

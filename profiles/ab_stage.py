@@ -96,4 +96,8 @@ if args.prof:
     print("  association per outer iteration: phase 1 %.0f (+wait %.0f)  scan+list %.0f  phase 2 %.0f (+wait %.0f)"
           % ((cov[:, 17] / no).mean(), (cov[:, 18] / no).mean(), (cov[:, 19] / no).mean(), (cov[:, 20] / no).mean(),
              (cov[:, 22] / no).mean()), flush=True)
+if args.prof:
+    npair = np.maximum(cov[:, 26], 1)
+    print("  phase 1 per pair (thread 0, %.1f pairs per problem): index+transform %.0f  nn_query %.0f  gate+store %.0f"
+          % (npair.mean(), (cov[:, 23] / npair).mean(), (cov[:, 24] / npair).mean(), (cov[:, 25] / npair).mean()), flush=True)
 ctx.close()
