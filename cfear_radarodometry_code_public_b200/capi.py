@@ -57,7 +57,7 @@ STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), (
 SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_update_config", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
-           "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_dev", "cfear_sync",
+           "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
            "cfear_cfar_filter", "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
@@ -108,6 +108,8 @@ def load():
         lib.cfear_register.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.cfear_register_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        lib.cfear_odometry_step_batch_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        lib.cfear_odometry_step_batch_wait.argtypes = [vp, i32]
         lib.cfear_odometry_step_batch_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         lib.cfear_stage_timing.argtypes = [vp, i32, vp]
         lib.cfear_last_counts.argtypes = [vp, i32, vp, vp, vp]
@@ -360,6 +362,25 @@ class Context:
                                                     _ptr(out["poses"]), _ptr(out["cov"]), _ptr(out["stats"]),
                                                     _ptr(out.get("npts")), None), "cfear_odometry_step_batch")
         return out
+
+    def odometry_step_batch_submit(self, polar, mot, kf_slots, cur_slots, out):
+        """Asynchronous half of odometry_step_batch (cfear_odometry_step_batch_submit): every array must be C-contiguous of
+        the right dtype already and stay alive and untouched until odometry_step_batch_wait(ticket).  `out` as in
+        odometry_step_batch, with out["poses"] holding the input poses (last = guess).  Returns the ticket."""
+        n, K = kf_slots.shape
+        for a, dt in ((polar, np.uint8), (kf_slots, np.int32), (cur_slots, np.int32), (out["poses"], np.float64)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise CfearError("odometry_step_batch_submit needs C-contiguous arrays of the ABI dtypes")
+        if mot is not None and (mot.dtype != np.float64 or not mot.flags["C_CONTIGUOUS"]):
+            raise CfearError("odometry_step_batch_submit needs C-contiguous arrays of the ABI dtypes")
+        t = C.c_int32(-1)
+        self._ck(self.lib.cfear_odometry_step_batch_submit(self.h, n, _ptr(polar), _ptr(mot), _ptr(kf_slots), K, _ptr(cur_slots),
+                                                           _ptr(out["poses"]), _ptr(out.get("cov")), _ptr(out.get("stats")),
+                                                           _ptr(out.get("npts")), C.byref(t)), "cfear_odometry_step_batch_submit")
+        return int(t.value)
+
+    def odometry_step_batch_wait(self, ticket):
+        self._ck(self.lib.cfear_odometry_step_batch_wait(self.h, int(ticket)), "cfear_odometry_step_batch_wait")
 
     def last_counts(self, cur_slots):
         cur_slots = np.ascontiguousarray(cur_slots, dtype=np.int32)

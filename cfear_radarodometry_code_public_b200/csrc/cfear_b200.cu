@@ -113,13 +113,16 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
+constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
+
 struct cfear_ctx {
   cfear_config cfg;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> ev;      // 4 per timed step: before K1, after K1, after K3, after K5
   int ev_used = 0;                  // timed steps recorded since the last cfear_stage_timing call
   cudaEvent_t* evset = nullptr;     // current step's 4 events
-  std::vector<cudaEvent_t> chunk_ev;
+  std::vector<cudaEvent_t> chunk_ev, k1_done, ticket_ev;   // host-buffer path: H2D done / staging area read / step done
+  cudaEvent_t polar_free = nullptr; bool polar_dirty = true; int next_ticket = 0;
   int64_t launches = 0;
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
@@ -177,6 +180,9 @@ void cfear_destroy(cfear_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->chunk_ev) cudaEventDestroy(e);
+  for (auto& e : c->k1_done) cudaEventDestroy(e);
+  for (auto& e : c->ticket_ev) cudaEventDestroy(e);
+  if (c->polar_free) cudaEventDestroy(c->polar_free);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -203,6 +209,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->polar_free, cudaEventDisableTiming));
   const int A = cfg->azimuths, R = cfg->range_bins, k = cfg->k_strongest, B = cfg->max_batch;
   c->cap_pts = A * k;
   c->max_cells = cfg->max_cells > 0 ? cfg->max_cells : A * k;
@@ -443,6 +450,7 @@ int cfear_filter(cfear_ctx* c, const uint8_t* polar, int nscans, int32_t* idx_ou
   if (nscans == 0) return CFEAR_OK;
   const int A = c->cfg.azimuths, R = c->cfg.range_bins, k = c->cfg.k_strongest;
   const size_t rows = (size_t)nscans * A;
+  c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
   RC(launch_k1(c, c->d_polar, nscans));
   if (idx_out) CK(cudaMemcpyAsync(idx_out, c->d_kidx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -511,6 +519,7 @@ int cfear_scans_to_cells_batch(cfear_ctx* c, int nscans, const uint8_t* polar, c
   if (nscans == 0) return CFEAR_OK;
   for (int i = 0; i < nscans; ++i) RC(check_slot(c, slots[i]));
   const size_t img = (size_t)c->cfg.azimuths * c->cfg.range_bins;
+  c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, (size_t)nscans * img, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_curslots, slots, (size_t)nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   const bool have_mot = mot != nullptr && c->cfg.compensate;
@@ -657,21 +666,31 @@ int cfear_odometry_step_batch_dev(cfear_ctx* c, int nprob, const uint8_t* d_pola
   return step_dev(c, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats, false);
 }
 
-int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, const double* mot,
-                              const int32_t* kf_slots, int K, const int32_t* cur_slots,
-                              double* poses, double* cov36, cfear_reg_stats* stats,
-                              int32_t* npts_out, int32_t* ncells_out) {
+// Host-buffer path, asynchronous half: enqueues the whole step (H2D in sub-batches on the copy stream, K1 -> K3 -> K5
+// per sub-batch on the compute stream, D2H of the results) and records the ticket's event.  Nothing here waits for the
+// device, so a caller that submits step i+1 before waiting for step i keeps the PCIe link busy while the
+// registration tail of step i (the slowest problem of its last sub-batch) finishes.
+int cfear_odometry_step_batch_submit(cfear_ctx* c, int nprob, const uint8_t* polar, const double* mot,
+                                     const int32_t* kf_slots, int K, const int32_t* cur_slots,
+                                     double* poses, double* cov36, cfear_reg_stats* stats,
+                                     int32_t* npts_out, int32_t* ticket_out) {
   ENTER(c);
   if (!polar || !kf_slots || !cur_slots || !poses) { g_err = "null argument"; return CFEAR_ERR_ARG; }
   if (K < 1 || K > c->cfg.max_keyframes) { g_err = "K must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
   if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
-  if (nprob == 0) return CFEAR_OK;
   for (int i = 0; i < nprob * K; ++i) RC(check_slot(c, kf_slots[i]));
   for (int i = 0; i < nprob; ++i) RC(check_slot(c, cur_slots[i]));
+  if ((int)c->ticket_ev.size() == 0) {
+    for (int i = 0; i < CFEAR_MAX_TICKETS; ++i) {
+      cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->ticket_ev.push_back(e);
+    }
+  }
+  const int ticket = c->next_ticket++ % CFEAR_MAX_TICKETS;
+  if (ticket_out) *ticket_out = ticket;
+  if (nprob == 0) { CK(cudaEventRecord(c->ticket_ev[ticket], c->stream)); return CFEAR_OK; }
   const int A = c->cfg.azimuths, R = c->cfg.range_bins;
   const size_t img = (size_t)A * R;
-  // small arguments first, then the images in chunks on the copy stream so K1 of chunk i overlaps the
-  // host->device copy of chunk i+1
   int32_t* d_kf = c->d_kfslots;
   CK(cudaMemcpyAsync(d_kf, kf_slots, (size_t)nprob * K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_curslots, cur_slots, (size_t)nprob * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -679,12 +698,15 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
   const bool have_mot = mot != nullptr && c->cfg.compensate;
   if (have_mot) CK(cudaMemcpyAsync(c->d_mot, mot, (size_t)nprob * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   // Sub-batches of `chunk` scans: the copy stream moves sub-batch i+1 host->device while the compute stream
-  // runs K1 -> K3 -> K5 on sub-batch i, so only the last sub-batch's kernels are exposed behind PCIe.
+  // runs K1 -> K3 -> K5 on sub-batch i.  The image staging area of sub-batch i is free again as soon as ITS K1 has
+  // read it (k1_done[i]), not when the whole previous step is done.
   const int chunk = 32;
   const int nchunks = (nprob + chunk - 1) / chunk;
-  while ((int)c->chunk_ev.size() < nchunks + 1) {
+  while ((int)c->chunk_ev.size() < nchunks) {
     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->chunk_ev.push_back(e);
+    cudaEvent_t f; CK(cudaEventCreateWithFlags(&f, cudaEventDisableTiming));
+    c->k1_done.push_back(f);
   }
   RC(begin_timed_step(c));
   const int timing = c->timing;
@@ -696,10 +718,14 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
   k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf, c->d_curslots, K, nprob, c->d_slots);
   c->launches++;
   CK(cudaGetLastError());
-  CK(cudaEventRecord(c->chunk_ev[nchunks], c->stream));
-  CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nchunks], 0));          // d_polar free (previous work done)
+  if (c->polar_dirty) {       // another entry point wrote the staging area on the compute stream since the last step
+    CK(cudaEventRecord(c->polar_free, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->polar_free, 0));
+    c->polar_dirty = false;
+  }
   for (int ch = 0; ch < nchunks; ++ch) {
     const int b0 = ch * chunk, nb = std::min(chunk, nprob - b0);
+    CK(cudaStreamWaitEvent(c->copy_stream, c->k1_done[ch], 0));              // no-op until the event has been recorded once
     CK(cudaMemcpyAsync(c->d_polar + b0 * img, polar + b0 * img, nb * img, cudaMemcpyHostToDevice, c->copy_stream));
     CK(cudaEventRecord(c->chunk_ev[ch], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->chunk_ev[ch], 0));
@@ -714,6 +740,7 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
     k1_launch(p, c->stream);
     c->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->k1_done[ch], c->stream));
     RC(launch_k3(c, 0, nb, have_mot ? c->d_mot + 3 * (size_t)b0 : nullptr, c->d_curslots + b0, false, b0));
     RC(launch_k5(c, nb, K + 1, c->d_slots + (size_t)b0 * (K + 1), c->d_poses + (size_t)b0 * (K + 1) * 3,
                  c->d_cov36 + (size_t)b0 * 36, c->d_stats + b0, nullptr, b0));
@@ -723,8 +750,25 @@ int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, con
   if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
   if (npts_out) CK(cudaMemcpyAsync(npts_out, c->d_npts, (size_t)nprob * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  if (ncells_out) RC(cfear_last_counts(c, nprob, cur_slots, nullptr, ncells_out));
+  CK(cudaEventRecord(c->ticket_ev[ticket], c->stream));
+  return CFEAR_OK;
+}
+
+int cfear_odometry_step_batch_wait(cfear_ctx* c, int32_t ticket) {
+  ENTER(c);
+  if (ticket < 0 || ticket >= (int)c->ticket_ev.size()) { g_err = "unknown ticket"; return CFEAR_ERR_ARG; }
+  CK(cudaEventSynchronize(c->ticket_ev[ticket]));
+  return CFEAR_OK;
+}
+
+int cfear_odometry_step_batch(cfear_ctx* c, int nprob, const uint8_t* polar, const double* mot,
+                              const int32_t* kf_slots, int K, const int32_t* cur_slots,
+                              double* poses, double* cov36, cfear_reg_stats* stats,
+                              int32_t* npts_out, int32_t* ncells_out) {
+  int32_t ticket = -1;
+  RC(cfear_odometry_step_batch_submit(c, nprob, polar, mot, kf_slots, K, cur_slots, poses, cov36, stats, npts_out, &ticket));
+  RC(cfear_odometry_step_batch_wait(c, ticket));
+  if (nprob > 0 && ncells_out) RC(cfear_last_counts(c, nprob, cur_slots, nullptr, ncells_out));
   return CFEAR_OK;
 }
 
@@ -780,6 +824,7 @@ int cfear_cfar_filter(cfear_ctx* c, const uint8_t* polar, int nscans, const cfea
   CK(cudaMallocAsync(&d_off, rows * 4, c->stream));
   CK(cudaMallocAsync(&d_n, (size_t)nscans * 4, c->stream));
   CK(cudaMallocAsync(&d_out, std::max<size_t>((size_t)nscans * capacity_per_scan, 1) * sizeof(float4), c->stream));
+  c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
   CfarParams p;
   p.polar = c->d_polar; p.nrows = (int)rows; p.A = A; p.R = R; p.window = cp->window_size; p.guard = cp->nb_guard_cells;
@@ -883,6 +928,7 @@ int cfear_seq_step(cfear_seq* s, const uint8_t* polar) {
   cfear_ctx* c = s->ctx;
   ENTER(c);
   const size_t bytes = (size_t)s->p.nseq * c->cfg.azimuths * c->cfg.range_bins;
+  c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, bytes, cudaMemcpyHostToDevice, c->stream));   // stream-ordered: the previous step's K1 is done
   return seq_step_common(s, c->d_polar);
 }

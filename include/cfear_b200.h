@@ -172,6 +172,16 @@ int cfear_odometry_step_batch(cfear_ctx* ctx, int nprob, const uint8_t* polar, c
                               const int32_t* kf_slots, int K, const int32_t* cur_slots,
                               double* poses, double* cov36, cfear_reg_stats* stats,
                               int32_t* npts_out, int32_t* ncells_out);
+/* The same step split in two so that consecutive steps pipeline: _submit enqueues the host->device copies, the kernels
+ * and the device->host copies of the results and returns at once with a ticket; _wait blocks until that step's results
+ * are in the caller's buffers.  Up to 8 steps may be in flight; every buffer passed to _submit (inputs and outputs,
+ * ideally pinned) must stay valid and untouched until its _wait.  Submitting step i+1 before waiting for step i keeps
+ * the PCIe link busy during the registration tail of step i.  cfear_odometry_step_batch == _submit + _wait. */
+int cfear_odometry_step_batch_submit(cfear_ctx* ctx, int nprob, const uint8_t* polar, const double* mot,
+                                     const int32_t* kf_slots, int K, const int32_t* cur_slots,
+                                     double* poses, double* cov36, cfear_reg_stats* stats,
+                                     int32_t* npts_out, int32_t* ticket_out);
+int cfear_odometry_step_batch_wait(cfear_ctx* ctx, int32_t ticket);
 /* Same with every buffer already resident on the device (d_ prefix = device pointer), asynchronous on the
  * context's stream (cfear_sync to wait).  d_poses [nprob][K+1][3] in/out, d_cov36 [nprob][36] (reg_cov.back(),
  * GetCovariance layout), d_stats [nprob]. */

@@ -255,6 +255,47 @@ def test_odometry_step_batch_matches_oracle_pipeline(orc):
     c.close()
 
 
+def test_submit_wait_pipelining_matches_synchronous_calls(orc):
+    """cfear_odometry_step_batch_submit/_wait with two steps in flight (two sub-batches each, another entry point writing
+    the image staging area in between) returns bit for bit what the synchronous call returns."""
+    K, radius, base, rep = 2, 3.0, 3, 12
+    nprob = base * rep                       # 36 problems -> two sub-batches of the host-buffer path
+    c = capi.Context(max_batch=nprob, max_cellsets=base * K + nprob, max_keyframes=K, cost="P2D", loss="Huber",
+                     weight_opt=4, regularization=0.1, radius=radius)
+    polar, poses, mot, kf = [], [], [], []
+    for b in range(base):
+        im, tp = helpers.scan_images(40 + b, K)
+        for i in range(K):
+            c.surface_points(c.filter(im[i][None])["clouds"][0], b * K + i)
+        polar.append(im[K]); P = tp.copy(); P[K] = tp[K - 1]; poses.append(P); mot.append(np.zeros(3)); kf.append([b * K, b * K + 1])
+    polar = np.ascontiguousarray(np.tile(np.stack(polar), (rep, 1, 1)))
+    kf = np.ascontiguousarray(np.tile(np.array(kf, np.int32), (rep, 1)))
+    mot = np.ascontiguousarray(np.tile(np.stack(mot), (rep, 1)))
+    cur = (base * K + np.arange(nprob)).astype(np.int32)
+    posesA = np.ascontiguousarray(np.tile(np.stack(poses), (rep, 1, 1)))
+    posesB = posesA.copy(); posesB[:, K, 0] += 0.3; posesB[:, K, 2] -= 0.01      # a second step with another guess
+    refA = c.odometry_step_batch(polar, mot, kf, cur, posesA)
+    refB = c.odometry_step_batch(polar, mot, kf, cur, posesB)
+    c.filter(polar[:2])                       # writes the staging area on the compute stream (polar_dirty path)
+
+    def outs(p):
+        return dict(poses=p.copy(), cov=np.zeros((nprob, 36)), stats=np.zeros(nprob, capi.STATS_DTYPE), npts=np.zeros(nprob, np.int32))
+    oA, oB, oA2 = outs(posesA), outs(posesB), outs(posesA)
+    tA = c.odometry_step_batch_submit(polar, mot, kf, cur, oA)
+    tB = c.odometry_step_batch_submit(polar, mot, kf, cur, oB)
+    c.odometry_step_batch_wait(tA)
+    tA2 = c.odometry_step_batch_submit(polar, mot, kf, cur, oA2)
+    c.odometry_step_batch_wait(tB)
+    c.odometry_step_batch_wait(tA2)
+    for o, r in ((oA, refA), (oB, refB), (oA2, refA)):
+        assert np.array_equal(o["poses"], r["poses"]) and np.array_equal(o["cov"], r["cov"])
+        assert np.array_equal(o["stats"], r["stats"]) and np.array_equal(o["npts"], r["npts"])
+    assert not np.array_equal(refA["poses"][:, K], posesA[:, K])
+    with pytest.raises(capi.CfearError):
+        c.odometry_step_batch_wait(99)
+    c.close()
+
+
 @pytest.mark.parametrize("cost,wopt,submap,wint,radius", [("P2L", 0, 3, True, 3.5), ("P2D", 4, 4, True, 3.0)])
 def test_sequences_lockstep_match_oracle_replay(orc, cost, wopt, submap, wint, radius):
     """cfear_seq_*: OdometryKeyframeFuser bookkeeping on the device, 3 sequences advancing together, no host sync per
