@@ -190,8 +190,25 @@ struct LMShared {
   int out_niter, out_usable, out_success, out_inner;
 };
 
-__device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+// Named barriers A / B of the evaluation service.  Warp 0 and the serving warps reach them from different places in
+// the code, each warp converged (the __syncwarp makes that explicit) -- the producer / consumer use of bar.sync the
+// PTX ISA documents: .aligned constrains the threads of a WARP to execute the same barrier instruction, not the warps
+// of a block.  compute-sanitizer's synccheck nevertheless reports "divergent thread(s) in block" for this form; the
+// two forms it accepts (CFEAR_K5_BAR=0: unaligned `barrier.sync`; =2: bar.sync inside one non-inlined function, so
+// every warp executes the same instruction) cost 5 % of the kernel (0.387 vs 0.368 ms) and are kept as build options.
+#ifndef CFEAR_K5_BAR
+#define CFEAR_K5_BAR 1
+#endif
+#if CFEAR_K5_BAR == 0
+__device__ __forceinline__ void bar_a() { asm volatile("barrier.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_b() { asm volatile("barrier.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+#elif CFEAR_K5_BAR == 1
+__device__ __forceinline__ void bar_a() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_b() { __syncwarp(); asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+#else
+__device__ __noinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __noinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+#endif
 
 // Warp reduction of the 10 sums by recursive halving: at each step a lane hands the half of its values its partner
 // keeps to that partner, so 5+3+2+1+1 = 12 exchanges replace the 50 of ten separate butterflies.  Ends with sum i in the
