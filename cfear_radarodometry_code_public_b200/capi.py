@@ -57,7 +57,7 @@ STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), (
 SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_update_config", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
-           "cfear_register_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_sync",
+           "cfear_register_batch", "cfear_get_cost_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
            "cfear_cfar_filter", "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
@@ -107,6 +107,7 @@ def load():
         lib.cfear_nearest.argtypes = [vp, i32, vp, i32, C.c_double, vp]
         lib.cfear_register.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.cfear_register_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
+        lib.cfear_get_cost_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch_wait.argtypes = [vp, i32]
@@ -338,6 +339,17 @@ class Context:
         self._ck(self.lib.cfear_register_batch(self.h, nprob, _ptr(slots), ns, _ptr(p), _ptr(cov), _ptr(st), _ptr(assoc)),
                  "cfear_register_batch")
         return p, cov.reshape(nprob, 6, 6), st, assoc
+
+    def get_cost_batch(self, slots, poses):
+        """n_scan_normal_reg::GetCost for (nprob, nscans) slot tables and (nprob, nscans, 3) poses.
+        Returns (cost [nprob], num_residuals [nprob], ok [nprob])."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n, ns = slots.shape
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(n, ns, 3)
+        cost = np.zeros(n); nres = np.zeros(n, np.int32); ok = np.zeros(n, np.int32)
+        self._ck(self.lib.cfear_get_cost_batch(self.h, n, _ptr(slots), ns, _ptr(poses), _ptr(cost), _ptr(nres), _ptr(ok)),
+                 "cfear_get_cost_batch")
+        return cost, nres, ok
 
     def register(self, slots, poses):
         slots = np.ascontiguousarray(slots, dtype=np.int32).reshape(1, -1)

@@ -393,7 +393,8 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
 }
 
 static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
-                     cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0, const int32_t* d_nscans_pp = nullptr) {
+                     cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0, const int32_t* d_nscans_pp = nullptr,
+                     int solver_mode_override = -1) {
   RegParams p;
   p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.nscans_pp = d_nscans_pp; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
   p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
@@ -401,6 +402,7 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
   p.radius = c->cfg.reg_radius;
+  if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
 #define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); break;
@@ -624,6 +626,29 @@ int cfear_register_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nsca
   if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
   if (assoc_out) CK(cudaMemcpyAsync(assoc_out, c->d_assoc, assoc_n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return CFEAR_OK;
+}
+
+// n_scan_normal_reg::GetCost for nprob independent (cell sets, poses) problems in one launch.
+int cfear_get_cost_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nscans, const double* poses,
+                         double* cost_out, int32_t* num_residuals_out, int32_t* ok_out) {
+  ENTER(c);
+  if (nprob < 0 || !slots || !poses || !cost_out) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (nscans < 2 || nscans > c->cfg.max_keyframes + 1) { g_err = "nscans must be in [2, max_keyframes+1]"; return CFEAR_ERR_ARG; }   // n_scan_normal.cpp:189
+  if (nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (nprob == 0) return CFEAR_OK;
+  for (size_t i = 0; i < (size_t)nprob * nscans; ++i) RC(check_slot(c, slots[i]));
+  CK(cudaMemcpyAsync(c->d_slots, slots, (size_t)nprob * nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  RC(launch_k5(c, nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, nullptr, CFEAR_SOLVER_COST_ONLY));
+  std::vector<cfear_reg_stats> st((size_t)nprob);
+  CK(cudaMemcpyAsync(st.data(), c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nprob; ++i) {
+    cost_out[i] = st[i].final_cost;
+    if (num_residuals_out) num_residuals_out[i] = st[i].num_residuals;
+    if (ok_out) ok_out[i] = st[i].success;
+  }
   return CFEAR_OK;
 }
 

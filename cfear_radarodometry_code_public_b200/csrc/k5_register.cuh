@@ -854,7 +854,26 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   bool have_H = false;
   bool success = true;
   int inner_total = 0, nres = 0, outer = 0;
-  if (P.solver_mode == 1) {
+  if (P.solver_mode == 2) {
+    // cost only -- n_scan_normal_reg::GetCost (n_scan_normal.cpp:187-213): one association at the registration radius
+    // (itr_ is past 1 whenever GetCost runs after a Register) and one evaluation of 1/2 sum w rho(s); no solve, the
+    // pose is returned untouched.  Used by the fuser's covariance-by-sampling (odometrykeyframefuser.cpp:261-380).
+    nres = associate(2);
+    outer = 0;
+    if (nres * per_block <= 1) success = false;                                 // :205-208
+    else {
+      if (w0) {
+        EvalOut ev;
+        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
+        if (lane_id() == 0) sh->out_final_cost = ev.cost;
+        finish_evals(sh);
+      } else {
+        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+      }
+      sum.final_cost = sh->out_final_cost;
+      __syncthreads();
+    }
+  } else if (P.solver_mode == 1) {
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
@@ -941,7 +960,10 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   double cov[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) cov[i] = 0.0;
-  if (success) {
+  if (success && P.solver_mode == 2) {
+    st.score = sum.final_cost / st.num_residuals;                               // score_ = score / max(#residuals, 1)  :211
+    st.success = 1;
+  } else if (success) {
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
     if (w0) {

@@ -23,6 +23,7 @@
  *   cfear_register / _batch             n_scan_normal_reg::Register (n_scan_normal.h:37, n_scan_normal.cpp:82-187)
  *                                       incl. BuildOptimizationProblem/AddScanPairCost (:215-391),
  *                                       SolveOptimizationProblem (:443-452), GetCovariance (:392-433)
+ *   cfear_get_cost_batch                n_scan_normal_reg::GetCost (n_scan_normal.h:41, n_scan_normal.cpp:187-213)
  *   cfear_odometry_step_batch[_dev]     one radarReader loop body (src/offline_odometry.cpp:103-108) for many
  *                                       independent scans: CallbackOffline -> Compensate -> MapPointNormal -> Register
  */
@@ -45,7 +46,7 @@ enum { CFEAR_LOSS_NONE = 0, CFEAR_LOSS_HUBER = 1, CFEAR_LOSS_CAUCHY = 2, CFEAR_L
 enum { CFEAR_WEIGHT_UNIFORM = 0, CFEAR_WEIGHT_SIM_N = 1, CFEAR_WEIGHT_SIM_DIRECTION = 2,
        CFEAR_WEIGHT_SIM_SCALE = 3, CFEAR_WEIGHT_COMBINED = 4 };
 /* inner solver: faithful Ceres trust-region LM loop, or fixed-count Gauss-Newton/IRLS */
-enum { CFEAR_SOLVER_CERES_LM = 0, CFEAR_SOLVER_GN_FIXED = 1 };
+enum { CFEAR_SOLVER_CERES_LM = 0, CFEAR_SOLVER_GN_FIXED = 1, CFEAR_SOLVER_COST_ONLY = 2 /* internal: cfear_get_cost_batch */ };
 
 /* status codes */
 enum { CFEAR_OK = 0, CFEAR_ERR_ARG = -1, CFEAR_ERR_CUDA = -2, CFEAR_ERR_CAPACITY = -3, CFEAR_ERR_NO_DEVICE = -4 };
@@ -163,6 +164,15 @@ int cfear_register(cfear_ctx* ctx, const int32_t* slots, int nscans, double* pos
  * last outer iteration's association per (keyframe, src cell), -1 = none (scan_associations_, registration.h:105). */
 int cfear_register_batch(cfear_ctx* ctx, int nprob, const int32_t* slots, int nscans, double* poses,
                          double* cov36, cfear_reg_stats* stats, int32_t* assoc_out);
+
+/* n_scan_normal_reg::GetCost (n_scan_normal.h:41, n_scan_normal.cpp:187-213) for nprob independent problems: associate
+ * once at the poses given (all fixed, the last set is the source) with the registration radius, return the robustified
+ * cost 1/2 sum w rho(|r|^2) (ceres::Problem::Evaluate with default options), the number of scalar residuals and
+ * ok = 0 where GetCost returns false (<= 1 residual).  slots [nprob][nscans], poses [nprob][nscans][3].
+ * num_residuals_out / ok_out may be NULL.  This is what approximateCovarianceBySampling
+ * (odometrykeyframefuser.cpp:261-380) calls once per pose sample; here all samples go in one launch. */
+int cfear_get_cost_batch(cfear_ctx* ctx, int nprob, const int32_t* slots, int nscans, const double* poses,
+                         double* cost_out, int32_t* num_residuals_out, int32_t* ok_out);
 
 /* ---- whole per-scan path, many independent scans ----------------------------------------------------------------- */
 /* For b in [0,nprob): polar[b] -> k-strongest -> cloud -> Compensate(mot[b]) -> surface points into cur_slots[b]

@@ -412,6 +412,58 @@ class n_scan_normal_reg : public Registration {
     return st.success != 0;
   }
 
+  // n_scan_normal.cpp:187-213.  Cost of the problem built at the poses given (nothing is optimised).  The per-residual
+  // values stay on the device: `residuals` is sized to the number of scalar residuals and zero-filled (the only caller,
+  // approximateCovarianceBySampling, reads the score alone).
+  bool GetCost(std::vector<MapNormalPtr>& scans, std::vector<Affine3d>& Tsrc, double& score, std::vector<double>& residuals) {
+    std::vector<std::vector<Affine3d> > one(1, Tsrc);
+    std::vector<double> scores; std::vector<int> nres; std::vector<bool> ok;
+    GetCostBatch(scans, one, scores, nres, ok);
+    score = scores[0];
+    residuals.assign((size_t)std::max(nres[0], 0), 0.0);
+    if (ok[0]) score_ = score / std::max(nres[0], 1);               // :211
+    return ok[0];
+  }
+  // The same for many pose hypotheses of one set of scans in a single launch (what the sampling loop of
+  // odometrykeyframefuser.cpp:293-320 does one call at a time).
+  void GetCostBatch(std::vector<MapNormalPtr>& scans, const std::vector<std::vector<Affine3d> >& Tsrc_samples,
+                    std::vector<double>& scores, std::vector<int>& num_residuals, std::vector<bool>& ok) {
+    const size_t n_scans = scans.size(), ns = Tsrc_samples.size();
+    assert(n_scans >= 2);
+    Backend& b = Backend::get();
+    cfear_config& cfg = b.cfg();
+    cfg.cost = cost_ == P2P ? CFEAR_COST_P2P : (cost_ == P2L ? CFEAR_COST_P2L : CFEAR_COST_P2D);
+    cfg.loss = (int)loss_; cfg.loss_limit = loss_limit_; cfg.weight_opt = (int)weight_opt_;
+    cfg.cov_scale = cov_scale_; cfg.regularization = regularization_; cfg.reg_radius = radius_;
+    b.apply();
+    std::vector<int32_t> slots(ns * n_scans);
+    std::vector<double> poses(ns * n_scans * 3), par;
+    for (size_t s = 0; s < ns; ++s) {
+      assert(Tsrc_samples[s].size() == n_scans);
+      for (size_t i = 0; i < n_scans; ++i) {
+        slots[s * n_scans + i] = scans[i]->slot();
+        Affine3dToVectorXYeZ(Tsrc_samples[s][i], par);
+        for (int k = 0; k < 3; ++k) poses[(s * n_scans + i) * 3 + k] = par[k];
+      }
+    }
+    scores.assign(ns, 0.0); num_residuals.assign(ns, 0); ok.assign(ns, false);
+    std::vector<int32_t> nr(ns), okv(ns);
+    const size_t max_batch = (size_t)cfg.max_batch;
+    for (size_t s0 = 0; s0 < ns; s0 += max_batch) {
+      const int nb = (int)std::min(max_batch, ns - s0);
+      if (cfear_get_cost_batch(b.ctx(), nb, slots.data() + s0 * n_scans, (int)n_scans, poses.data() + s0 * n_scans * 3,
+                               scores.data() + s0, nr.data() + s0, okv.data() + s0) != CFEAR_OK)
+        throw std::runtime_error(std::string("cfear_get_cost_batch: ") + cfear_last_error());
+    }
+    for (size_t s = 0; s < ns; ++s) { num_residuals[s] = nr[s]; ok[s] = okv[s] != 0; }
+  }
+  // n_scan_normal.cpp:435-441 (summary_ of the last Register; three parameters in the reduced problem)
+  bool GetCovarianceScaler(double& cov_scale) {
+    if (summary_.num_residuals - 3 == 0) return false;
+    cov_scale = summary_.final_cost / (summary_.num_residuals - 3);
+    return true;
+  }
+
  private:
   double cov_scale_ = 1;
   double regularization_ = 0.01;
@@ -419,10 +471,76 @@ class n_scan_normal_reg : public Registration {
   unsigned int max_itr_solver_ = 20;
 };
 
+// ---- small dense linear algebra for the covariance-by-sampling fit (the reference uses Eigen there) ------------------
+namespace detail {
+// min |A q - c|_2, A row-major m x n with m >= n, by Householder QR on column-equilibrated A.  False if rank deficient.
+inline bool lstsq_qr(std::vector<double> A, int m, int n, std::vector<double> c, double* q) {
+  std::vector<double> cs(n, 1.0);
+  for (int j = 0; j < n; ++j) {
+    double mx = 0; for (int i = 0; i < m; ++i) mx = std::max(mx, std::fabs(A[(size_t)i * n + j]));
+    if (mx == 0) return false;
+    cs[j] = 1.0 / mx;
+    for (int i = 0; i < m; ++i) A[(size_t)i * n + j] *= cs[j];
+  }
+  for (int k = 0; k < n; ++k) {
+    double nrm = 0; for (int i = k; i < m; ++i) nrm += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+    nrm = std::sqrt(nrm);
+    if (nrm < 1e-13) return false;
+    const double alpha = A[(size_t)k * n + k] > 0 ? -nrm : nrm;
+    std::vector<double> v(m, 0.0);
+    for (int i = k; i < m; ++i) v[i] = A[(size_t)i * n + k];
+    v[k] -= alpha;
+    double vv = 0; for (int i = k; i < m; ++i) vv += v[i] * v[i];
+    if (vv == 0) continue;
+    for (int j = k; j < n; ++j) {
+      double d = 0; for (int i = k; i < m; ++i) d += v[i] * A[(size_t)i * n + j];
+      d = 2 * d / vv;
+      for (int i = k; i < m; ++i) A[(size_t)i * n + j] -= d * v[i];
+    }
+    double d = 0; for (int i = k; i < m; ++i) d += v[i] * c[i];
+    d = 2 * d / vv;
+    for (int i = k; i < m; ++i) c[i] -= d * v[i];
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    double t = c[k];
+    for (int j = k + 1; j < n; ++j) t -= A[(size_t)k * n + j] * q[j];
+    q[k] = t / A[(size_t)k * n + k];
+  }
+  for (int j = 0; j < n; ++j) q[j] *= cs[j];
+  return true;
+}
+// eigenvalues of a symmetric 3x3 (cyclic Jacobi)
+inline void eig3_sym(const double H[9], double ev[3]) {
+  double a[9]; for (int i = 0; i < 9; ++i) a[i] = H[i];
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    const double off = std::fabs(a[1]) + std::fabs(a[2]) + std::fabs(a[5]);
+    if (off < 1e-300 || off < 1e-18 * (std::fabs(a[0]) + std::fabs(a[4]) + std::fabs(a[8]))) break;
+    for (int p = 0; p < 3; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (a[3 * p + q] == 0) continue;
+      const double theta = (a[3 * q + q] - a[3 * p + p]) / (2 * a[3 * p + q]);
+      const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+      const double c = 1 / std::sqrt(t * t + 1), sn = t * c;
+      for (int k = 0; k < 3; ++k) { const double akp = a[3 * k + p], akq = a[3 * k + q]; a[3 * k + p] = c * akp - sn * akq; a[3 * k + q] = sn * akp + c * akq; }
+      for (int k = 0; k < 3; ++k) { const double apk = a[3 * p + k], aqk = a[3 * q + k]; a[3 * p + k] = c * apk - sn * aqk; a[3 * q + k] = sn * apk + c * aqk; }
+    }
+  }
+  ev[0] = a[0]; ev[1] = a[4]; ev[2] = a[8];
+}
+inline bool inv3(const double H[9], double I[9]) {
+  const double c00 = H[4] * H[8] - H[5] * H[7], c01 = H[5] * H[6] - H[3] * H[8], c02 = H[3] * H[7] - H[4] * H[6];
+  const double det = H[0] * c00 + H[1] * c01 + H[2] * c02;
+  if (det == 0 || !std::isfinite(det)) return false;
+  I[0] = c00 / det; I[1] = (H[2] * H[7] - H[1] * H[8]) / det; I[2] = (H[1] * H[5] - H[2] * H[4]) / det;
+  I[3] = c01 / det; I[4] = (H[0] * H[8] - H[2] * H[6]) / det; I[5] = (H[2] * H[3] - H[0] * H[5]) / det;
+  I[6] = c02 / det; I[7] = (H[1] * H[6] - H[0] * H[7]) / det; I[8] = (H[0] * H[4] - H[1] * H[3]) / det;
+  return true;
+}
+}  // namespace detail
+
 // ---- OdometryKeyframeFuser (odometrykeyframefuser.h:66-293, odometrykeyframefuser.cpp:23-259, 397-416, 470-494) -----
 // Per-scan orchestration: motion compensation with the previous motion, constant-velocity guess, registration against
-// the sliding window of keyframes, sanity check, keyframe insertion.  ROS publishing / TF / pose-graph logging and
-// covariance-by-sampling are out of scope.  Quirk kept from the reference: the return value of Register() lands in a
+// the sliding window of keyframes, sanity check, keyframe insertion, optional covariance by cost sampling.  ROS
+// publishing / TF / pose-graph logging are out of scope.  Quirk kept from the reference: the return value of Register() lands in a
 // shadowed local (odometrykeyframefuser.cpp:184-186), so the pose in T_vek.back() is used whether or not it succeeded.
 struct RadarScan {                         // the members of types.h:93-143 the pose path touches
   Affine3d T;                              // GetPose()
@@ -448,6 +566,12 @@ class OdometryKeyframeFuser {
     double loss_limit_ = 0.1;
     double covar_scale_ = 1.0;
     double regularization_ = 0.0;
+    // covariance by cost sampling (odometrykeyframefuser.h:104-110)
+    bool estimate_cov_by_sampling = false;
+    double cov_sampling_xy_range = 0.4;
+    double cov_sampling_yaw_range = 0.0043625;
+    unsigned int cov_sampling_samples_per_axis = 3;
+    double cov_sampling_covariance_scaler = 4.0;
   };
 
   OdometryKeyframeFuser(const Parameters& pars, bool disable_callback = false) : par(pars) {
@@ -487,6 +611,64 @@ class OdometryKeyframeFuser {
     return true;
   }
 
+  // odometrykeyframefuser.cpp:261-380.  The samples_per_axis^3 cost samples (yaw-major, then x, then y, like the
+  // reference's loops) are evaluated in ONE cfear_get_cost_batch launch; the quadric fit, convexity check and scaling
+  // follow the reference (its bdcSvd least-squares solve is a Householder QR here).  Writing the samples to a csv file
+  // (cov_samples_to_file_as_well) is not mirrored.
+  bool approximateCovarianceBySampling(std::vector<MapNormalPtr>& scans_vek, const std::vector<Affine3d>& T_vek, Matrix6d& cov_sampled) {
+    const Affine3d T_best_guess = T_vek.back();
+    const double xy_sample_range = par.cov_sampling_xy_range * 0.5, theta_range = par.cov_sampling_yaw_range * 0.5;
+    const unsigned int n = par.cov_sampling_samples_per_axis;
+    const std::vector<double> xy_samples = linspace(-xy_sample_range, xy_sample_range, (int)n);
+    const std::vector<double> theta_samples = linspace(-theta_range, theta_range, (int)n);
+    std::vector<std::vector<Affine3d> > samples;
+    std::vector<double> sx, sy, syaw;
+    const double yaw0 = std::atan2(T_best_guess(1, 0), T_best_guess(0, 0));
+    for (unsigned int it = 0; it < n; ++it)
+      for (unsigned int ix = 0; ix < n; ++ix)
+        for (unsigned int iy = 0; iy < n; ++iy) {
+          std::vector<Affine3d> T(T_vek);
+          T.back() = vectorToAffine3d(T_best_guess(0, 3) + xy_samples[ix], T_best_guess(1, 3) + xy_samples[iy], yaw0 + theta_samples[it]);
+          samples.push_back(T);
+          sx.push_back(xy_samples[ix]); sy.push_back(xy_samples[iy]); syaw.push_back(theta_samples[it]);
+        }
+    std::vector<double> cost; std::vector<int> nres; std::vector<bool> ok;
+    radar_reg->GetCostBatch(scans_vek, samples, cost, nres, ok);
+    const int m = (int)samples.size();
+    if (m < 10) return false;
+    // f(x,y,z) = a x^2 + b y^2 + c z^2 + d xy + e yz + f zx + g x + h y + i z + j
+    std::vector<double> A((size_t)m * 10);
+    for (int r = 0; r < m; ++r) {
+      const double x = sx[r], y = sy[r], z = syaw[r];
+      const double row[10] = {x * x, y * y, z * z, x * y, y * z, z * x, x, y, z, 1.0};
+      for (int k = 0; k < 10; ++k) A[(size_t)r * 10 + k] = row[k];
+    }
+    double q[10];
+    if (!detail::lstsq_qr(A, m, 10, cost, q)) return false;
+    const double H[9] = {2 * q[0], q[3], q[5], q[3], 2 * q[1], q[4], q[5], q[4], 2 * q[2]};
+    double ev[3];
+    detail::eig3_sym(H, ev);
+    if (!(ev[0] > 0.0) || !(ev[1] > 0.0) || !(ev[2] > 0.0)) return false;   // not convex: sampling not used for this scan
+    double score_scale = 1.0, Hi[9];
+    if (!radar_reg->GetCovarianceScaler(score_scale) || !detail::inv3(H, Hi)) return false;
+    const double f = 2.0 * score_scale * par.cov_sampling_covariance_scaler;
+    cov_sampled = Matrix6d::Identity();
+    cov_sampled(0, 0) = f * Hi[0]; cov_sampled(0, 1) = f * Hi[1]; cov_sampled(1, 0) = f * Hi[3]; cov_sampled(1, 1) = f * Hi[4];
+    cov_sampled(5, 5) = f * Hi[8];
+    cov_sampled(0, 5) = f * Hi[2]; cov_sampled(1, 5) = f * Hi[5]; cov_sampled(5, 0) = f * Hi[6]; cov_sampled(5, 1) = f * Hi[7];
+    return true;
+  }
+  // odometrykeyframefuser.cpp:497-523
+  static std::vector<double> linspace(double start, double end, int num) {
+    std::vector<double> v;
+    if (num == 0) return v;
+    if (num == 1) { v.push_back(start); return v; }
+    const double delta = (end - start) / (num - 1);
+    for (int i = 0; i < num - 1; ++i) v.push_back(start + delta * i);
+    v.push_back(end);
+    return v;
+  }
+
   bool updated = false;
   size_t nr_callbacks_ = 0, frame_nr_ = 0;
   double distance_traveled = 0;
@@ -524,6 +706,10 @@ class OdometryKeyframeFuser {
     const Affine3d Tmot_current = T_prev.inverse() * Tcurrent;
     if (!AccelerationVelocitySanityCheck(Tmot, Tmot_current)) Tcurrent = Tguess;    // :197-199
     Tmot = T_prev.inverse() * Tcurrent;
+    if (par.estimate_cov_by_sampling && !par.disable_registration) {              // :203-208
+      Matrix6d cov_sampled;
+      if (approximateCovarianceBySampling(scans_vek, T_vek, cov_sampled)) { cov_current = cov_sampled; cov_vek.back() = cov_sampled; }
+    }
     const Affine3d Tkeydiff = keyframes_.back().T.inverse() * Tcurrent;
     const bool fuse = KeyFrameBasedFuse(Tkeydiff, par.use_keyframe, par.min_keyframe_dist_, par.min_keyframe_rot_deg_);
     if (fuse) {                                                      // `success && fuse` with success always true

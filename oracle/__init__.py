@@ -152,6 +152,49 @@ def register(sets, poses, cfg, want_assoc=False):
     return bool(ok), p, cov36.reshape(6, 6), st, assoc
 
 
+def get_cost(sets, poses, cfg):
+    """n_scan_normal_reg::GetCost at fixed poses (K+1, 3).  Returns (ok, cost, num_residuals)."""
+    ci, cd = cfg
+    offs, mean, normal, cov, plan, ns = concat_cellsets(sets)
+    p = np.ascontiguousarray(poses, dtype=np.float64)
+    cost = C.c_double(0.0); nres = C.c_int32(0)
+    ok = lib().orc_get_cost(_p(ci), _p(cd), len(sets), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
+                            _p(p), C.byref(cost), C.byref(nres))
+    return bool(ok), float(cost.value), int(nres.value)
+
+
+def sampled_covariance(sets, poses, cfg, final_cost, num_residuals, xy_range=0.4, yaw_range=0.0043625, samples_per_axis=3,
+                       covariance_scaler=4.0):
+    """OdometryKeyframeFuser::approximateCovarianceBySampling (odometrykeyframefuser.cpp:261-380): sample GetCost on a
+    samples_per_axis^3 grid around poses[-1] (yaw-major, then x, then y), least-squares quadric fit (the reference's
+    bdcSvd solve == numpy lstsq), Hessian convexity check, cov = 2 H^-1 * cov_scale * covariance_scaler with
+    cov_scale = final_cost / (num_residuals - 3) of the preceding Register (GetCovarianceScaler, n_scan_normal.cpp:435-441).
+    Returns (success, cov6x6, samples [n^3, 4] = x, y, yaw, cost)."""
+    poses = np.asarray(poses, dtype=np.float64)
+    xs = np.linspace(-xy_range * 0.5, xy_range * 0.5, samples_per_axis)
+    ts = np.linspace(-yaw_range * 0.5, yaw_range * 0.5, samples_per_axis)
+    rows = []
+    for t in ts:
+        for x in xs:
+            for y in xs:
+                p = poses.copy()
+                p[-1] = [poses[-1, 0] + x, poses[-1, 1] + y, poses[-1, 2] + t]
+                _, c, _ = get_cost(sets, p, cfg)
+                rows.append((x, y, t, c))
+    S = np.array(rows)
+    x, y, z, c = S.T
+    A = np.stack([x * x, y * y, z * z, x * y, y * z, z * x, x, y, z, np.ones_like(x)], 1)
+    q = np.linalg.lstsq(A, c, rcond=None)[0]
+    H = np.array([[2 * q[0], q[3], q[5]], [q[3], 2 * q[1], q[4]], [q[5], q[4], 2 * q[2]]])
+    cov6 = np.eye(6)
+    if np.any(np.linalg.eigvalsh(H) <= 0.0) or num_residuals - 3 == 0:
+        return False, cov6, S
+    c3 = 2.0 * np.linalg.inv(H) * (final_cost / (num_residuals - 3)) * covariance_scaler
+    cov6[0:2, 0:2] = c3[0:2, 0:2]; cov6[5, 5] = c3[2, 2]
+    cov6[0, 5] = c3[0, 2]; cov6[1, 5] = c3[1, 2]; cov6[5, 0] = c3[2, 0]; cov6[5, 1] = c3[2, 1]
+    return True, cov6, S
+
+
 def eval_cost(cfg, res8, x):
     ci, cd = cfg
     res8 = np.ascontiguousarray(res8, dtype=np.float64)

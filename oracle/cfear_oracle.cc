@@ -867,6 +867,40 @@ int orc_register(const int32_t* cfg_i, const double* cfg_d, int nscans, const in
 
 int orc_regstats_size() { return (int)sizeof(RegStats); }
 
+// n_scan_normal_reg::GetCost (n_scan_normal.cpp:187-213): BuildOptimizationProblem at the poses given, then
+// ceres::Problem::Evaluate with default options = 1/2 sum w rho(s) over the residual blocks.  itr_ is whatever the last
+// Register left (>= 2), so the association radius is cfg.radius (:222).  Returns 1 / 0 like GetCost's bool.
+int orc_get_cost(const int32_t* cfg_i, const double* cfg_d, int nscans, const int32_t* offsets,
+                 const double* mean, const double* normal, const double* cov, const double* planarity,
+                 const int32_t* nsamples, const double* poses, double* cost_out, int32_t* num_residuals_out) {
+  RegCfg cfg;
+  cfg.cost = cfg_i[0]; cfg.loss = cfg_i[1]; cfg.weight_opt = cfg_i[2];
+  cfg.max_outer = cfg_i[3]; cfg.min_outer = cfg_i[4]; cfg.max_inner = cfg_i[5];
+  cfg.solver_mode = cfg_i[6]; cfg.gn_iters = cfg_i[7];
+  cfg.loss_limit = cfg_d[0]; cfg.cov_scale = cfg_d[1]; cfg.regularization = cfg_d[2]; cfg.radius = cfg_d[3];
+  std::vector<CellSet> sets(nscans);
+  std::vector<CellSet*> ptrs(nscans);
+  for (int i = 0; i < nscans; ++i) {
+    const int o = offsets[i];
+    sets[i].n = offsets[i + 1] - o;
+    sets[i].mean = mean + 2 * (size_t)o; sets[i].normal = normal + 2 * (size_t)o; sets[i].cov = cov + 4 * (size_t)o;
+    sets[i].planarity = planarity + o; sets[i].nsamples = nsamples + o;
+    if (i < nscans - 1) sets[i].build_index();
+    ptrs[i] = &sets[i];
+  }
+  std::vector<double> p(poses, poses + 3 * (size_t)nscans);
+  std::vector<Residual> res;
+  build_problem(cfg, ptrs, p, 2, res, nullptr);
+  const int nr = num_scalar_residuals(cfg, res.size());
+  if (num_residuals_out) *num_residuals_out = nr;
+  *cost_out = 0.0;
+  if (nr <= 1) return 0;                                                         // :205-208
+  Eval ev;
+  evaluate(cfg, res, &p[3 * (size_t)(nscans - 1)], false, ev);
+  *cost_out = ev.cost;
+  return 1;
+}
+
 // Evaluate cost + normal equations for a fixed association at x (unit tests of the LM pieces).
 double orc_eval_cost(const int32_t* cfg_i, const double* cfg_d, int nres, const double* res8 /*px,py,qx,qy,a,b,c,w*/,
                      const double* x, double* H6, double* g3) {

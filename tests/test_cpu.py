@@ -286,3 +286,59 @@ def test_trajectory_writers_match_reference_formats(tmp_path):
     cr = open(cov).read().strip().split("\n")[0].split(" ")
     assert cr[0] == "1547120000.000000625" and len(cr) == 37
     assert cr[1] == "0.0123457" and cr[6] == "-1.5e-07" and cr[36] == "0.0001" and cr[2] == "0"
+
+
+def test_mirror_dense_helpers_match_numpy(tmp_path):
+    """The Householder least-squares fit, the symmetric 3x3 eigenvalues and the 3x3 inverse behind the mirror's
+    approximateCovarianceBySampling (the reference uses Eigen's bdcSvd / SelfAdjointEigenSolver / inverse there),
+    on the reference's own sampling grid (+-0.2 m, +-0.00218 rad, 3 samples per axis: badly scaled columns)."""
+    import struct
+    import subprocess
+    exe = str(tmp_path / "linalg_test")
+    pkg = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "linalg_test.cpp"),
+                           "-o", exe, "-L" + pkg, "-lcfear_b200", "-Wl,-rpath," + pkg])
+    rng = np.random.default_rng(5)
+    xs = np.linspace(-0.2, 0.2, 3); ts = np.linspace(-0.00218125, 0.00218125, 3)
+    g = np.array([(x, y, t) for t in ts for x in xs for y in xs])
+    x, y, z = g.T
+    A = np.stack([x * x, y * y, z * z, x * y, y * z, z * x, x, y, z, np.ones_like(x)], 1)
+    qtrue = np.array([40.0, 55.0, 9e4, -6.0, 30.0, -80.0, 0.3, -0.2, 12.0, 17.5])
+    c = A @ qtrue + 1e-9 * rng.standard_normal(27)
+    H = np.array([[2 * qtrue[0], qtrue[3], qtrue[5]], [qtrue[3], 2 * qtrue[1], qtrue[4]], [qtrue[5], qtrue[4], 2 * qtrue[2]]])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<ii", 27, 10)); f.write(A.tobytes()); f.write(c.tobytes()); f.write(H.tobytes())
+    subprocess.check_call([exe, fin, fout])
+    raw = open(fout, "rb").read()
+    assert struct.unpack_from("<i", raw, 0)[0] == 1
+    q = np.frombuffer(raw, np.float64, 10, 4); ev = np.frombuffer(raw, np.float64, 3, 84); Hi = np.frombuffer(raw, np.float64, 9, 108).reshape(3, 3)
+    qn = np.linalg.lstsq(A, c, rcond=None)[0]
+    np.testing.assert_allclose(q, qn, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(np.sort(ev), np.linalg.eigvalsh(H), rtol=1e-12)
+    np.testing.assert_allclose(Hi, np.linalg.inv(H), rtol=1e-11, atol=1e-18)
+
+
+def test_oracle_get_cost_and_sampled_covariance(orc):
+    """Oracle restatements of GetCost / approximateCovarianceBySampling: the cost at the registered pose is the
+    solver's final cost up to the last re-association, the sampled cost surface is convex around it and the fitted
+    covariance is symmetric positive definite in (x, y, yaw)."""
+    import helpers
+    K = 2
+    im, tp = helpers.scan_images(31, K)
+    sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(K + 1)]
+    P = tp.copy(); P[K] = tp[K - 1]
+    cfg = orc.reg_cfg(cost="P2D", loss="Huber", weight_opt=4, regularization=0.1)
+    ok, p, _, st, _ = orc.register(sets, P, cfg)
+    assert ok
+    gok, cost, nres = orc.get_cost(sets, p, cfg)
+    assert gok and nres > 100
+    np.testing.assert_allclose(cost, st.final_cost, rtol=0.05)         # same pose, fresh association
+    sok, cov6, S = orc.sampled_covariance(sets, p, cfg, st.final_cost, st.num_residuals)
+    assert sok and S.shape == (27, 4) and S[:, 3].min() >= cost * 0.999
+    c3 = cov6[np.ix_([0, 1, 5], [0, 1, 5])]
+    np.testing.assert_allclose(c3, c3.T, rtol=1e-9)
+    assert np.all(np.linalg.eigvalsh(c3) > 0) and cov6[2, 2] == 1 and cov6[0, 2] == 0
+    # degenerate: a source that sees nothing of the keyframes
+    far = p.copy(); far[K, :2] += 1e4
+    assert orc.get_cost(sets, far, cfg)[0] is False

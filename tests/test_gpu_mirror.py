@@ -92,3 +92,44 @@ def test_fuser_sequence_replay_matches_oracle(fuser_exe, orc, tmp_path, cost, wo
     c, s = np.cos(yaw), np.sin(yaw)
     exp = "%.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f" % (c, -s, 0, x, s, c, 0, y, 0, 0, 1, 0)
     assert rows[-1] == exp
+
+
+@pytest.fixture(scope="module")
+def covsample_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cpp") / "covsample_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "covsample_test.cpp"), "-o", out, "-L" + PKG, "-lcfear_b200",
+                           "-Wl,-rpath," + PKG])
+    return out
+
+
+@pytest.mark.parametrize("cost,wopt,K", [("P2D", 4, 3), ("P2L", 0, 2)])
+def test_covariance_by_sampling_matches_oracle(covsample_exe, orc, tmp_path, cost, wopt, K):
+    """approximateCovarianceBySampling (27 GetCost samples in one launch + quadric fit) of the mirror vs the oracle
+    restatement (one GetCost per sample, numpy lstsq)."""
+    im, tp = helpers.scan_images(33, K)
+    radius, reg = 3.0, 0.1
+    P = tp.copy(); P[K] = tp[K - 1]
+    mot = se2_mul(se2_inv(tp[K - 2]), tp[K - 1])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<iiifiiid", K + 1, im.shape[1], im.shape[2], radius, orc.COST[cost], orc.LOSS["Huber"], wopt, reg))
+        f.write(im[:K + 1].tobytes()); f.write(P.astype(np.float64).tobytes()); f.write(mot.astype(np.float64).tobytes())
+    subprocess.check_call([covsample_exe, fin, fout])
+    raw = open(fout, "rb").read()
+    reg_ok, cov_ok, nres = struct.unpack_from("<3i", raw, 0)
+    final_cost = np.frombuffer(raw, np.float64, 1, 12)[0]
+    pose = np.frombuffer(raw, np.float64, 3, 20)
+    cov = np.frombuffer(raw, np.float64, 36, 44).reshape(6, 6)
+    cost_here = np.frombuffer(raw, np.float64, 1, 44 + 288)[0]
+    sets = [helpers.oracle_cells(orc, im[i], radius=radius, mot=(mot if i == K else None))[1] for i in range(K + 1)]
+    cfg = orc.reg_cfg(cost=cost, loss="Huber", weight_opt=wopt, regularization=reg)
+    o_ok, op, _, ost, _ = orc.register(sets, P, cfg)
+    assert bool(reg_ok) == o_ok and nres == ost.num_residuals
+    np.testing.assert_allclose(final_cost, ost.final_cost, rtol=1e-6)
+    g_ok, g_cost, g_nres = orc.get_cost(sets, op, cfg)
+    np.testing.assert_allclose(cost_here, g_cost, rtol=1e-6)
+    s_ok, ocov, _ = orc.sampled_covariance(sets, op, cfg, ost.final_cost, ost.num_residuals)
+    assert bool(cov_ok) == s_ok
+    if s_ok:
+        np.testing.assert_allclose(cov, ocov, rtol=2e-3, atol=1e-12)

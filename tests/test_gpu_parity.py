@@ -198,6 +198,40 @@ def test_register_parity(orc, imgs, cost, loss, wopt, K, solver):
     c.close()
 
 
+def test_get_cost_batch_matches_oracle(orc, imgs):
+    """cfear_get_cost_batch (n_scan_normal_reg::GetCost): 27 pose samples around a registered pose in one launch vs one
+    oracle GetCost per sample; a sample that sees nothing returns ok = 0."""
+    K = 3
+    c = capi.Context(max_batch=32, max_cellsets=K + 1, max_keyframes=K, cost="P2D", loss="Huber", weight_opt=4, regularization=0.1)
+    sets = []
+    for i in range(K + 1):
+        cl, s = helpers.oracle_cells(orc, imgs[0][i], radius=3.5)
+        sets.append(s); c.cells_upload(i, s)
+    P = imgs[1][:K + 1].copy(); P[K] = imgs[1][K - 1]
+    cfg = orc.reg_cfg(cost="P2D", loss="Huber", weight_opt=4, regularization=0.1)
+    ok, p, _, st, _ = orc.register(sets, P, cfg)
+    assert ok
+    xs = np.linspace(-0.2, 0.2, 3); ts = np.linspace(-0.00218125, 0.00218125, 3)
+    samples = [p.copy() for _ in range(28)]
+    n = 0
+    for t in ts:
+        for x in xs:
+            for y in xs:
+                samples[n][K] = p[K] + [x, y, t]; n += 1
+    samples[27][K, :2] += 1e4                                       # nothing in reach: GetCost returns false
+    cost, nres, okv = c.get_cost_batch(np.tile(np.arange(K + 1, dtype=np.int32), (28, 1)), np.stack(samples))
+    for i in range(28):
+        o_ok, o_cost, o_nres = orc.get_cost(sets, samples[i], cfg)
+        assert bool(okv[i]) == o_ok and nres[i] == o_nres
+        if o_ok:
+            np.testing.assert_allclose(cost[i], o_cost, rtol=1e-11)
+    assert okv[:27].all() and not okv[27]
+    # the pose table is an input only, and a following Register is unaffected by the cost-only launch
+    p2, _, st2, _ = c.register_batch(np.arange(K + 1, dtype=np.int32)[None], P[None])
+    assert st2["outer_iterations"][0] == st.outer_iterations and np.abs(p2[0, K] - p[K]).max() < 1e-9
+    c.close()
+
+
 def test_register_failure_modes(orc, imgs):
     im, poses = imgs
     sets, P = _problem(orc, im, poses, 1, 3.0)
