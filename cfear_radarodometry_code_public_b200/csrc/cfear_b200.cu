@@ -227,7 +227,8 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cfg->range_bins + 1) * 4)));
   c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
-#define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
+#define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem)); \
+  CK(cudaFuncSetAttribute(k5_register<CO, LO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
 #ifdef CFEAR_K5_MINIMAL      /* experiment builds (profiles/ab): only the bench's P2D / Huber instantiation */
   K5_ATTR(2, 1)
 #else
@@ -405,7 +406,10 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-#define K5_CASE(CO, LO) case (CO) * 6 + (LO): k5_register<CO, LO><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); break;
+#define K5_CASE(CO, LO) case (CO) * 6 + (LO): \
+    if (p.solver_mode == CFEAR_SOLVER_CERES_LM) k5_register<CO, LO, false><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); \
+    else k5_register<CO, LO, true><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); \
+    break;
   switch (p.cost * 6 + p.loss) {
 #ifdef CFEAR_K5_MINIMAL
     K5_CASE(2, 1)

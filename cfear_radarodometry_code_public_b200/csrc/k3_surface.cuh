@@ -26,6 +26,10 @@
 namespace cfear {
 
 constexpr int K3_THREADS = 512;
+#ifndef CFEAR_K3_LPC
+#define CFEAR_K3_LPC 4
+#endif
+constexpr int K3_LANES_PER_CENTROID = CFEAR_K3_LPC;   // 8 -> 4: 0.164 -> 0.142 ms (fixed cost per centroid amortised over twice as many per warp); 2: 0.140, 1: 0.160, 16: 0.218
 constexpr int K3_HIST_CAP = 16384;        // voxel / NN-grid bins kept in shared memory
 
 struct K3Params {
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   }
   __syncthreads();
 
-  // ---- per centroid: radius neighbourhood -> cell.  8 lanes share one centroid and groups pull centroids
+  // ---- per centroid: radius neighbourhood -> cell.  LPC (4) lanes share one centroid and groups pull centroids
   // from a shared counter (dense neighbourhoods cluster in voxel order, static assignment would idle most
   // of the block).  One pass accumulates the weight / first / second moments about the centroid q
   // (exact in fp64: q and the points are fp32), from which the weighted mean and the central covariance of
@@ -383,9 +387,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   const float r2 = (float)((double)r * (double)r);
   const float rq = r * 1.0001f + 1e-4f;                    // bin-range margin (the d2 test itself is exact)
   const size_t cbase = (size_t)slot * p.pool.max_cells;
-  const int sl = tid & 7;
-  const unsigned gmask = 0xffu << (lane_id() & 24);
-  const int gleader = lane_id() & 24;
+  constexpr int LPC = K3_LANES_PER_CENTROID;               // lanes sharing one centroid (power of two <= 32)
+  const int sl = tid & (LPC - 1);
+  const int gleader = lane_id() & ~(LPC - 1);
+  const unsigned gmask = (LPC == 32 ? 0xffffffffu : ((1u << LPC) - 1u)) << gleader;
   const bool wint = p.weight_intensity != 0;
   double2* tmp = p.cell_tmp + (size_t)scan * cap * 4;                        // [cap][4] double2: raw moments
   if (tid == 0) s_misc[1] = 0;
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     for (int by = by0; by <= by1; ++by) {
       const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
       const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
-      for (int a = s + sl; a < e; a += 8) {
+      for (int a = s + sl; a < e; a += LPC) {
         const float4 pt = pts[a];
         const float dx = q.x - pt.x, dy = q.y - pt.y;
         float d2 = dx * dx; d2 += dy * dy;                  // FLANN L2_Simple in fp32, strict d2 < r2
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
       }
     }
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
+    for (int d = 1; d < LPC; d <<= 1) {
       gN += __shfl_xor_sync(gmask, gN, d);
       S0 += __shfl_xor_sync(gmask, S0, d); S1x += __shfl_xor_sync(gmask, S1x, d); S1y += __shfl_xor_sync(gmask, S1y, d);
       Sxx += __shfl_xor_sync(gmask, Sxx, d); Sxy += __shfl_xor_sync(gmask, Sxy, d); Syy += __shfl_xor_sync(gmask, Syy, d);

@@ -203,8 +203,13 @@ struct LMShared {
 __device__ __forceinline__ void bar_a() { asm volatile("barrier.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
 __device__ __forceinline__ void bar_b() { asm volatile("barrier.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
 #elif CFEAR_K5_BAR == 1
-__device__ __forceinline__ void bar_a() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_b() { __syncwarp(); asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+#ifdef CFEAR_K5_NO_SYNCWARP
+#define K5_SYNCWARP
+#else
+#define K5_SYNCWARP __syncwarp();
+#endif
+__device__ __forceinline__ void bar_a() { K5_SYNCWARP asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_b() { K5_SYNCWARP asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
 #else
 __device__ __noinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
 __device__ __noinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
@@ -735,7 +740,9 @@ __device__ __forceinline__ void stage_grids(const RegParams& P, const int32_t* s
 // Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes to it.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int COST, int LOSS>
+// AUX = false: the ceres_lm solver only (the product path).  AUX = true: the two auxiliary modes -- gn_fixed and cost
+// only -- which live in their own instantiation so that their code does not cost the main kernel registers.
+template <int COST, int LOSS, bool AUX>
 __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
@@ -854,7 +861,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   bool have_H = false;
   bool success = true;
   int inner_total = 0, nres = 0, outer = 0;
-  if (P.solver_mode == 2) {
+  if (AUX && P.solver_mode == 2) {
     // cost only -- n_scan_normal_reg::GetCost (n_scan_normal.cpp:187-213): one association at the registration radius
     // (itr_ is past 1 whenever GetCost runs after a Register) and one evaluation of 1/2 sum w rho(s); no solve, the
     // pose is returned untouched.  Used by the fuser's covariance-by-sampling (odometrykeyframefuser.cpp:261-380).
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
       sum.final_cost = sh->out_final_cost;
       __syncthreads();
     }
-  } else if (P.solver_mode == 1) {
+  } else if (AUX && P.solver_mode == 1) {
     // gn_fixed: N undamped Gauss-Newton / IRLS iterations, re-associating before each one
     int it;
     for (it = 1; it <= P.gn_iters; ++it) {
@@ -960,7 +967,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   double cov[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) cov[i] = 0.0;
-  if (success && P.solver_mode == 2) {
+  if (AUX && success && P.solver_mode == 2) {
     st.score = sum.final_cost / st.num_residuals;                               // score_ = score / max(#residuals, 1)  :211
     st.success = 1;
   } else if (success) {
