@@ -16,7 +16,7 @@
 #include "common.cuh"
 #include "k1_kstrongest.cuh"
 #include "k3_surface.cuh"
-#include "k5_register.cuh"
+#include "k5_launch.cuh"
 #include "k6_fuser.cuh"
 #include "k7_cfar.cuh"
 
@@ -227,16 +227,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cfg->range_bins + 1) * 4)));
   c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
-#define K5_ATTR(CO, LO) CK(cudaFuncSetAttribute(k5_register<CO, LO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem)); \
-  CK(cudaFuncSetAttribute(k5_register<CO, LO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k5_smem));
-#ifdef CFEAR_K5_MINIMAL      /* experiment builds (profiles/ab): only the bench's P2D / Huber instantiation */
-  K5_ATTR(2, 1)
-#else
-  K5_ATTR(0, 0) K5_ATTR(0, 1) K5_ATTR(0, 2) K5_ATTR(0, 3) K5_ATTR(0, 4) K5_ATTR(0, 5)
-  K5_ATTR(1, 0) K5_ATTR(1, 1) K5_ATTR(1, 2) K5_ATTR(1, 3) K5_ATTR(1, 4) K5_ATTR(1, 5)
-  K5_ATTR(2, 0) K5_ATTR(2, 1) K5_ATTR(2, 2) K5_ATTR(2, 3) K5_ATTR(2, 4) K5_ATTR(2, 5)
-#endif
-#undef K5_ATTR
+CK(k5_set_smem_cost0(c->k5_smem)); CK(k5_set_smem_cost1(c->k5_smem)); CK(k5_set_smem_cost2(c->k5_smem));
 
   const size_t rows = (size_t)B * A;
   AL(c->d_polar, rows * R);
@@ -406,21 +397,13 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-#define K5_CASE(CO, LO) case (CO) * 6 + (LO): \
-    if (p.solver_mode == CFEAR_SOLVER_CERES_LM) k5_register<CO, LO, false><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); \
-    else k5_register<CO, LO, true><<<nprob, K5_THREADS, c->k5_smem, c->stream>>>(p); \
-    break;
-  switch (p.cost * 6 + p.loss) {
-#ifdef CFEAR_K5_MINIMAL
-    K5_CASE(2, 1)
-    default: g_err = "experiment build: only P2D / Huber is instantiated"; return CFEAR_ERR_ARG;
-#else
-    K5_CASE(0, 0) K5_CASE(0, 1) K5_CASE(0, 2) K5_CASE(0, 3) K5_CASE(0, 4) K5_CASE(0, 5)
-    K5_CASE(1, 0) K5_CASE(1, 1) K5_CASE(1, 2) K5_CASE(1, 3) K5_CASE(1, 4) K5_CASE(1, 5)
-    K5_CASE(2, 0) K5_CASE(2, 1) K5_CASE(2, 2) K5_CASE(2, 3) K5_CASE(2, 4) K5_CASE(2, 5)
-#endif
+bool launched = false;
+  switch (p.cost) {
+    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, c->stream); break;
+    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, c->stream); break;
+    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, c->stream); break;
   }
-#undef K5_CASE
+  if (!launched) { g_err = "this build has no instantiation for the requested cost / loss"; return CFEAR_ERR_ARG; }
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cfear {
 
@@ -56,32 +57,6 @@ struct K3Params {
   double2* cell_tmp;           // [nscans][cap_pts][4] per-centroid raw moments (scratch)
   CellPool pool;
 };
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (bytes % 16 == 0, 16-B aligned).
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
 
 // utils.h:28-32 GetRelTimeStamp
 __device__ __forceinline__ double rel_time_stamp(double x, double y, bool ccw) {

@@ -1,0 +1,39 @@
+// Body of one K5 translation unit; CFEAR_K5_TU_COST selects the cost metric (0 P2P, 1 P2L, 2 P2D).
+#include "k5_launch.cuh"
+
+#define K5_CAT2(a, b) a##b
+#define K5_CAT(a, b) K5_CAT2(a, b)
+
+namespace cfear {
+
+#ifdef CFEAR_K5_MINIMAL      /* experiment builds (profiles/ab): only the Huber instantiations */
+#define K5_FOR_EACH_LOSS(X) X(1)
+#else
+#define K5_FOR_EACH_LOSS(X) X(0) X(1) X(2) X(3) X(4) X(5)
+#endif
+
+cudaError_t K5_CAT(k5_set_smem_cost, CFEAR_K5_TU_COST)(int bytes) {
+  cudaError_t e = cudaSuccess;
+#define K5_ATTR(LO)                                                                                                              \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k5_register<CFEAR_K5_TU_COST, LO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k5_register<CFEAR_K5_TU_COST, LO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  K5_FOR_EACH_LOSS(K5_ATTR)
+#undef K5_ATTR
+  return e;
+}
+
+bool K5_CAT(k5_launch_cost, CFEAR_K5_TU_COST)(const RegParams& p, int nprob, int smem, cudaStream_t stream) {
+  const bool aux = p.solver_mode != 0;            // gn_fixed / cost only
+  switch (p.loss) {
+#define K5_CASE(LO)                                                                                       \
+  case LO:                                                                                                \
+    if (aux) k5_register<CFEAR_K5_TU_COST, LO, true><<<nprob, K5_THREADS, smem, stream>>>(p);             \
+    else k5_register<CFEAR_K5_TU_COST, LO, false><<<nprob, K5_THREADS, smem, stream>>>(p);                \
+    return true;
+    K5_FOR_EACH_LOSS(K5_CASE)
+#undef K5_CASE
+    default: return false;
+  }
+}
+
+}  // namespace cfear

@@ -17,7 +17,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
-#include "k3_surface.cuh"   // mbarrier / TMA bulk-copy helpers
+#include "tma.cuh"
 
 namespace cfear {
 
