@@ -183,6 +183,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + 1), max_keyframes=K, **workload.CFEAR3)
