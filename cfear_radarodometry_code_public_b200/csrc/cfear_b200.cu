@@ -66,7 +66,7 @@ __global__ void k2b_compensate(float4* cloud, int n, double m0, double m1, doubl
   float4 pt = cloud[i];
   const double x = (double)pt.x, y = (double)pt.y;
   const double d = rel_time_stamp(x, y, ccw != 0);
-  double s1, c1; sincos(d * m2, &s1, &c1);
+  double s1, c1; sincos_small(d * m2, &s1, &c1);
   const double tx = c1 * x + (-s1) * y + d * m0;
   const double ty = s1 * x + c1 * y + d * m1;
   pt.x = (float)tx; pt.y = (float)ty;

@@ -65,10 +65,16 @@ __device__ __forceinline__ uint32_t ge_flags(uint32_t x, uint32_t addc) {
 }
 
 // flags of a uint4 packed in one word: byte b of word w -> bit 8b + 7 - w
+// The kernel is bound by the integer ALU pipe (LOP3 / SHF / ISETP at half rate), so the three shift-and-or merges are
+// written as multiply-high-and-add (x >> n == umulhi(x, 2^(32-n)); the flag bits of different words never collide, so
+// + is |): IMAD.HI runs on the FMA pipe, which this kernel leaves idle.
 template <bool ZHI>
 __device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc) {
-  return ge_flags<ZHI>(d.x, addc) | (ge_flags<ZHI>(d.y, addc) >> 1) | (ge_flags<ZHI>(d.z, addc) >> 2) |
-         (ge_flags<ZHI>(d.w, addc) >> 3);
+  uint32_t m = ge_flags<ZHI>(d.x, addc);
+  m = __umulhi(ge_flags<ZHI>(d.y, addc), 0x80000000u) + m;
+  m = __umulhi(ge_flags<ZHI>(d.z, addc), 0x40000000u) + m;
+  m = __umulhi(ge_flags<ZHI>(d.w, addc), 0x20000000u) + m;
+  return m;
 }
 
 // ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
