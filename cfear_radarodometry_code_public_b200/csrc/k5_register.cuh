@@ -70,9 +70,14 @@ __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
   if constexpr (LOSS == 1) {            // HuberLoss
     const double b = a * a;
     // sqrt(s) = s * rsqrt(s), a / sqrt(s) = a * rsqrt(s): one reciprocal square root instead of a square root and a
-    // division per outlier (each within an ulp of the library forms; the unused rho[2] is dead code)
-    if (s > b) { const double ri = rsqrt_normal(s); rho[0] = fma(2.0 * a, s * ri, -b); rho[1] = fmax(2.2250738585072014e-308, a * ri); rho[2] = -rho[1] / (2.0 * s); }
-    else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+    // division per outlier (each within an ulp of the library forms; the unused rho[2] is dead code).  Branch-free:
+    // in a warp some residual is always an outlier, so the reciprocal square root is paid anyway, and without the branch
+    // the two residuals of an unrolled iteration interleave.
+    const bool outlier = s > b;
+    const double ri = rsqrt_normal(outlier ? s : b);
+    rho[0] = outlier ? fma(2.0 * a, s * ri, -b) : s;
+    rho[1] = outlier ? fmax(2.2250738585072014e-308, a * ri) : 1.0;
+    rho[2] = outlier ? -rho[1] / (2.0 * s) : 0.0;
   } else if constexpr (LOSS == 2) {     // CauchyLoss
     const double b = a * a, c = 1.0 / b;
     const double sum = 1.0 + s * c, inv = 1.0 / sum;
@@ -199,6 +204,7 @@ struct LMShared {
 #ifndef CFEAR_K5_BAR
 #define CFEAR_K5_BAR 1
 #endif
+
 #if CFEAR_K5_BAR == 0
 __device__ __forceinline__ void bar_a() { asm volatile("barrier.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
 __device__ __forceinline__ void bar_b() { asm volatile("barrier.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
