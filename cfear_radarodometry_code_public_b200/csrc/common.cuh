@@ -56,6 +56,22 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// sin / cos of small angles (Compensate: time stamp in [-0.5, 0.5] times the inter-scan yaw; K5: the yaw component of an
+// LM step): Taylor polynomials, exact to an ulp below 1/16 rad, the library routine above.
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
+  if (fabs(x) < 0.0625) {
+    const double z = x * x;
+    double ps = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0);
+    ps = fma(z, ps, -1.0 / 5040.0); ps = fma(z, ps, 1.0 / 120.0); ps = fma(z, ps, -1.0 / 6.0);
+    *s = fma(x * z, ps, x);
+    double pc = fma(z, 1.0 / 479001600.0, -1.0 / 3628800.0);
+    pc = fma(z, pc, 1.0 / 40320.0); pc = fma(z, pc, -1.0 / 720.0); pc = fma(z, pc, 1.0 / 24.0); pc = fma(z, pc, -0.5);
+    *c = fma(z, pc, 1.0);
+  } else {
+    sincos(x, s, c);
+  }
+}
+
 // Block-wide exclusive scan of one int per thread.  s_warp: >= 33 ints of shared memory.
 // Returns the exclusive prefix; *total gets the block sum.  Contains __syncthreads().
 __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {

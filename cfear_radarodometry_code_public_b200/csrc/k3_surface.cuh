@@ -69,22 +69,6 @@ __device__ __forceinline__ double rel_time_stamp(double x, double y, bool ccw) {
   return ccw ? -(d - 0.5) : (d - 0.5);
 }
 
-// sin / cos of the small angles Compensate rotates by (time stamp in [-0.5, 0.5] times the inter-scan yaw): Taylor
-// polynomials, exact to an ulp below 1/16 rad, the library routine above.
-__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
-  if (fabs(x) < 0.0625) {
-    const double z = x * x;
-    double ps = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0);
-    ps = fma(z, ps, -1.0 / 5040.0); ps = fma(z, ps, 1.0 / 120.0); ps = fma(z, ps, -1.0 / 6.0);
-    *s = fma(x * z, ps, x);
-    double pc = fma(z, 1.0 / 479001600.0, -1.0 / 3628800.0);
-    pc = fma(z, pc, 1.0 / 40320.0); pc = fma(z, pc, -1.0 / 720.0); pc = fma(z, pc, 1.0 / 24.0); pc = fma(z, pc, -0.5);
-    *c = fma(z, pc, 1.0);
-  } else {
-    sincos(x, s, c);
-  }
-}
-
 // closed-form symmetric 2x2 eigen decomposition: (a b; b d) -> ascending eigenvalues, unit eigenvectors
 struct Eig2 { double lmin, lmax, nx, ny; };
 __device__ __forceinline__ Eig2 eig2_sym(double a, double b, double d) {

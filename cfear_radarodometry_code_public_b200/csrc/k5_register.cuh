@@ -64,6 +64,17 @@ __device__ __forceinline__ double rsqrt_normal(double s) {
   return fma(y, e, y);
 }
 
+// 1 / x for x in the normal range: hardware seed and two Newton steps, no special-case branches (so independent
+// chains interleave); within 2 ulp.  Used where the operand is known to be a well-scaled positive quantity.
+__device__ __forceinline__ double rcp_normal(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 // ceres/loss_function.cc (rho[2] is only needed by Ceres' corrector when rho'' > 0, which none of these have)
 template <int LOSS>
 __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
@@ -323,15 +334,15 @@ __device__ __forceinline__ void finish_evals(LMShared* sh) {
 // Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal square root per pivot.
 __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3], double y[3]) {
   if (!(A[0] > 0.0) || !isfinite(A[0])) return false;
-  const double r00 = rsqrt(A[0]);
+  const double r00 = rsqrt_normal(A[0]);
   const double l10 = A[1] * r00, l20 = A[2] * r00;
   const double d1 = A[3] - l10 * l10;
   if (!(d1 > 0.0)) return false;
-  const double r11 = rsqrt(d1);
+  const double r11 = rsqrt_normal(d1);
   const double l21 = (A[4] - l20 * l10) * r11;
   const double d2 = A[5] - l20 * l20 - l21 * l21;
   if (!(d2 > 0.0)) return false;
-  const double r22 = rsqrt(d2);
+  const double r22 = rsqrt_normal(d2);
   const double z0 = b[0] * r00;
   const double z1 = (b[1] - l10 * z0) * r11;
   const double z2 = (b[2] - l20 * z0 - l21 * z1) * r22;
@@ -431,7 +442,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
     }
     const double cost_change = x_cost - cand_cost;
     if (fabs(cost_change) <= kFunctionTol * x_cost) return;
-    const double rel = cost_change / model_change;
+    const double rel = cost_change * rcp_normal(model_change);      // model_change > 0
     sum.n_iterations++; sum.last_rel = rel;
     if (rel > kMinRelDecrease) {
       x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
@@ -443,7 +454,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
       // 1/3 whatever the last bits of rel are: that case needs neither the quotient nor the cube.
       double f = 1.0 / 3.0;
       if (!(cost_change >= 0.94 * model_change)) { const double t = 2.0 * rel - 1.0; f = fmax(1.0 / 3.0, 1.0 - t * t * t); }
-      radius = fmin(kMaxRadius, radius / f);
+      radius = fmin(kMaxRadius, radius * rcp_normal(f));           // f in [1/3, 2]
       inv_radius = fmax(1.0 / kMaxRadius, inv_radius * f);
       decrease_factor = 2.0; reuse_diagonal = false;
       min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
@@ -524,7 +535,7 @@ __device__ __forceinline__ bool normal_gate(double ntx, double nty, uint32_t nrm
   return fmax(ntx * n.x + nty * n.y, 0.0) > thr;
 }
 
-__device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) / (x + y); }
+__device__ __forceinline__ double sim_ratio(double x, double y) { return 2 * fmin(x, y) * rcp_normal(x + y); }
 
 constexpr int K5_TILE_MAX = 4096;     // (keyframe, source cell) pairs associated per tile (2 x u16 of shared memory each)
 constexpr uint16_t K5_NONE = 0xffffu;
@@ -579,11 +590,12 @@ __device__ __forceinline__ void make_record(const RegParams& P, const RelT& T, d
     s00 = (P.regularization + s00) * P.cov_scale; s11 = (P.regularization + s11) * P.cov_scale;
     s01 = s01 * P.cov_scale; s10 = s10 * P.cov_scale;
     // inverse and its lower Cholesky factor with one reciprocal, one reciprocal square root and one square root
-    const double idet = 1.0 / (s00 * s11 - s01 * s10);
+    const double idet = rcp_normal(s00 * s11 - s01 * s10);
     const double i00 = s11 * idet, i10 = -(s10 * idet), i11 = s00 * idet;
-    const double rl = rsqrt(i00);
+    const double rl = rsqrt_normal(i00);
     const double l00 = i00 * rl, l10 = i10 * rl;
-    const double l11 = sqrt(i11 - l10 * l10);
+    const double t11 = i11 - l10 * l10;
+    const double l11 = t11 * rsqrt_normal(t11);                                  // sqrt; t11 > 0 for a positive definite block
     rab = make_double2(l00, l10); rcw.x = l11;
   }
 }
