@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
   __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
   __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
   __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
+  __shared__ uint2 s_queue[K1_WARPS][K1_TILES * 32];      // vectors of one super-tile that hold candidates
   const int grow = blockIdx.x * K1_WARPS + warp_id();
   if (grow >= p.nrows) return;                 // no block-level sync in this kernel
   const int lane = lane_id();
@@ -98,13 +99,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
   const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
 
   // ---- pass 1: stream the row, collect the candidates ---------------------------------------------
-  // Candidates are sparse (a few vectors per row hold any), so they are emitted cooperatively: the warp walks the
-  // vectors that have flags set (ballot), two at a time, and lane l handles byte (l & 15) of the first (l < 16) or second
-  // (l >= 16) of them.  Only range bins are emitted here; the intensities are re-read (L2) once the list is complete.
+  // Candidates are sparse (a few vectors per row hold any), so they are emitted cooperatively: every lane whose vector
+  // has flags pushes (flags, first range bin) onto a per-warp queue (one ballot per 32 vectors), then the warp drains
+  // the queue two vectors at a time with lane l handling byte (l & 15) of the first (l < 16) or second (l >= 16).
+  // Only range bins are emitted here; the intensities are re-read (L2) once the list is complete.
   const int jb = lane & 15, jw = jb >> 2;
   const uint32_t mybit = 1u << (8 * (jb & 3) + 7 - jw);                          // flag bit of byte jb (see ge_flags16)
   const uint32_t lowmask = 0x01010101u * (0x100u - (0x100u >> jw)) |             // flag bits of the bytes before jb
                            ((0x80808080u >> jw) & ((1u << (8 * (jb & 3))) - 1u));
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  uint2* q = s_queue[warp_id()];
   const bool hi = lane >= 16;
   int C = 0;                                   // warp-uniform candidate count
   for (int v0 = 0; v0 < nvec; v0 += 32 * K1_TILES) {
@@ -135,25 +139,29 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
         g[i] = m;
       }
     }
+    int nq = 0;                                // warp-uniform queue length
 #pragma unroll
     for (int i = 0; i < K1_TILES; ++i) {
-      uint32_t bal = __ballot_sync(FULL, g[i] != 0);
-      while (bal) {                              // warp-uniform
-        const int l1 = __ffs(bal) - 1; bal &= bal - 1;
-        const bool two = bal != 0;
-        const int l2 = two ? __ffs(bal) - 1 : l1;
-        if (two) bal &= bal - 1;
-        const uint32_t m1 = __shfl_sync(FULL, g[i], l1);
-        uint32_t m2 = __shfl_sync(FULL, g[i], l2);
-        if (!two) m2 = 0;
-        const uint32_t mm = hi ? m2 : m1;
-        if (mm & mybit) {
-          const int pos = C + (hi ? __popc(m1) : 0) + __popc(mm & lowmask);
-          if (pos < K1_CAP) cand[pos] = (uint32_t)((v0 + i * 32 + (hi ? l2 : l1)) * 16 - off + jb);
-        }
-        C += __popc(m1) + __popc(m2);
+      const bool has = g[i] != 0;
+      const uint32_t bal = __ballot_sync(FULL, has);
+      if (bal) {                                 // warp-uniform
+        if (has) q[nq + __popc(bal & lanes_below)] = make_uint2(g[i], (uint32_t)((v0 + i * 32 + lane) * 16 - off));
+        nq += __popc(bal);
       }
     }
+    __syncwarp();
+    for (int e = 0; e < nq; e += 2) {
+      const uint2 e1 = q[e];
+      const uint2 e2 = (e + 1 < nq) ? q[e + 1] : make_uint2(0u, 0u);
+      const uint32_t mm = hi ? e2.x : e1.x;
+      const int c1 = __popc(e1.x);
+      if (mm & mybit) {
+        const int pos = C + (hi ? c1 : 0) + __popc(mm & lowmask);
+        if (pos < K1_CAP) cand[pos] = (hi ? e2.y : e1.y) + (uint32_t)jb;
+      }
+      C += c1 + __popc(e2.x);
+    }
+    __syncwarp();                                // the queue is rewritten by the next super-tile
   }
   __syncwarp();
   if (C <= K1_CAP) {                             // range bins -> keys (intensity << 16 | range)
@@ -195,10 +203,25 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
     work = sel;
     nwork = k;
   }
-  // <= 64 distinct keys, at most two per lane: the kk largest, one warp-wide max reduction (REDUX) each, written in
-  // ascending order (position kk-1-t for the t-th largest)
-  {
-    uint32_t k0 = (lane < nwork) ? work[lane] + 1u : 0u;           // +1: 0 is the "taken / absent" mark
+  if (nwork <= 32) {
+    // the usual case, one key per lane: bitonic sort across the warp (15 shuffle + min/max steps), ascending, empty
+    // lanes (0) first, so the kk largest sit in the top kk lanes already in output order
+    uint32_t key = (lane < nwork) ? work[lane] + 1u : 0u;          // +1: 0 is "absent"
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(FULL, key, j);
+        const bool up = (lane & k2) == 0, lower = (lane & j) == 0;
+        key = (lower == up) ? min(key, other) : max(key, other);
+      }
+    }
+    if (lane >= 32 - kk) outk[lane - (32 - kk)] = key - 1u;
+  } else {
+    // <= 64 distinct keys, two per lane: the kk largest, one warp-wide max reduction (REDUX) each, written in
+    // ascending order (position kk-1-t for the t-th largest)
+    uint32_t k0 = work[lane] + 1u;                                 // +1: 0 is the "taken / absent" mark
     uint32_t k1 = (lane + 32 < nwork) ? work[lane + 32] + 1u : 0u;
     __syncwarp();
     for (int t = 0; t < kk; ++t) {
