@@ -362,7 +362,7 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
   K3Params p;
   p.mode = mode; p.A = c->cfg.azimuths; p.k = c->cfg.k_strongest;
   p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
-  p.mot = (c->cfg.compensate && mode == 0) ? d_mot : nullptr; p.ccw = c->cfg.radar_ccw;
+  p.mot = (c->cfg.compensate && mode == 0) ? d_mot : nullptr; p.ccw = c->cfg.radar_ccw; p.cs = c->d_cs;
   p.cloud = (mode == 1 || write_cloud) ? c->d_cloud : nullptr; p.npts = c->d_npts; p.cap_pts = c->cap_pts;
   p.slots = d_slots; p.radius = c->cfg.radius;
   p.leaf = (float)((double)c->cfg.radius / c->cfg.downsample_factor);        // pointnormal.cpp:279

@@ -43,6 +43,7 @@ struct K3Params {
   const float4* rowcloud;      // [nscans][A][k]
   const int32_t* rowcnt;       // [nscans][A]
   const double* mot;           // [nscans][3] previous motion (x, y, yaw) or nullptr = no compensation
+  const double2* cs;           // [A] (cos, sin) of the row angles 2 pi (a+1) / A (the table K1 uses), mode 0
   int ccw;
   float4* cloud;               // [nscans][cap_pts] out (mode 0, may be null) / in (mode 1)
   int32_t* npts;               // [nscans] out (mode 0) / in (mode 1)
@@ -68,6 +69,24 @@ __device__ __forceinline__ double rel_time_stamp(double x, double y, bool ccw) {
   const double d = (a > 0.00001 ? a : (2 * M_PI + a)) * (1.0 / (2 * M_PI));
   return ccw ? -(d - 0.5) : (d - 0.5);
 }
+
+// The same time stamp for a point of azimuth row a (mode 0): the point is the fp32 rounding of rho (cos, sin)(theta_a),
+// so atan2(y, x) = theta_a + eps with eps = cross((cos, sin)(theta_a), (x, y)) / |(x, y)| to first order (|eps| ~ 1e-7,
+// the cubic term is 1e-22): a dozen FP64 instructions instead of the ~120 of atan2, accurate to ~1e-14 rad -- a
+// compensated coordinate moves by < 1e-13 m, eight orders below an fp32 ulp at these ranges.  theta_a lies in (0, 2 pi],
+// which is already the interval utils.h:30 maps atan2's result to (its 1e-5 threshold is never reached: theta_1 = 0.0157).
+#ifndef CFEAR_K3_ATAN2
+__device__ __forceinline__ double rel_time_stamp_row(double x, double y, double2 cs, double theta, bool ccw) {
+  const double cross = fma(cs.x, y, -(cs.y * x));
+  const double r2 = fma(x, x, y * y);
+  double ri; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ri) : "d"(r2));
+  const double h = 0.5 * r2;
+  double e = fma(-h * ri, ri, 0.5); ri = fma(ri, e, ri);
+  e = fma(-h * ri, ri, 0.5); ri = fma(ri, e, ri);
+  const double d = fma(cross, ri, theta) * (1.0 / (2 * M_PI));
+  return ccw ? -(d - 0.5) : (d - 0.5);
+}
+#endif
 
 // closed-form symmetric 2x2 eigen decomposition: (a b; b d) -> ascending eigenvalues, unit eigenvectors
 struct Eig2 { double lmin, lmax, nx, ny; };
@@ -222,7 +241,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
           pt = p.pts_in_smem ? bufA[s] : src[s];
           if (mot) {                                       // utils.cpp:96-113
             const double x = (double)pt.x, y = (double)pt.y;
+#ifdef CFEAR_K3_ATAN2
             const double d = rel_time_stamp(x, y, p.ccw != 0);
+#else
+            const double d = rel_time_stamp_row(x, y, p.cs[a], (double)(a + 1) * (2 * M_PI / (double)p.A), p.ccw != 0);
+#endif
             double s1, c1; sincos_small(d * m2, &s1, &c1);
             const double tx = c1 * x + (-s1) * y + d * m0;
             const double ty = s1 * x + c1 * y + d * m1;
