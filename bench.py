@@ -183,8 +183,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout while it initialises (NCCL_DEBUG=VERSION in some environments); stdout
+        # must carry the one JSON line only, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + 1), max_keyframes=K, **workload.CFEAR3)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)

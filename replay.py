@@ -49,7 +49,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()                         # NCCL's version banner goes to stdout during init: keep stdout to the JSON line
+        saved_stdout = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)
     K = args.submap
     ctx = capi.Context(device=local, max_batch=args.nseq, max_cellsets=args.nseq * (K + 1), max_keyframes=K, **workload.CFEAR3)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
