@@ -46,3 +46,19 @@ def to_pinned_batch(images) -> np.ndarray:
     for i, im in enumerate(images):
         out[i] = im
     return out
+
+
+def write_frames(path: str, imgs, stamps_ns=None) -> None:
+    """Raw frame file read by examples/offline_odometry.cpp (stands in for the reference's rosbag of sensor_msgs::Image):
+    "CFRS" | int32 n, azimuths, range_bins | n x { uint64 stamp_ns | azimuths*range_bins uint8 }.  imgs: (n, A, R) uint8,
+    rows = azimuths (what load_oxford_png / load_range_azimuth_png return)."""
+    imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+    n, A, R = imgs.shape
+    if stamps_ns is None:
+        stamps_ns = np.arange(n, dtype=np.uint64) * np.uint64(250_000_000)           # 4 Hz
+    with open(path, "wb") as f:
+        f.write(b"CFRS")
+        f.write(np.array([n, A, R], np.int32).tobytes())
+        for i in range(n):
+            f.write(np.uint64(stamps_ns[i]).tobytes())
+            f.write(imgs[i].tobytes())

@@ -768,6 +768,25 @@ class EvalTrajectory {
   void CallbackESTEigen(const Affine3d& pose, const Matrix6d& cov, uint32_t sec, uint32_t nsec) {   // eval_trajectory.cpp:56-62
     PoseStamped p; p.pose = pose; p.cov = cov; p.sec = sec; p.nsec = nsec; est_vek.push_back(p);
   }
+  // eval_trajectory.cpp:74-143 (DatasetToSequence): the Oxford Radar RobotCar sequence names in evaluation order ->
+  // "00" .. "31"; anything else maps to "01" like the reference's fall-through.
+  static std::string SequenceToFileName(const std::string& sequence) {
+    static const char* const names[] = {
+        "2019-01-10-11-46-21-radar-oxford-10k", "2019-01-10-12-32-52-radar-oxford-10k", "2019-01-10-14-02-34-radar-oxford-10k",
+        "2019-01-10-14-36-48-radar-oxford-10k-partial", "2019-01-10-14-50-05-radar-oxford-10k", "2019-01-10-15-19-41-radar-oxford-10k",
+        "2019-01-11-12-26-55-radar-oxford-10k", "2019-01-11-13-24-51-radar-oxford-10k", "2019-01-11-14-02-26-radar-oxford-10k",
+        "2019-01-11-14-37-14-radar-oxford-10k", "2019-01-14-12-05-52-radar-oxford-10k", "2019-01-14-12-41-28-radar-oxford-10k",
+        "2019-01-14-13-38-21-radar-oxford-10k", "2019-01-14-14-15-12-radar-oxford-10k", "2019-01-14-14-48-55-radar-oxford-10k",
+        "2019-01-15-12-01-32-radar-oxford-10k", "2019-01-15-12-52-32-radar-oxford-10k-partial", "2019-01-15-13-06-37-radar-oxford-10k",
+        "2019-01-15-13-53-14-radar-oxford-10k", "2019-01-15-14-24-38-radar-oxford-10k", "2019-01-16-11-53-11-radar-oxford-10k",
+        "2019-01-16-13-09-37-radar-oxford-10k", "2019-01-16-13-42-28-radar-oxford-10k", "2019-01-16-14-15-33-radar-oxford-10k",
+        "2019-01-17-11-46-31-radar-oxford-10k", "2019-01-17-12-48-25-radar-oxford-10k", "2019-01-17-13-26-39-radar-oxford-10k",
+        "2019-01-17-14-03-00-radar-oxford-10k", "2019-01-18-12-42-34-radar-oxford-10k", "2019-01-18-14-14-42-radar-oxford-10k",
+        "2019-01-18-14-46-59-radar-oxford-10k", "2019-01-18-15-20-12-radar-oxford-10k"};
+    for (int i = 0; i < 32; ++i)
+      if (sequence == names[i]) { char b[8]; snprintf(b, sizeof b, "%02d", i); return b; }
+    return "01";
+  }
   static void Write(const std::string& path, const poseStampedVector& v) {                          // :169-183
     std::ofstream f(path);
     for (size_t i = 0; i < v.size(); ++i) f << MatToString(v[i].pose) << std::endl;

@@ -133,3 +133,29 @@ def test_covariance_by_sampling_matches_oracle(covsample_exe, orc, tmp_path, cos
     assert bool(cov_ok) == s_ok
     if s_ok:
         np.testing.assert_allclose(cov, ocov, rtol=2e-3, atol=1e-12)
+
+
+def test_offline_odometry_example_matches_oracle_replay(orc, tmp_path):
+    """examples/offline_odometry.cpp -- the reference's radarReader loop and command-line options over the mirror -- on a
+    synthetic 10-frame file: est/01.txt (KITTI rows) equals the oracle's sequential replay, TUM / cov files are written."""
+    from cfear_radarodometry_code_public_b200 import io as cio, synth
+    exe = str(tmp_path / "offline_odometry")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "offline_odometry.cpp"), "-o", exe, "-L" + PKG, "-lcfear_b200",
+                           "-Wl,-rpath," + PKG])
+    imgs, _ = synth.make_sequence(9, 10)
+    frames = str(tmp_path / "seq.cfrs")
+    cio.write_frames(frames, imgs)
+    out = subprocess.check_output([exe, "--frames", frames, "--est_directory", str(tmp_path), "--cost_type", "P2L", "--res", "3.5",
+                                   "--submap_scan_size", "3", "--z-min", "65", "--weight_option", "0", "--tum", "true", "--cov=true",
+                                   "--sequence", "2019-01-10-12-32-52-radar-oxford-10k"]).decode()
+    assert "Frame: 9" in out and "Trajectory saved to" in out
+    rows = np.loadtxt(str(tmp_path / "01.txt"))
+    assert rows.shape == (10, 12)
+    ref = orc.odometry_sequence(imgs, orc.reg_cfg(cost="P2L", weight_opt=0, regularization=1.0), z_min=65, radius=3.5,
+                                weight_intensity=True, submap_scan_size=3)
+    x, y, yaw = rows[:, 3], rows[:, 7], np.arctan2(rows[:, 4], rows[:, 0])
+    assert np.abs(x - ref["poses"][:, 0]).max() < 1e-4 + 1e-6 and np.abs(y - ref["poses"][:, 1]).max() < 1e-4 + 1e-6
+    assert np.abs(yaw - ref["poses"][:, 2]).max() < 1e-5 + 2e-6
+    assert len(open(str(tmp_path / "01_tum.txt")).read().strip().split("\n")) == 10
+    assert len(open(str(tmp_path / "01_cov.txt")).read().strip().split("\n")[0].split(" ")) == 37
