@@ -342,3 +342,19 @@ def test_oracle_get_cost_and_sampled_covariance(orc):
     # degenerate: a source that sees nothing of the keyframes
     far = p.copy(); far[K, :2] += 1e4
     assert orc.get_cost(sets, far, cfg)[0] is False
+
+
+def test_frame_file_layout(tmp_path):
+    """io.write_frames: the raw frame container examples/offline_odometry.cpp reads (header, per-frame stamp + image)."""
+    import struct
+    from cfear_radarodometry_code_public_b200 import io as cio
+    imgs = (np.arange(3 * 4 * 16, dtype=np.uint32) % 251).astype(np.uint8).reshape(3, 4, 16)
+    path = str(tmp_path / "s.cfrs")
+    cio.write_frames(path, imgs, stamps_ns=[5, 250_000_005, 500_000_005])
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"CFRS" and struct.unpack_from("<3i", raw, 4) == (3, 4, 16)
+    assert len(raw) == 16 + 3 * (8 + 64)
+    for i, t in enumerate([5, 250_000_005, 500_000_005]):
+        off = 16 + i * 72
+        assert struct.unpack_from("<Q", raw, off)[0] == t
+        assert raw[off + 8: off + 72] == imgs[i].tobytes()
