@@ -196,6 +196,35 @@ def test_golden_vectors(orc):
     np.testing.assert_allclose(op, g["poses_out"], atol=1e-9)
 
 
+def test_golden_vectors_v2(orc):
+    """P2D registration against two keyframes (pose, iteration counts, cost, covariance), GetCost, covariance by sampling
+    and an 8-scan fuser replay, frozen in cfear_golden_v2.npz."""
+    g = np.load(os.path.join(GOLD, "cfear_golden_v2.npz"))
+    K = 2
+    img = synth.make_problem_images(int(g["seed"]), K)[0]
+    assert np.array_equal(img[K, ::8, ::8], g["img_sub"])
+    sets = [helpers.oracle_cells(orc, img[i], radius=3.0)[1] for i in range(K + 1)]
+    cfg = orc.reg_cfg(cost="P2D", loss="Huber", weight_opt=4, regularization=0.1)
+    ok, op, cov, st, _ = orc.register(sets, g["poses_in"], cfg)
+    assert ok and st.outer_iterations == int(g["outer"]) and st.inner_iterations == int(g["inner"])
+    assert st.num_residuals == int(g["num_residuals"])
+    np.testing.assert_allclose(op, g["poses_out"], atol=1e-9)
+    np.testing.assert_allclose(st.final_cost, float(g["final_cost"]), rtol=1e-9)
+    np.testing.assert_allclose(cov, g["cov"], rtol=1e-7, atol=1e-14)
+    gok, gcost, gnres = orc.get_cost(sets, op, cfg)
+    assert gok and gnres == int(g["get_cost_nres"])
+    np.testing.assert_allclose(gcost, float(g["get_cost"]), rtol=1e-9)
+    sok, scov, S = orc.sampled_covariance(sets, op, cfg, st.final_cost, st.num_residuals)
+    assert sok
+    np.testing.assert_allclose(S, g["samples"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(scov, g["sampled_cov"], rtol=1e-5, atol=1e-14)
+    seq = synth.make_sequence(int(g["seq_seed"]), 8)[0]
+    assert np.array_equal(seq[-1, ::8, ::8], g["seq_sub"])
+    rep = orc.odometry_sequence(seq, orc.reg_cfg(cost="P2L", weight_opt=0), radius=3.5, weight_intensity=True, submap_scan_size=3)
+    assert np.array_equal(rep["keyframe"], g["seq_keyframe"])
+    np.testing.assert_allclose(rep["poses"], g["seq_poses"], atol=1e-9)
+
+
 # ---- boundary: header <-> library <-> binding -------------------------------------------------------------------
 def test_capi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "cfear_b200.h")).read()
