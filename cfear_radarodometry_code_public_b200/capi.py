@@ -7,6 +7,7 @@ calls raise.  This module never imports oracle/.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -169,29 +170,16 @@ def bind_to_device_numa(device: int) -> dict:
 
 
 def pinned_array(shape, dtype):
-    """numpy array over page-locked host memory (freed when the array is garbage collected)."""
+    """numpy array over page-locked host memory.  The memory is released (cfear_free_pinned) when the last numpy view of
+    it is garbage collected: the finalizer hangs on the ctypes buffer every view keeps alive through `.base`."""
     lib = load()
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = lib.cfear_alloc_pinned(max(n, 1))
     if not p:
         raise CfearError(lib.cfear_last_error().decode())
     buf = (C.c_char * max(n, 1)).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib.cfear_free_pinned(self.ptr)
-            except Exception:
-                pass
-    _OWNERS[id(buf)] = (buf, _Owner(p))
-    return arr
-
-
-_OWNERS: dict = {}
+    weakref.finalize(buf, lib.cfear_free_pinned, p).atexit = False      # at interpreter exit the driver reclaims it
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Context:

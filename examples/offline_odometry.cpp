@@ -10,6 +10,7 @@
 //   g++ -std=c++14 -O2 -I include examples/offline_odometry.cpp -o offline_odometry
 //       -L cfear_radarodometry_code_public_b200 -lcfear_b200 -Wl,-rpath,cfear_radarodometry_code_public_b200
 //   ./offline_odometry --frames seq.cfrs --est_directory out --cost_type P2L --submap_scan_size 4 --res 3 --k_strongest 12
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,7 +39,7 @@ static std::map<std::string, std::string> ParseArgs(int argc, char** argv) {
 }
 static bool ToBool(const std::string& s) { return s == "true" || s == "1" || s == "True"; }
 
-int main(int argc, char** argv) {
+static int run(int argc, char** argv) {
   std::map<std::string, std::string> vm = ParseArgs(argc, argv);
   if (vm.count("help") || !vm.count("frames")) {
     std::cout << "offline_odometry --frames <file.cfrs> [--est_directory DIR] [--sequence NAME] [--res 3.5] [--range-res 0.0438]\n"
@@ -97,6 +98,17 @@ int main(int argc, char** argv) {
   std::cout << "Loading frames from: " << vm["frames"] << " (" << n << " x " << A << " x " << R << ")" << std::endl;
   std::cout << rad_pars.ToString();
 
+  // The device context is shaped by the data and the options: image geometry from the frame header, k, and room for the
+  // keyframe window (+ current scan + the sets MapPointNormal objects of the last frames still hold).
+  cfear_config cfg;
+  cfear_default_config(&cfg);
+  cfg.azimuths = A; cfg.range_bins = R; cfg.k_strongest = rad_pars.k_strongest;
+  cfg.max_keyframes = std::max(odom_pars.submap_scan_size, 1);
+  cfg.max_cellsets = cfg.max_keyframes + 8;
+  cfg.max_batch = std::max(1, (int)(odom_pars.cov_sampling_samples_per_axis * odom_pars.cov_sampling_samples_per_axis *
+                                     odom_pars.cov_sampling_samples_per_axis));
+  Backend::Configure(cfg);
+
   radarDriver driver(rad_pars, true);
   OdometryKeyframeFuser fuser(odom_pars, true);
   EvalTrajectory eval;
@@ -125,4 +137,13 @@ int main(int argc, char** argv) {
   std::cout << "Trajectory saved to: " << est_dir << "/" << nn << ".txt (" << eval.est_vek.size() << " poses, "
             << fuser.frame_nr_ << " keyframes, " << fuser.distance_traveled << " m)" << std::endl;
   return 0;
+}
+
+int main(int argc, char** argv) {
+  try {
+    return run(argc, argv);
+  } catch (const std::exception& e) {
+    std::cerr << "offline_odometry: " << e.what() << std::endl;
+    return 1;
+  }
 }
