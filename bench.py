@@ -6,7 +6,9 @@ scans per GPU, each: k=12 k-strongest filter -> cloud -> Compensate -> oriented 
 registration against 4 resident keyframe cell sets (P2D, Huber 0.1, regularization 0.1, weight option 4,
 Ceres-style LM loop).  One "step" = one pass of that path over the batch.
 
-  value      device-timed: polar images already resident in HBM (344 MB per step per GPU > 126 MB L2)
+  value      device-timed: polar images already resident in HBM (344 MB per step per GPU > 126 MB L2); consecutive steps
+             are submitted through cfear_odometry_step_batch_dev_submit (two steps in flight on the library's own streams,
+             each step's K1 -> K3 -> K5 chain intact, results double-buffered) -- `--serial` times the stream-ordered call
   e2e        the same through cfear_odometry_step_batch_submit/_wait with pinned HOST buffers (two steps in flight):
              H2D of the images + D2H of the poses / covariances / stats of every step inside the timed region
   roofline   dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM copy bandwidth
@@ -104,12 +106,12 @@ def oracle_cfg(orc):
     return orc.reg_cfg(cost="P2D", loss="Huber", loss_limit=0.1, weight_opt=4, regularization=0.1, cov_scale=1.0)
 
 
-def cpu_leg(batch, nsample, min_seconds, steps=None, warmup=0):
-    """Times the CPU oracle port on the first `nsample` problems with all host threads.
-    Returns (scans_per_s, threads, seconds, reps, poses of the sample)."""
+def cpu_leg(batch, nsample, min_seconds, steps=None, warmup=0, threads=None):
+    """Times the CPU oracle port on the first `nsample` problems with `threads` host threads (default: all).
+    Returns (scans_per_s, threads, seconds, reps, output of the last pass, per-scan stage ms [filter, build_normals, register])."""
     import oracle as orc
     orc.build()
-    threads = os.cpu_count() or 1
+    threads = threads or (os.cpu_count() or 1)
     cfg = oracle_cfg(orc)
     sl = slice(0, nsample)
     # keyframe cell sets (untimed set-up, like the resident keyframes of the GPU arm)
@@ -125,8 +127,10 @@ def cpu_leg(batch, nsample, min_seconds, steps=None, warmup=0):
     for _ in range(max(warmup, 1)):
         out = run()
     reps, t0 = 0, time.perf_counter()
+    stage = np.zeros(3)
     while True:
         out = run()
+        stage += out["stage_ms"]
         reps += 1
         el = time.perf_counter() - t0
         if steps is not None:
@@ -134,7 +138,7 @@ def cpu_leg(batch, nsample, min_seconds, steps=None, warmup=0):
                 break
         elif el >= min_seconds:
             break
-    return nsample * reps / el, threads, el, reps, out
+    return nsample * reps / el, threads, el, reps, out, (stage / (reps * nsample)).tolist()
 
 
 def main():
@@ -147,6 +151,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="device-resident arm through the stream-ordered cfear_odometry_step_batch_dev")
+    ap.add_argument("--min-seconds", type=float, default=0.25, help="the K-step timed region is repeated until it lasts this long")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -161,14 +167,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        nsample = min(64, nprob)
-        batch = workload.make_batch(nsample, K, seed0=0)
-        sps, threads, el, reps, _ = cpu_leg(batch, nsample, 0.0, steps=max(args.steps, 1), warmup=args.warmup)
-        sample = f"{nsample} scans of the workload per step (first {nsample} problems, seeds 0..{nsample - 1}), {threads} host threads"
+        # one step = the same nprob scans one b200 step processes (seeds 0..nprob-1), all host threads
+        batch = workload.make_batch(nprob, K, seed0=0)
+        sps, threads, el, reps, _, stage = cpu_leg(batch, nprob, 0.0, steps=max(args.steps, 1), warmup=args.warmup)
+        sample = (f"{nprob} scans per step = the whole per-GPU batch of the workload (seeds 0..{nprob - 1}), {threads} host threads; "
+                  "oracle/cfear_oracle.cc, g++ -O3 -ffp-contract=off (the reference's own flags class, CMakeLists.txt:32-33: -O3, no -march); "
+                  "the ROS/PCL/Ceres reference itself cannot be built here")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": sps, "unit": "scans/s", "n_gpus": args.gpus,
                           "steps": reps, "warmup": args.warmup, "ms_per_step": 1e3 * el / reps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": threads, "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": threads, "kind": "port", "sample": sample,
+                                           "stage_ms_per_scan_per_thread": dict(zip(["filter", "build_normals", "register"], stage))},
                           "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -197,12 +206,14 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + 1), max_keyframes=K, **workload.CFEAR3)
+    NSETS = 2                      # result / current-slot sets the overlapped steps rotate through
+    ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + NSETS), max_keyframes=K, **workload.CFEAR3)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
 
     # resident keyframe cell sets, built by the GPU path from the keyframe images (untimed set-up)
     kf_slots = np.arange(nprob * K, dtype=np.int32).reshape(nprob, K)
-    cur_slots = (nprob * K + np.arange(nprob)).astype(np.int32)
+    cur_sets = [(nprob * (K + j) + np.arange(nprob)).astype(np.int32) for j in range(NSETS)]
+    cur_slots = cur_sets[0]
     for i in range(K):
         ctx.scans_to_cells_batch(batch["kf_polar"][:, i], None, kf_slots[:, i])
 
@@ -210,19 +221,31 @@ def main():
     t_polar = torch.from_numpy(batch["polar"]).to(dev)
     t_mot = torch.from_numpy(batch["mot"]).to(dev)
     t_kf = torch.from_numpy(kf_slots).to(dev)
-    t_cur = torch.from_numpy(cur_slots).to(dev)
+    t_cur = [torch.from_numpy(cs).to(dev) for cs in cur_sets]
     t_poses0 = torch.from_numpy(batch["poses"]).to(dev)
-    t_poses = t_poses0.clone()
-    t_cov = torch.zeros(nprob, 36, dtype=torch.float64, device=dev)
-    t_stats = torch.zeros(nprob, capi.STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    t_poses = [t_poses0.clone() for _ in range(NSETS)]
+    t_cov = [torch.zeros(nprob, 36, dtype=torch.float64, device=dev) for _ in range(NSETS)]
+    t_stats = [torch.zeros(nprob, capi.STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in range(NSETS)]
     t_gather = torch.zeros(world * nprob, K + 1, 3, dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
+    tickets = [None] * NSETS
+    nstep = [0]
 
     def step_dev():
+        j = nstep[0] % NSETS
+        nstep[0] += 1
+        if tickets[j] is not None:
+            ctx.stream_wait_ticket(tickets[j])                  # the restore below overwrites that step's in/out pose table
+            tickets[j] = None
         with torch.cuda.stream(ext):
-            t_poses.copy_(t_poses0, non_blocking=True)          # Register() works in/out on Tsrc: restore the guess
-        ctx.odometry_step_batch_dev(nprob, t_polar.data_ptr(), t_mot.data_ptr(), t_kf.data_ptr(), K, t_cur.data_ptr(),
-                                    t_poses.data_ptr(), t_cov.data_ptr(), t_stats.data_ptr())
+            t_poses[j].copy_(t_poses0, non_blocking=True)       # Register() works in/out on Tsrc: restore the guess
+        a = (nprob, t_polar.data_ptr(), t_mot.data_ptr(), t_kf.data_ptr(), K, t_cur[j].data_ptr(),
+             t_poses[j].data_ptr(), t_cov[j].data_ptr(), t_stats[j].data_ptr())
+        if args.serial:
+            ctx.odometry_step_batch_dev(*a)
+        else:
+            tickets[j] = ctx.odometry_step_batch_dev_submit(*a)
+        return j
 
     def barrier():
         if world > 1:
@@ -232,8 +255,20 @@ def main():
     for _ in range(warmup):
         step_dev()
     ctx.sync()
-    npts, ncells = ctx.last_counts(cur_slots)
+    npts, ncells = ctx.last_counts(cur_sets[(nstep[0] - 1) % NSETS])
     _, kf_ncells = None, np.array([ctx.cells_count(s) for s in kf_slots[: min(nprob, 32)].ravel()])
+    # the K-step region is repeated until the timed region lasts --min-seconds (a 20-step region is ~10 ms: too few clock samples)
+    est = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    est[0].record(ext)
+    for _ in range(4):
+        step_dev()
+    ctx.join()
+    est[1].record(ext)
+    torch.cuda.synchronize()
+    ms_est = est[0].elapsed_time(est[1]) / 4
+    regions = max(1, int(np.ceil(args.min_seconds * 1e3 / max(ms_est * args.steps, 1e-6))))
+    regions = min(regions, max(1, 4096 // max(args.steps, 1)))          # stage-event capacity of the library
+    total_steps = regions * args.steps
     sampler = ClockSampler(local)
     time.sleep(0.3)
     ctx.stage_timing(True)
@@ -242,11 +277,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record(ext)
-    for _ in range(args.steps):
-        step_dev()
+    for _ in range(total_steps):
+        jlast = step_dev()
+    ctx.join()                                                     # the context stream waits for the steps in flight
     if world > 1:
         with torch.cuda.stream(ext):
-            dist.all_gather_into_tensor(t_gather.view(-1), t_poses.view(-1))   # the path's only collective
+            dist.all_gather_into_tensor(t_gather.view(-1), t_poses[jlast].view(-1))   # the path's only collective
     e1.record(ext)
     barrier()
     tw1 = time.time()
@@ -257,9 +293,21 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * nprob * args.steps / (ms * 1e-3)
-    stats = np.frombuffer(t_stats.cpu().numpy().tobytes(), dtype=capi.STATS_DTYPE)
-    poses_dev = t_poses.cpu().numpy()
+    value = world * nprob * total_steps / (ms * 1e-3)
+    stats = np.frombuffer(t_stats[jlast].cpu().numpy().tobytes(), dtype=capi.STATS_DTYPE)
+    poses_dev = t_poses[jlast].cpu().numpy()
+    for j in range(NSETS):                                          # every set holds the same problems: identical results
+        assert np.array_equal(t_poses[j].cpu().numpy(), poses_dev), "overlapped steps disagree between result sets"
+    # the same kernels timed one at a time (stream-ordered call): what each costs when it has the GPU to itself
+    ctx.stage_timing(True)
+    for _ in range(20):
+        with torch.cuda.stream(ext):
+            t_poses[0].copy_(t_poses0, non_blocking=True)
+        ctx.odometry_step_batch_dev(nprob, t_polar.data_ptr(), t_mot.data_ptr(), t_kf.data_ptr(), K, t_cur[0].data_ptr(),
+                                    t_poses[0].data_ptr(), t_cov[0].data_ptr(), t_stats[0].data_ptr())
+    ctx.sync()
+    nser, stage_ser = ctx.stage_timing(False)
+    assert np.array_equal(t_poses[0].cpu().numpy(), poses_dev), "overlapped and stream-ordered steps disagree"
 
     # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8(d), per-kernel split in DESIGN.md) ----
     hbm_peak, peak_src = peaks()
@@ -270,6 +318,7 @@ def main():
            "k5_register": (K * n_kf_cells + n_cells) * 80 + K * n_kf_cells * 12 + (K + 1) * 24 + 36 * 8 + 40}
     names = ["k1_kstrongest", "k3_surface_points", "k5_register"]
     per_launch_ms = [m / max(nst, 1) for m in stage_ms]
+    serial_ms = [m / max(nser, 1) for m in stage_ser]
     dom = int(np.argmax(per_launch_ms))
     ach = alg[names[dom]] * nprob / (per_launch_ms[dom] * 1e-3) / 1e9 if per_launch_ms[dom] > 0 else 0.0
     b_scan = A * R + 2 * n_pts * 16 + n_cells * 80 + (K * n_kf_cells + n_cells) * 80 + 24
@@ -277,6 +326,13 @@ def main():
             "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_scan": alg[names[dom]],
             "stage_ms_per_step": dict(zip(names, per_launch_ms)),
+            "stage_ms_note": ("CUDA events around each kernel on the stream it is launched on, averaged over the timed region; "
+                              + ("stream-ordered steps" if args.serial else
+                                 "two steps are in flight, so a kernel shares the SMs with the neighbouring step's kernels and the "
+                                 "durations overlap (their sum exceeds ms_per_step)")),
+            "stage_ms_alone": dict(zip(names, serial_ms)),
+            "stage_frac_of_hbm_peak_alone": {n: (alg[n] * nprob / (t * 1e-3) / 1e9 / hbm_peak if t > 0 else None)
+                                             for n, t in zip(names, serial_ms)},
             "stage_frac_of_hbm_peak": {n: (alg[n] * nprob / (t * 1e-3) / 1e9 / hbm_peak if t > 0 else None)
                                        for n, t in zip(names, per_launch_ms)},
             "whole_path": {"bytes_per_scan": b_scan, "achieved": b_scan * value / world / 1e9,
@@ -308,7 +364,7 @@ def main():
             for i in range(nsteps):
                 o = h_outs[i & 1]
                 np.copyto(o["poses"], batch["poses"])               # Register() works in/out on Tsrc: restore the guess
-                t = ctx.odometry_step_batch_submit(h_polar, h_mot, kf_slots, cur_slots, o)
+                t = ctx.odometry_step_batch_submit(h_polar, h_mot, kf_slots, cur_slots, o)   # (host path: stream-ordered chunks, one slot set)
                 if pending is not None:
                     ctx.odometry_step_batch_wait(pending)
                 pending = t
@@ -316,9 +372,10 @@ def main():
             return h_outs[(nsteps - 1) & 1]
 
         run_e2e(warmup)
+        e2e_steps = max(args.steps, 20)                  # >= 0.1 s of timed region at ~6 ms per step
         barrier()
         t0 = time.perf_counter()
-        h_out = run_e2e(args.steps)
+        h_out = run_e2e(e2e_steps)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         if world > 1:
@@ -327,8 +384,8 @@ def main():
             el = float(t.item())
         h2d = h_polar.nbytes + batch["mot"].nbytes + kf_slots.nbytes + cur_slots.nbytes + batch["poses"].nbytes
         d2h = h_out["poses"].nbytes + h_out["cov"].nbytes + h_out["stats"].nbytes + h_out["npts"].nbytes
-        e2e = {"value": world * nprob * args.steps / el, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / args.steps, "host_numa_binding": numa,
+        e2e = {"value": world * nprob * e2e_steps / el, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps, "host_numa_binding": numa,
                "api": "cfear_odometry_step_batch_submit / _wait, two steps in flight, pinned host buffers"}
         assert np.allclose(h_out["poses"], poses_dev, atol=1e-12), "e2e and device-resident arms disagree"
 
@@ -338,17 +395,34 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nsample = min(64, nprob)
-        sps, threads, el, reps, out = cpu_leg(batch, nsample, args.cpu_seconds)
+        sps, threads, el, reps, out, stage_n = cpu_leg(batch, nsample, args.cpu_seconds * 0.6)
+        sps1, _, el1, reps1, _, stage_1 = cpu_leg(batch, nsample, args.cpu_seconds * 0.4, threads=1)
         d = poses_dev[:nsample, K] - out["poses"][:, K]
+        par = {"max_pos_err_m": float(np.hypot(d[:, 0], d[:, 1]).max()), "max_rot_err_rad": float(np.abs(d[:, 2]).max()),
+               "outer_iterations_equal": bool(np.array_equal(stats["outer_iterations"][:nsample], [s.outer_iterations for s in out["stats"]])),
+               "inner_iterations_equal": bool(np.array_equal(stats["inner_iterations"][:nsample], [s.inner_iterations for s in out["stats"]])),
+               "num_residuals_equal": bool(np.array_equal(stats["num_residuals"][:nsample], [s.num_residuals for s in out["stats"]])),
+               "npts_equal": bool(np.array_equal(npts[:nsample], out["npts"])), "ncells_equal": bool(np.array_equal(ncells[:nsample], out["ncells"]))}
         cpu = {"value": sps, "unit": "scans/s", "cores": threads, "kind": "port",
                "sample": f"first {nsample} scans of the workload x {reps} passes ({el:.1f} s), {threads} host threads; "
-                         "oracle/cfear_oracle.cc (the ROS/PCL/Ceres reference cannot be built here)",
-               "parity_vs_gpu": {"max_pos_err_m": float(np.hypot(d[:, 0], d[:, 1]).max()), "max_rot_err_rad": float(np.abs(d[:, 2]).max())}}
+                         "oracle/cfear_oracle.cc built -O3 -ffp-contract=off (the reference's flags class, CMakeLists.txt:32-33); "
+                         "the ROS/PCL/Ceres reference cannot be built here",
+               "single_thread": {"value": sps1, "unit": "scans/s", "cores": 1,
+                                 "sample": f"same {nsample} scans x {reps1} passes ({el1:.1f} s), one scan at a time (the reference's execution model)",
+                                 "stage_ms_per_scan": dict(zip(["filter", "build_normals", "register"], stage_1))},
+               "stage_ms_per_scan_per_thread": dict(zip(["filter", "build_normals", "register"], stage_n)),
+               "parity_vs_gpu": par}
+        # north_star tolerance: 1e-4 m / 1e-5 rad after the same iteration count -- a fast wrong answer is not a result
+        if not (par["max_pos_err_m"] < 1e-4 and par["max_rot_err_rad"] < 1e-5 and par["outer_iterations_equal"]
+                and par["inner_iterations_equal"] and par["num_residuals_equal"] and par["npts_equal"] and par["ncells_equal"]):
+            raise SystemExit("bench.py: the CUDA path disagrees with the CPU oracle on the bench workload: " + json.dumps(par))
 
     if rank == 0:
         err = poses_dev[:, K] - batch["truth"]
+        config["steps_in_flight"] = 1 if args.serial else 2
+        config["api"] = "cfear_odometry_step_batch_dev" if args.serial else "cfear_odometry_step_batch_dev_submit (two steps in flight)"
         line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "timed_regions": regions, "steps_timed": total_steps, "ms_per_step": ms / total_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "workload_stats": {"n_pts_mean": n_pts, "n_cells_mean": n_cells, "kf_cells_mean": n_kf_cells,

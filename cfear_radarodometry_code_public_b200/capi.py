@@ -58,7 +58,7 @@ STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), (
 SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_update_config", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
-           "cfear_register_batch", "cfear_get_cost_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_sync",
+           "cfear_register_batch", "cfear_get_cost_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_odometry_step_batch_dev_submit", "cfear_stream_wait_ticket", "cfear_join", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
            "cfear_cfar_filter", "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
@@ -113,6 +113,9 @@ def load():
         lib.cfear_odometry_step_batch_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch_wait.argtypes = [vp, i32]
         lib.cfear_odometry_step_batch_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
+        lib.cfear_odometry_step_batch_dev_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+        lib.cfear_stream_wait_ticket.argtypes = [vp, i32]
+        lib.cfear_join.argtypes = [vp]
         lib.cfear_stage_timing.argtypes = [vp, i32, vp]
         lib.cfear_last_counts.argtypes = [vp, i32, vp, vp, vp]
         lib.cfear_cfar_filter.argtypes = [vp, vp, i32, C.POINTER(CfarParams), vp, i32, vp]
@@ -424,6 +427,19 @@ class Context:
     def odometry_step_batch_dev(self, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats):
         self._ck(self.lib.cfear_odometry_step_batch_dev(self.h, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses,
                                                         d_cov36, d_stats), "cfear_odometry_step_batch_dev")
+
+    def odometry_step_batch_dev_submit(self, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats):
+        """Overlapped device-resident step (cfear_odometry_step_batch_dev_submit); returns the ticket."""
+        t = C.c_int32(-1)
+        self._ck(self.lib.cfear_odometry_step_batch_dev_submit(self.h, n, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses,
+                                                               d_cov36, d_stats, C.byref(t)), "cfear_odometry_step_batch_dev_submit")
+        return int(t.value)
+
+    def stream_wait_ticket(self, ticket):
+        self._ck(self.lib.cfear_stream_wait_ticket(self.h, int(ticket)), "cfear_stream_wait_ticket")
+
+    def join(self):
+        self._ck(self.lib.cfear_join(self.h), "cfear_join")
 
 
 class Sequences:

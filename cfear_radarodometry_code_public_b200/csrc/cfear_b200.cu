@@ -114,6 +114,18 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
+constexpr int CFEAR_NPIPES = 2;        // device-resident steps that may overlap (cfear_odometry_step_batch_dev_submit)
+
+// Everything one step writes between K1 and K5.  Set 0 aliases the context's own buffers (every stream-ordered entry
+// point uses it on the context stream); sets 1..CFEAR_NPIPES have their own streams so that consecutive device-resident
+// steps can overlap: K1 / K3 of step i+1 fill the SMs that K5 of step i leaves idle in its tail.
+struct PipeBufs {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t in = nullptr, done = nullptr;
+  int32_t *d_kidx = nullptr, *d_kcnt = nullptr, *d_rowcnt = nullptr, *d_npts = nullptr, *d_status = nullptr, *d_slots = nullptr;
+  float4 *d_rowcloud = nullptr, *d_bufA = nullptr, *d_bufB = nullptr;
+  int* d_ghist = nullptr; double2 *d_celltmp = nullptr, *d_res = nullptr;
+};
 
 struct cfear_ctx {
   cfear_config cfg;
@@ -140,6 +152,9 @@ struct cfear_ctx {
   double2* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
   CellPool pool;
   std::vector<double2> h_cs;
+  PipeBufs pb[CFEAR_NPIPES + 1];    // [0] aliases the buffers above on the context stream; [1..] the overlapped steps' sets
+  bool pipes_ready = false, inflight = false;
+  int next_pipe = 0, last_pipe = 0;
 
   template <typename T> int alloc(T** p, size_t count) {
     void* q = nullptr;
@@ -177,12 +192,19 @@ void cfear_destroy(cfear_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 1; i <= CFEAR_NPIPES; ++i) if (c->pb[i].stream) cudaStreamSynchronize(c->pb[i].stream);
   for (void* p : c->allocs) cudaFree(p);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->chunk_ev) cudaEventDestroy(e);
   for (auto& e : c->k1_done) cudaEventDestroy(e);
   for (auto& e : c->ticket_ev) cudaEventDestroy(e);
   if (c->polar_free) cudaEventDestroy(c->polar_free);
+  for (int i = 1; i <= CFEAR_NPIPES; ++i) {
+    PipeBufs& B = c->pb[i];
+    if (B.stream) cudaStreamDestroy(B.stream);
+    if (B.in) cudaEventDestroy(B.in);
+    if (B.done) cudaEventDestroy(B.done);
+  }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -206,10 +228,20 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   cfear_ctx* c = new (std::nothrow) cfear_ctx();
   if (!c) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
   c->cfg = *cfg;
-  CK(cudaSetDevice(cfg->device));
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&c->polar_free, cudaEventDisableTiming));
+  // from here on a CUDA failure must not leak the half-built context
+#define CKC(expr)                                                                                 \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                \
+      cfear_destroy(c);                                                                           \
+      return CFEAR_ERR_CUDA;                                                                      \
+    }                                                                                             \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&c->polar_free, cudaEventDisableTiming));
   const int A = cfg->azimuths, R = cfg->range_bins, k = cfg->k_strongest, B = cfg->max_batch;
   c->cap_pts = A * k;
   c->max_cells = cfg->max_cells > 0 ? cfg->max_cells : A * k;
@@ -218,16 +250,16 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   c->g_hist_cap = 1 << 18;
   // shared-memory plan of K3
   int max_optin = 0;
-  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+  CKC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
   const size_t hist_bytes = (size_t)(K3_HIST_CAP + 1) * sizeof(int);
   const size_t full = (size_t)c->cap_pts * 32 + hist_bytes;
   c->pts_in_smem = (full + 2048 <= (size_t)max_optin) ? 1 : 0;
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
-  CK(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
-  CK(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-  CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cfg->range_bins + 1) * 4)));
+  CKC(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+  CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+  // (the CA-CFAR kernel's shared-memory attribute is set by cfear_cfar_filter, which is the only place that needs it)
   c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
-CK(k5_set_smem_cost0(c->k5_smem)); CK(k5_set_smem_cost1(c->k5_smem)); CK(k5_set_smem_cost2(c->k5_smem));
+  CKC(k5_set_smem_cost0(c->k5_smem)); CKC(k5_set_smem_cost1(c->k5_smem)); CKC(k5_set_smem_cost2(c->k5_smem));
 
   const size_t rows = (size_t)B * A;
   AL(c->d_polar, rows * R);
@@ -253,13 +285,13 @@ CK(k5_set_smem_cost0(c->k5_smem)); CK(k5_set_smem_cost1(c->k5_smem)); CK(k5_set_
   AL(P.avg_intensity, S * M); AL(P.nsamples, S * M); AL(P.grid, S);
   P.grid_stride = P.grid_cap + 8;
   AL(P.gstart, S * P.grid_stride); AL(P.gpt, S * M); AL(P.fm_scratch, S * M);
-  CK(cudaMemsetAsync(P.ncells, 0, S * sizeof(int), c->stream));
-  CK(cudaMemsetAsync(P.gstart, 0, S * P.grid_stride * sizeof(uint16_t), c->stream));
+  CKC(cudaMemsetAsync(P.ncells, 0, S * sizeof(int), c->stream));
+  CKC(cudaMemsetAsync(P.gstart, 0, S * P.grid_stride * sizeof(uint16_t), c->stream));
   {
     std::vector<NNGrid> g(S);
     for (auto& x : g) { x.ox = x.oy = 0.f; x.g = 4.f; x.inv_g = 0.25f; x.nx = x.ny = 1; }
-    CK(cudaMemcpyAsync(P.grid, g.data(), S * sizeof(NNGrid), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CKC(cudaMemcpyAsync(P.grid, g.data(), S * sizeof(NNGrid), cudaMemcpyHostToDevice, c->stream));
+    CKC(cudaStreamSynchronize(c->stream));
   }
   // theta = 2 pi (a+1)/A  (radar_filters.cpp:317), host libm like the reference
   c->h_cs.resize(A);
@@ -267,8 +299,16 @@ CK(k5_set_smem_cost0(c->k5_smem)); CK(k5_set_smem_cost1(c->k5_smem)); CK(k5_set_
     const double theta = ((double)(a + 1) / A) * 2. * M_PI;
     c->h_cs[a] = make_double2(cos(theta), sin(theta));
   }
-  CK(cudaMemcpyAsync(c->d_cs, c->h_cs.data(), A * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  CKC(cudaMemcpyAsync(c->d_cs, c->h_cs.data(), A * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+  CKC(cudaStreamSynchronize(c->stream));
+#undef CKC
+  {   // buffer set 0 = the context's own buffers on the context stream
+    PipeBufs& B0 = c->pb[0];
+    B0.stream = c->stream;
+    B0.d_kidx = c->d_kidx; B0.d_kcnt = c->d_kcnt; B0.d_rowcnt = c->d_rowcnt; B0.d_npts = c->d_npts; B0.d_status = c->d_status;
+    B0.d_slots = c->d_slots; B0.d_rowcloud = c->d_rowcloud; B0.d_bufA = c->d_bufA; B0.d_bufB = c->d_bufB;
+    B0.d_ghist = c->d_ghist; B0.d_celltmp = c->d_celltmp; B0.d_res = c->d_res;
+  }
   *out = c;
   return CFEAR_OK;
 }
@@ -294,6 +334,11 @@ int64_t cfear_launch_count(const cfear_ctx* c) { return c ? c->launches : 0; }
 void* cfear_stream(cfear_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int cfear_sync(cfear_ctx* c) {
   if (!c) return CFEAR_ERR_ARG;
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->inflight) {
+    for (int i = 1; i <= CFEAR_NPIPES; ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
+    c->inflight = false;
+  }
   CK(cudaStreamSynchronize(c->stream));
   return CFEAR_OK;
 }
@@ -328,7 +373,7 @@ int cfear_memcpy_d2h(cfear_ctx* c, void* dst, const void* src, size_t bytes) {
 }  // extern "C"
 
 // ---- launch helpers (device-resident arguments) ----------------------------------------------------
-static int launch_k1(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
+static int launch_k1(cfear_ctx* c, const PipeBufs& B, const uint8_t* d_polar, int nscans) {
   K1Params p;
   p.polar = d_polar; p.nrows = nscans * c->cfg.azimuths; p.A = c->cfg.azimuths; p.R = c->cfg.range_bins;
   p.polar_end = d_polar + (size_t)p.nrows * p.R;
@@ -337,8 +382,8 @@ static int launch_k1(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
   const double range_res = (double)c->cfg.range_res, min_distance = (double)c->cfg.min_distance;
   p.min_range_bin = (int)ceil(min_distance / range_res);                      // radar_filters.cpp:315
   p.range_res = range_res; p.cs = c->d_cs;
-  p.kidx = c->d_kidx; p.kcnt = c->d_kcnt; p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
-  k1_launch(p, c->stream);
+  p.kidx = B.d_kidx; p.kcnt = B.d_kcnt; p.rowcloud = B.d_rowcloud; p.rowcnt = B.d_rowcnt;
+  k1_launch(p, B.stream);
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;
@@ -358,18 +403,18 @@ static int launch_peaks(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
   return CFEAR_OK;
 }
 
-static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud, int off = 0) {
+static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud, int off = 0) {
   K3Params p;
   p.mode = mode; p.A = c->cfg.azimuths; p.k = c->cfg.k_strongest;
-  p.rowcloud = c->d_rowcloud; p.rowcnt = c->d_rowcnt;
+  p.rowcloud = B.d_rowcloud; p.rowcnt = B.d_rowcnt;
   p.mot = (c->cfg.compensate && mode == 0) ? d_mot : nullptr; p.ccw = c->cfg.radar_ccw; p.cs = c->d_cs;
-  p.cloud = (mode == 1 || write_cloud) ? c->d_cloud : nullptr; p.npts = c->d_npts; p.cap_pts = c->cap_pts;
+  p.cloud = (mode == 1 || write_cloud) ? c->d_cloud : nullptr; p.npts = B.d_npts; p.cap_pts = c->cap_pts;
   p.slots = d_slots; p.radius = c->cfg.radius;
   p.leaf = (float)((double)c->cfg.radius / c->cfg.downsample_factor);        // pointnormal.cpp:279
   p.weight_intensity = c->cfg.weight_intensity; p.origin_x = 0.0; p.origin_y = 0.0;   // odometrykeyframefuser.cpp:161
   p.nn_cell = 8.0f;
-  p.pts_in_smem = c->pts_in_smem; p.g_bufA = c->d_bufA; p.g_bufB = c->d_bufB;
-  p.g_hist = c->d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = c->d_status; p.cell_tmp = c->d_celltmp; p.pool = c->pool;
+  p.pts_in_smem = c->pts_in_smem; p.g_bufA = B.d_bufA; p.g_bufB = B.d_bufB;
+  p.g_hist = B.d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = B.d_status; p.cell_tmp = B.d_celltmp; p.pool = c->pool;
   if (off) {   // sub-batch: every per-scan array starts at scan `off` (d_mot / d_slots are passed already offset)
     const size_t o = (size_t)off;
     p.rowcloud += o * p.A * p.k; p.rowcnt += o * p.A;
@@ -378,18 +423,18 @@ static int launch_k3(cfear_ctx* c, int mode, int nscans, const double* d_mot, co
     if (p.g_bufA) { p.g_bufA += o * p.cap_pts; p.g_bufB += o * p.cap_pts; }
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, c->stream>>>(p);
+  k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, B.stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;
 }
 
-static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
+static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
                      cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0, const int32_t* d_nscans_pp = nullptr,
                      int solver_mode_override = -1) {
   RegParams p;
   p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.nscans_pp = d_nscans_pp; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
-  p.stats = d_stats; p.assoc = d_assoc; p.res = c->d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
+  p.stats = d_stats; p.assoc = d_assoc; p.res = B.d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
   p.cost = c->cfg.cost; p.loss = c->cfg.loss; p.weight_opt = c->cfg.weight_opt; p.solver_mode = c->cfg.solver_mode;
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
@@ -399,9 +444,9 @@ static int launch_k5(cfear_ctx* c, int nprob, int nscans, const int32_t* d_slots
   p.smem_bytes = c->k5_smem;
 bool launched = false;
   switch (p.cost) {
-    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, c->stream); break;
-    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, c->stream); break;
-    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, c->stream); break;
+    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, B.stream); break;
+    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, B.stream); break;
+    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, B.stream); break;
   }
   if (!launched) { g_err = "this build has no instantiation for the requested cost / loss"; return CFEAR_ERR_ARG; }
   c->launches++;
@@ -427,7 +472,16 @@ static int check_slot(cfear_ctx* c, int slot) {
   return CFEAR_OK;
 }
 #define RC(expr) do { int rc__ = (expr); if (rc__ != CFEAR_OK) return rc__; } while (0)
-#define ENTER(c) do { if (!(c)) { g_err = "null context"; return CFEAR_ERR_ARG; } CK(cudaSetDevice((c)->cfg.device)); } while (0)
+// The overlapped device-resident steps (cfear_odometry_step_batch_dev_submit) run on their own streams; every other
+// entry point works on the context stream and first makes it wait, on the device, for the steps still in flight.
+static int join_pipes(cfear_ctx* c) {
+  if (!c->inflight) return CFEAR_OK;
+  for (int i = 1; i <= CFEAR_NPIPES; ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
+  c->inflight = false;
+  return CFEAR_OK;
+}
+#define ENTER_NOJOIN(c) do { if (!(c)) { g_err = "null context"; return CFEAR_ERR_ARG; } CK(cudaSetDevice((c)->cfg.device)); } while (0)
+#define ENTER(c) do { ENTER_NOJOIN(c); RC(join_pipes(c)); } while (0)
 
 extern "C" {
 
@@ -441,7 +495,7 @@ int cfear_filter(cfear_ctx* c, const uint8_t* polar, int nscans, int32_t* idx_ou
   const size_t rows = (size_t)nscans * A;
   c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
-  RC(launch_k1(c, c->d_polar, nscans));
+  RC(launch_k1(c, c->pb[0], c->d_polar, nscans));
   if (idx_out) CK(cudaMemcpyAsync(idx_out, c->d_kidx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (cnt_out) CK(cudaMemcpyAsync(cnt_out, c->d_kcnt, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (cloud_out || npts_out) {
@@ -490,7 +544,7 @@ int cfear_surface_points(cfear_ctx* c, const cfear_point* cloud, int n, int slot
   const int32_t n32 = n, s32 = slot;
   CK(cudaMemcpyAsync(c->d_npts, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  RC(launch_k3(c, 1, 1, nullptr, c->d_curslots, false));
+  RC(launch_k3(c, c->pb[0], 1, 1, nullptr, c->d_curslots, false));
   int32_t st = 0, nc = 0;
   CK(cudaMemcpyAsync(&st, c->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(&nc, c->pool.ncells + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -513,8 +567,9 @@ int cfear_scans_to_cells_batch(cfear_ctx* c, int nscans, const uint8_t* polar, c
   CK(cudaMemcpyAsync(c->d_curslots, slots, (size_t)nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   const bool have_mot = mot != nullptr && c->cfg.compensate;
   if (have_mot) CK(cudaMemcpyAsync(c->d_mot, mot, (size_t)nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  RC(launch_k1(c, c->d_polar, nscans));
-  RC(launch_k3(c, 0, nscans, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
+  c->last_pipe = 0;
+  RC(launch_k1(c, c->pb[0], c->d_polar, nscans));
+  RC(launch_k3(c, c->pb[0], 0, nscans, have_mot ? c->d_mot : nullptr, c->d_curslots, false));
   std::vector<int32_t> st(nscans);
   CK(cudaMemcpyAsync(st.data(), c->d_status, (size_t)nscans * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -607,7 +662,7 @@ int cfear_register_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nsca
     }
     CK(cudaMemsetAsync(c->d_assoc, 0xff, assoc_n * sizeof(int32_t), c->stream));
   }
-  RC(launch_k5(c, nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, assoc_out ? c->d_assoc : nullptr));
+  RC(launch_k5(c, c->pb[0], nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, assoc_out ? c->d_assoc : nullptr));
   CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
@@ -627,7 +682,7 @@ int cfear_get_cost_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nsca
   for (size_t i = 0; i < (size_t)nprob * nscans; ++i) RC(check_slot(c, slots[i]));
   CK(cudaMemcpyAsync(c->d_slots, slots, (size_t)nprob * nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  RC(launch_k5(c, nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, nullptr, CFEAR_SOLVER_COST_ONLY));
+  RC(launch_k5(c, c->pb[0], nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, nullptr, CFEAR_SOLVER_COST_ONLY));
   std::vector<cfear_reg_stats> st((size_t)nprob);
   CK(cudaMemcpyAsync(st.data(), c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -651,19 +706,19 @@ __global__ void k_merge_slots(const int32_t* kf, const int32_t* cur, int K, int 
   out[i] = (j < K) ? kf[b * K + j] : cur[b];
 }
 
-static int step_dev(cfear_ctx* c, int nprob, const uint8_t* d_polar, const double* d_mot, const int32_t* d_kf_slots, int K,
-                    const int32_t* d_cur_slots, double* d_poses, double* d_cov36, cfear_reg_stats* d_stats, bool k1_done) {
+static int step_dev(cfear_ctx* c, const PipeBufs& B, int nprob, const uint8_t* d_polar, const double* d_mot, const int32_t* d_kf_slots, int K,
+                    const int32_t* d_cur_slots, double* d_poses, double* d_cov36, cfear_reg_stats* d_stats) {
   RC(begin_timed_step(c));
-  if (c->timing) CK(cudaEventRecord(c->evset[0], c->stream));
-  if (!k1_done) RC(launch_k1(c, d_polar, nprob));
-  if (c->timing) CK(cudaEventRecord(c->evset[1], c->stream));
-  RC(launch_k3(c, 0, nprob, d_mot, d_cur_slots, false));
-  if (c->timing) CK(cudaEventRecord(c->evset[2], c->stream));
-  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, c->stream>>>(d_kf_slots, d_cur_slots, K, nprob, c->d_slots);
+  if (c->timing) CK(cudaEventRecord(c->evset[0], B.stream));
+  RC(launch_k1(c, B, d_polar, nprob));
+  if (c->timing) CK(cudaEventRecord(c->evset[1], B.stream));
+  RC(launch_k3(c, B, 0, nprob, d_mot, d_cur_slots, false));
+  if (c->timing) CK(cudaEventRecord(c->evset[2], B.stream));
+  k_merge_slots<<<(nprob * (K + 1) + 255) / 256, 256, 0, B.stream>>>(d_kf_slots, d_cur_slots, K, nprob, B.d_slots);
   c->launches++;
   CK(cudaGetLastError());
-  RC(launch_k5(c, nprob, K + 1, c->d_slots, d_poses, d_cov36, d_stats, nullptr));
-  if (c->timing) CK(cudaEventRecord(c->evset[3], c->stream));
+  RC(launch_k5(c, B, nprob, K + 1, B.d_slots, d_poses, d_cov36, d_stats, nullptr));
+  if (c->timing) CK(cudaEventRecord(c->evset[3], B.stream));
   return CFEAR_OK;
 }
 
@@ -675,7 +730,81 @@ int cfear_odometry_step_batch_dev(cfear_ctx* c, int nprob, const uint8_t* d_pola
   if (K < 1 || K > c->cfg.max_keyframes) { g_err = "K must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
   if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
   if (nprob == 0) return CFEAR_OK;
-  return step_dev(c, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats, false);
+  c->last_pipe = 0;
+  return step_dev(c, c->pb[0], nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats);
+}
+
+static int ensure_tickets(cfear_ctx* c) {
+  while ((int)c->ticket_ev.size() < CFEAR_MAX_TICKETS) {
+    cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ticket_ev.push_back(e);
+  }
+  return CFEAR_OK;
+}
+
+// Streams, events and the extra buffer sets of the overlapped device-resident steps, created on first use.
+static int ensure_pipes(cfear_ctx* c) {
+  if (c->pipes_ready) return CFEAR_OK;
+  const int A = c->cfg.azimuths, k = c->cfg.k_strongest, B = c->cfg.max_batch;
+  const size_t rows = (size_t)B * A;
+  for (int i = 1; i <= CFEAR_NPIPES; ++i) {
+    PipeBufs& P = c->pb[i];
+    CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&P.in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+    CK(cudaEventRecord(P.done, P.stream));
+#define ALP(p, n) do { int rc__ = c->alloc(&(p), (size_t)(n)); if (rc__ != CFEAR_OK) return rc__; } while (0)
+    ALP(P.d_kidx, rows * k); ALP(P.d_kcnt, rows); ALP(P.d_rowcnt, rows); ALP(P.d_rowcloud, rows * k);
+    ALP(P.d_npts, B); ALP(P.d_status, B);
+    if (!c->pts_in_smem) { ALP(P.d_bufA, (size_t)B * c->cap_pts); ALP(P.d_bufB, (size_t)B * c->cap_pts); }
+    ALP(P.d_ghist, (size_t)B * (c->g_hist_cap + 1));
+    ALP(P.d_celltmp, (size_t)B * c->cap_pts * 4);
+    ALP(P.d_slots, (size_t)B * (c->cfg.max_keyframes + 1));
+    ALP(P.d_res, (size_t)B * c->res_cap * 4);
+#undef ALP
+  }
+  c->pipes_ready = true;
+  return CFEAR_OK;
+}
+
+// Device-resident step, overlapped: step i goes to stream i mod CFEAR_NPIPES with its own K1..K5 scratch, so the filter
+// and surface-point kernels of one step run while the registration of the previous one is still in its tail (K5 lasts as
+// long as its slowest problem and leaves most SMs idle by then).  Inputs are ordered after the work already enqueued on
+// the context stream; outputs are complete at cfear_odometry_step_batch_wait(ticket) (host) /
+// cfear_stream_wait_ticket (context stream) / cfear_join / cfear_sync.
+int cfear_odometry_step_batch_dev_submit(cfear_ctx* c, int nprob, const uint8_t* d_polar, const double* d_mot,
+                                         const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
+                                         double* d_poses, double* d_cov36, cfear_reg_stats* d_stats, int32_t* ticket_out) {
+  ENTER_NOJOIN(c);
+  if (!d_polar || !d_kf_slots || !d_cur_slots || !d_poses || !d_cov36 || !d_stats) { g_err = "null argument"; return CFEAR_ERR_ARG; }
+  if (K < 1 || K > c->cfg.max_keyframes) { g_err = "K must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
+  if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  RC(ensure_tickets(c));
+  RC(ensure_pipes(c));
+  const int ticket = c->next_ticket++ % CFEAR_MAX_TICKETS;
+  if (ticket_out) *ticket_out = ticket;
+  const int pi = 1 + c->next_pipe;
+  c->next_pipe = (c->next_pipe + 1) % CFEAR_NPIPES;
+  PipeBufs& B = c->pb[pi];
+  CK(cudaEventRecord(B.in, c->stream));
+  CK(cudaStreamWaitEvent(B.stream, B.in, 0));
+  if (nprob > 0) RC(step_dev(c, B, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats));
+  CK(cudaEventRecord(B.done, B.stream));
+  CK(cudaEventRecord(c->ticket_ev[ticket], B.stream));
+  c->inflight = true; c->last_pipe = pi;
+  return CFEAR_OK;
+}
+
+int cfear_stream_wait_ticket(cfear_ctx* c, int32_t ticket) {
+  ENTER_NOJOIN(c);
+  if (ticket < 0 || ticket >= (int)c->ticket_ev.size()) { g_err = "unknown ticket"; return CFEAR_ERR_ARG; }
+  CK(cudaStreamWaitEvent(c->stream, c->ticket_ev[ticket], 0));
+  return CFEAR_OK;
+}
+
+int cfear_join(cfear_ctx* c) {
+  ENTER(c);
+  return CFEAR_OK;
 }
 
 // Host-buffer path, asynchronous half: enqueues the whole step (H2D in sub-batches on the copy stream, K1 -> K3 -> K5
@@ -692,12 +821,8 @@ int cfear_odometry_step_batch_submit(cfear_ctx* c, int nprob, const uint8_t* pol
   if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
   for (int i = 0; i < nprob * K; ++i) RC(check_slot(c, kf_slots[i]));
   for (int i = 0; i < nprob; ++i) RC(check_slot(c, cur_slots[i]));
-  if ((int)c->ticket_ev.size() == 0) {
-    for (int i = 0; i < CFEAR_MAX_TICKETS; ++i) {
-      cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      c->ticket_ev.push_back(e);
-    }
-  }
+  RC(ensure_tickets(c));
+  c->last_pipe = 0;
   const int ticket = c->next_ticket++ % CFEAR_MAX_TICKETS;
   if (ticket_out) *ticket_out = ticket;
   if (nprob == 0) { CK(cudaEventRecord(c->ticket_ev[ticket], c->stream)); return CFEAR_OK; }
@@ -753,8 +878,8 @@ int cfear_odometry_step_batch_submit(cfear_ctx* c, int nprob, const uint8_t* pol
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->k1_done[ch], c->stream));
-    RC(launch_k3(c, 0, nb, have_mot ? c->d_mot + 3 * (size_t)b0 : nullptr, c->d_curslots + b0, false, b0));
-    RC(launch_k5(c, nb, K + 1, c->d_slots + (size_t)b0 * (K + 1), c->d_poses + (size_t)b0 * (K + 1) * 3,
+    RC(launch_k3(c, c->pb[0], 0, nb, have_mot ? c->d_mot + 3 * (size_t)b0 : nullptr, c->d_curslots + b0, false, b0));
+    RC(launch_k5(c, c->pb[0], nb, K + 1, c->d_slots + (size_t)b0 * (K + 1), c->d_poses + (size_t)b0 * (K + 1) * 3,
                  c->d_cov36 + (size_t)b0 * 36, c->d_stats + b0, nullptr, b0));
   }
   if (timing) CK(cudaEventRecord(c->evset[3], c->stream));
@@ -767,7 +892,7 @@ int cfear_odometry_step_batch_submit(cfear_ctx* c, int nprob, const uint8_t* pol
 }
 
 int cfear_odometry_step_batch_wait(cfear_ctx* c, int32_t ticket) {
-  ENTER(c);
+  ENTER_NOJOIN(c);
   if (ticket < 0 || ticket >= (int)c->ticket_ev.size()) { g_err = "unknown ticket"; return CFEAR_ERR_ARG; }
   CK(cudaEventSynchronize(c->ticket_ev[ticket]));
   return CFEAR_OK;
@@ -808,7 +933,7 @@ int cfear_stage_timing(cfear_ctx* c, int enable, float ms_out[3]) {
 int cfear_last_counts(cfear_ctx* c, int nprob, const int32_t* cur_slots, int32_t* npts_out, int32_t* ncells_out) {
   ENTER(c);
   if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
-  if (npts_out) CK(cudaMemcpyAsync(npts_out, c->d_npts, (size_t)nprob * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (npts_out) CK(cudaMemcpyAsync(npts_out, c->pb[c->last_pipe].d_npts, (size_t)nprob * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (ncells_out) {
     if (!cur_slots) { g_err = "null slots"; return CFEAR_ERR_ARG; }
     std::vector<int32_t> all(c->cfg.max_cellsets);
@@ -846,6 +971,7 @@ int cfear_cfar_filter(cfear_ctx* c, const uint8_t* polar, int nscans, const cfea
   p.min_distance = (double)c->cfg.min_distance; p.max_distance = cp->max_distance;
   p.cs = c->d_cs; p.rowcnt = d_cnt; p.rowoff = d_off; p.cloud = d_out; p.cap = capacity_per_scan; p.pass = 0;
   const size_t smem = (size_t)(R + 1) * 4;
+  CK(cudaFuncSetAttribute(k7_cfar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k7_cfar<<<(int)rows, K7_THREADS, smem, c->stream>>>(p);
   k7_offsets<<<nscans, 512, A * sizeof(int), c->stream>>>(d_cnt, A, d_off, d_n);
   p.pass = 1;
@@ -917,12 +1043,13 @@ static int seq_step_common(cfear_seq* s, const uint8_t* d_polar) {
   cfear_ctx* c = s->ctx;
   const SeqParams& P = s->p;
   const int B = P.nseq;
+  c->last_pipe = 0;
   k6_pre<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
   c->launches++;
   CK(cudaGetLastError());
-  RC(launch_k1(c, d_polar, B));
-  RC(launch_k3(c, 0, B, c->d_mot, c->d_curslots, false));
-  RC(launch_k5(c, B, P.kmax + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, P.nscans_pp));
+  RC(launch_k1(c, c->pb[0], d_polar, B));
+  RC(launch_k3(c, c->pb[0], 0, B, c->d_mot, c->d_curslots, false));
+  RC(launch_k5(c, c->pb[0], B, P.kmax + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, P.nscans_pp));
   k6_post<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
   c->launches++;
   CK(cudaGetLastError());

@@ -198,6 +198,22 @@ int cfear_odometry_step_batch_wait(cfear_ctx* ctx, int32_t ticket);
 int cfear_odometry_step_batch_dev(cfear_ctx* ctx, int nprob, const uint8_t* d_polar, const double* d_mot,
                                   const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
                                   double* d_poses, double* d_cov36, cfear_reg_stats* d_stats);
+/* The same step, overlapped with its neighbours: step i runs on internal stream i mod 2 with its own scratch, so that the
+ * filter / surface-point kernels of step i+1 execute while the registration of step i is in its tail (the radarReader loop
+ * of src/offline_odometry.cpp:103-108 has no dependency from CallbackOffline of frame t+1 on the pose of frame t; for
+ * independent batches neither has the MapPointNormal build).  Ordering contract:
+ *   - inputs must be complete with respect to the context stream (cfear_stream) at the time of the call;
+ *   - every buffer of the step (d_polar .. d_stats) and the cell-set slots it names belong to the step until it is
+ *     complete: cfear_odometry_step_batch_wait(ticket) on the host, cfear_stream_wait_ticket(ticket) on the context
+ *     stream, or cfear_join / cfear_sync / any other entry point (all of which join first);
+ *   - d_cur_slots of a step must not name a slot (keyframe or current) of a step still in flight: rotate two sets.
+ * cfear_odometry_step_batch_dev == this + cfear_join, i.e. fully ordered on the context stream. */
+int cfear_odometry_step_batch_dev_submit(cfear_ctx* ctx, int nprob, const uint8_t* d_polar, const double* d_mot,
+                                         const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
+                                         double* d_poses, double* d_cov36, cfear_reg_stats* d_stats, int32_t* ticket_out);
+/* Makes the context stream wait (on the device; the host does not block) for one step / for every step in flight. */
+int cfear_stream_wait_ticket(cfear_ctx* ctx, int32_t ticket);
+int cfear_join(cfear_ctx* ctx);
 int cfear_sync(cfear_ctx* ctx);
 /* The CUDA stream (cudaStream_t as void*) the context launches on, for event timing by the caller. */
 void* cfear_stream(cfear_ctx* ctx);

@@ -135,3 +135,72 @@ def test_oxford_width_png_through_the_whole_path(orc, tmp_path):
     assert np.hypot(d[0], d[1]) < POS_TOL and abs(d[2]) < ROT_TOL
     assert np.hypot(*(got["poses"][0, K, :2] - tp[K, :2])) < 0.3
     c.close()
+
+
+def test_overlapped_device_steps_equal_stream_ordered_steps(orc):
+    """cfear_odometry_step_batch_dev_submit: consecutive steps on the library's two internal streams (K1 / K3 of step i+1
+    under K5 of step i), rotating two current-slot / result sets -- bit for bit what the stream-ordered call returns,
+    whatever entry point is interleaved; tickets can be waited for from the host or from the context stream."""
+    import torch
+    K, nprob, nsets = 2, 6, 2
+    c = capi.Context(max_batch=nprob, max_cellsets=nprob * (K + nsets), max_keyframes=K, cost="P2D", loss="Huber",
+                     weight_opt=4, regularization=0.1, radius=3.0)
+    b = workload.make_batch(nprob, K, seed0=300, workers=1)
+    kf = np.arange(nprob * K, dtype=np.int32).reshape(nprob, K)
+    for i in range(K):
+        c.scans_to_cells_batch(b["kf_polar"][:, i], None, kf[:, i])
+    curs = [(nprob * (K + j) + np.arange(nprob)).astype(np.int32) for j in range(nsets)]
+    dev = torch.device("cuda", 0)
+    ext = torch.cuda.ExternalStream(c.stream_ptr, device=dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    t_polar, t_mot, t_kf = t(b["polar"]), t(b["mot"]), t(kf)
+    guesses = [b["poses"].copy() for _ in range(3)]
+    guesses[1][:, K, 0] += 0.2; guesses[2][:, K, 2] -= 0.01
+    t_cur = [t(x) for x in curs]
+    t_pose = [torch.zeros(nprob, K + 1, 3, dtype=torch.float64, device=dev) for _ in range(nsets)]
+    t_cov = [torch.zeros(nprob, 36, dtype=torch.float64, device=dev) for _ in range(nsets)]
+    t_st = [torch.zeros(nprob, capi.STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in range(nsets)]
+
+    def args(j):
+        return (nprob, t_polar.data_ptr(), t_mot.data_ptr(), t_kf.data_ptr(), K, t_cur[j].data_ptr(), t_pose[j].data_ptr(),
+                t_cov[j].data_ptr(), t_st[j].data_ptr())
+    # stream-ordered reference results for the three guesses
+    want = []
+    for g in guesses:
+        with torch.cuda.stream(ext):
+            t_pose[0].copy_(t(g), non_blocking=True)
+        torch.cuda.synchronize()
+        c.odometry_step_batch_dev(*args(0))
+        c.sync()
+        want.append((t_pose[0].cpu().numpy().copy(), t_cov[0].cpu().numpy().copy(), t_st[0].cpu().numpy().copy()))
+    assert not np.array_equal(want[0][0], want[1][0])
+    # overlapped: 9 steps cycling through the guesses and the two sets
+    tickets, which, got = [None] * nsets, [None] * nsets, []
+    for s in range(9):
+        j = s % nsets
+        if tickets[j] is not None:
+            if s % 3 == 0:
+                c.odometry_step_batch_wait(tickets[j])            # host wait
+            else:
+                c.stream_wait_ticket(tickets[j])                  # device-side wait of the context stream
+                torch.cuda.current_stream().wait_stream(ext)
+            with torch.cuda.stream(ext):
+                got.append((which[j], t_pose[j].clone(), t_cov[j].clone(), t_st[j].clone()))
+        g = s % 3
+        with torch.cuda.stream(ext):
+            t_pose[j].copy_(t(guesses[g]), non_blocking=True)
+        tickets[j], which[j] = c.odometry_step_batch_dev_submit(*args(j)), g
+        if s == 4:
+            c.kstrongest(b["polar"][:2])                          # any other entry point joins the steps in flight first
+    c.join()
+    with torch.cuda.stream(ext):
+        for j in range(nsets):
+            got.append((which[j], t_pose[j].clone(), t_cov[j].clone(), t_st[j].clone()))
+    c.sync()
+    assert len(got) == 9
+    for g, p, cv, st in got:
+        assert np.array_equal(p.cpu().numpy(), want[g][0]) and np.array_equal(cv.cpu().numpy(), want[g][1])
+        assert np.array_equal(st.cpu().numpy(), want[g][2])
+    npts, ncells = c.last_counts(curs[0])
+    assert (npts > 1000).all() and (ncells > 100).all()
+    c.close()
