@@ -7,7 +7,7 @@ registration against 4 resident keyframe cell sets (P2D, Huber 0.1, regularizati
 Ceres-style LM loop).  One "step" = one pass of that path over the batch.
 
   value      device-timed: polar images already resident in HBM (344 MB per step per GPU > 126 MB L2); consecutive steps
-             are submitted through cfear_odometry_step_batch_dev_submit (two steps in flight on the library's own streams,
+             are submitted through cfear_odometry_step_batch_dev_submit (--inflight steps on the library's own streams,
              each step's K1 -> K3 -> K5 chain intact, results double-buffered) -- `--serial` times the stream-ordered call
   e2e        the same through cfear_odometry_step_batch_submit/_wait with pinned HOST buffers (two steps in flight):
              H2D of the images + D2H of the poses / covariances / stats of every step inside the timed region
@@ -151,6 +151,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lib", default=None, help="experiment builds: path of another libcfear_b200.so (profiles/ab)")
+    ap.add_argument("--batch-cache", default=None, help="npz file caching the generated workload between runs")
+    ap.add_argument("--save-poses", default=None, help="experiment builds: save poses / iteration counts (npz)")
+    ap.add_argument("--ref-poses", default=None, help="experiment builds: compare with the npz another build saved")
+    ap.add_argument("--inflight", type=int, default=4, help="result / slot sets the overlapped steps rotate through")
     ap.add_argument("--serial", action="store_true", help="device-resident arm through the stream-ordered cfear_odometry_step_batch_dev")
     ap.add_argument("--min-seconds", type=float, default=0.25, help="the K-step timed region is repeated until it lasts this long")
     args = ap.parse_args()
@@ -182,11 +187,19 @@ def main():
         return
 
     # ---- inputs (numpy, before CUDA is touched: the generator forks workers) ----
-    batch = workload.make_batch(nprob, K, seed0=rank * nprob)
+    cache = args.batch_cache and f"{args.batch_cache}.{rank}.{nprob}.npz"
+    if cache and os.path.exists(cache):
+        batch = dict(np.load(cache))
+    else:
+        batch = workload.make_batch(nprob, K, seed0=rank * nprob)
+        if cache:
+            np.savez(cache, **batch)
 
     import torch
     import torch.distributed as dist
     from cfear_radarodometry_code_public_b200 import capi
+    if args.lib:
+        capi.LIB_PATH = os.path.abspath(args.lib)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -206,8 +219,9 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    NSETS = 2                      # result / current-slot sets the overlapped steps rotate through
-    ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + NSETS), max_keyframes=K, **workload.CFEAR3)
+    NSETS = max(1, args.inflight)  # result / current-slot sets the overlapped steps rotate through
+    ctx = capi.Context(device=local, max_batch=nprob, max_cellsets=nprob * (K + NSETS), max_keyframes=K, steps_in_flight=NSETS,
+                       **workload.CFEAR3)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
 
     # resident keyframe cell sets, built by the GPU path from the keyframe images (untimed set-up)
@@ -300,7 +314,7 @@ def main():
         assert np.array_equal(t_poses[j].cpu().numpy(), poses_dev), "overlapped steps disagree between result sets"
     # the same kernels timed one at a time (stream-ordered call): what each costs when it has the GPU to itself
     ctx.stage_timing(True)
-    for _ in range(20):
+    for _ in range(100):
         with torch.cuda.stream(ext):
             t_poses[0].copy_(t_poses0, non_blocking=True)
         ctx.odometry_step_batch_dev(nprob, t_polar.data_ptr(), t_mot.data_ptr(), t_kf.data_ptr(), K, t_cur[0].data_ptr(),
@@ -319,22 +333,25 @@ def main():
     names = ["k1_kstrongest", "k3_surface_points", "k5_register"]
     per_launch_ms = [m / max(nst, 1) for m in stage_ms]
     serial_ms = [m / max(nser, 1) for m in stage_ser]
-    dom = int(np.argmax(per_launch_ms))
-    ach = alg[names[dom]] * nprob / (per_launch_ms[dom] * 1e-3) / 1e9 if per_launch_ms[dom] > 0 else 0.0
+    # The roofline is quoted for the dominant kernel running ALONE (stream-ordered steps timed right after the overlapped
+    # region, same inputs, CUDA events on its stream): with several steps in flight a kernel shares the SMs with the
+    # neighbouring steps' kernels and its start-to-end time says how long it was resident, not how fast it runs.
+    dom = int(np.argmax(serial_ms))
+    ach = alg[names[dom]] * nprob / (serial_ms[dom] * 1e-3) / 1e9 if serial_ms[dom] > 0 else 0.0
     b_scan = A * R + 2 * n_pts * 16 + n_cells * 80 + (K * n_kf_cells + n_cells) * 80 + 24
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_scan": alg[names[dom]],
-            "stage_ms_per_step": dict(zip(names, per_launch_ms)),
-            "stage_ms_note": ("CUDA events around each kernel on the stream it is launched on, averaged over the timed region; "
-                              + ("stream-ordered steps" if args.serial else
-                                 "two steps are in flight, so a kernel shares the SMs with the neighbouring step's kernels and the "
-                                 "durations overlap (their sum exceeds ms_per_step)")),
+            "duration_ms": serial_ms[dom],
+            "duration_note": f"{names[dom]} alone: average over {nser} stream-ordered steps run right after the timed region (CUDA events on its stream)",
             "stage_ms_alone": dict(zip(names, serial_ms)),
             "stage_frac_of_hbm_peak_alone": {n: (alg[n] * nprob / (t * 1e-3) / 1e9 / hbm_peak if t > 0 else None)
                                              for n, t in zip(names, serial_ms)},
-            "stage_frac_of_hbm_peak": {n: (alg[n] * nprob / (t * 1e-3) / 1e9 / hbm_peak if t > 0 else None)
-                                       for n, t in zip(names, per_launch_ms)},
+            "stage_ms_in_flight": dict(zip(names, per_launch_ms)),
+            "stage_ms_in_flight_note": ("CUDA events around each kernel on the stream it is launched on, averaged over the timed region; "
+                                        + ("stream-ordered steps" if args.serial else
+                                           "several steps are in flight, so a kernel shares the SMs with the neighbouring steps' kernels and "
+                                           "the durations overlap (their sum exceeds ms_per_step)")),
             "whole_path": {"bytes_per_scan": b_scan, "achieved": b_scan * value / world / 1e9,
                            "frac": b_scan * value / world / 1e9 / hbm_peak}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")        # dram bytes per launch from the committed ncu capture
@@ -417,14 +434,22 @@ def main():
                 and par["inner_iterations_equal"] and par["num_residuals_equal"] and par["npts_equal"] and par["ncells_equal"]):
             raise SystemExit("bench.py: the CUDA path disagrees with the CPU oracle on the bench workload: " + json.dumps(par))
 
+    ab = None
+    if rank == 0 and args.save_poses:
+        np.savez(args.save_poses, poses=poses_dev, outer=stats["outer_iterations"], inner=stats["inner_iterations"])
+    if rank == 0 and args.ref_poses and os.path.exists(args.ref_poses):
+        r = np.load(args.ref_poses)
+        dd = poses_dev[:, K] - r["poses"][:, K]
+        ab = {"dpos": float(np.hypot(dd[:, 0], dd[:, 1]).max()), "drot": float(np.abs(dd[:, 2]).max()),
+              "outer_diff": int((stats["outer_iterations"] != r["outer"]).sum()), "inner_diff": int((stats["inner_iterations"] != r["inner"]).sum())}
     if rank == 0:
         err = poses_dev[:, K] - batch["truth"]
-        config["steps_in_flight"] = 1 if args.serial else 2
-        config["api"] = "cfear_odometry_step_batch_dev" if args.serial else "cfear_odometry_step_batch_dev_submit (two steps in flight)"
+        config["steps_in_flight"] = 1 if args.serial else NSETS
+        config["api"] = "cfear_odometry_step_batch_dev" if args.serial else f"cfear_odometry_step_batch_dev_submit ({NSETS} steps in flight)"
         line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "timed_regions": regions, "steps_timed": total_steps, "ms_per_step": ms / total_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": int(launches), "clocks": clocks, **({"ab_vs_ref": ab} if ab else {}),
                 "workload_stats": {"n_pts_mean": n_pts, "n_cells_mean": n_cells, "kf_cells_mean": n_kf_cells,
                                    "outer_iterations_mean": float(stats["outer_iterations"].mean()),
                                    "inner_iterations_mean": float(stats["inner_iterations"].mean()),

@@ -29,7 +29,7 @@ class Config(C.Structure):
                 ("cov_scale", C.c_double), ("regularization", C.c_double), ("reg_radius", C.c_double),
                 ("max_outer", C.c_int32), ("min_outer", C.c_int32), ("max_inner", C.c_int32), ("gn_iters", C.c_int32),
                 ("max_keyframes", C.c_int32), ("max_cellsets", C.c_int32), ("max_cells", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("steps_in_flight", C.c_int32)]
 
 
 class RegStats(C.Structure):

@@ -114,7 +114,7 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
-constexpr int CFEAR_NPIPES = 2;        // device-resident steps that may overlap (cfear_odometry_step_batch_dev_submit)
+constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 4)
 
 // Everything one step writes between K1 and K5.  Set 0 aliases the context's own buffers (every stream-ordered entry
 // point uses it on the context stream); sets 1..CFEAR_NPIPES have their own streams so that consecutive device-resident
@@ -139,7 +139,7 @@ struct cfear_ctx {
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
-  int pts_in_smem = 0; size_t k3_smem = 0; int k5_smem = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0;
   int g_hist_cap = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -154,7 +154,8 @@ struct cfear_ctx {
   std::vector<double2> h_cs;
   PipeBufs pb[CFEAR_NPIPES + 1];    // [0] aliases the buffers above on the context stream; [1..] the overlapped steps' sets
   bool pipes_ready = false, inflight = false;
-  int next_pipe = 0, last_pipe = 0;
+  int npipes = 4, next_pipe = 0, last_pipe = 0;
+  int pipe_user = 0;                // who enqueued on the internal streams last: 1 = overlapped batch steps, 2 = sequence replay
 
   template <typename T> int alloc(T** p, size_t count) {
     void* q = nullptr;
@@ -185,7 +186,7 @@ void cfear_default_config(cfear_config* cfg) {
   cfg->cost = CFEAR_COST_P2L; cfg->loss = CFEAR_LOSS_HUBER; cfg->weight_opt = CFEAR_WEIGHT_UNIFORM;
   cfg->solver_mode = CFEAR_SOLVER_CERES_LM; cfg->loss_limit = 0.1; cfg->cov_scale = 1.0; cfg->regularization = 1.0;
   cfg->reg_radius = 2.0; cfg->max_outer = 8; cfg->min_outer = 3; cfg->max_inner = 20; cfg->gn_iters = 10;
-  cfg->max_keyframes = 4; cfg->max_cellsets = 8; cfg->max_cells = 0;
+  cfg->max_keyframes = 4; cfg->max_cellsets = 8; cfg->max_cells = 0; cfg->steps_in_flight = 0;
 }
 
 void cfear_destroy(cfear_ctx* c) {
@@ -228,6 +229,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   cfear_ctx* c = new (std::nothrow) cfear_ctx();
   if (!c) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
   c->cfg = *cfg;
+  c->npipes = cfg->steps_in_flight > 0 ? std::min(cfg->steps_in_flight, CFEAR_NPIPES) : 4;
   // from here on a CUDA failure must not leak the half-built context
 #define CKC(expr)                                                                                 \
   do {                                                                                            \
@@ -251,10 +253,12 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   // shared-memory plan of K3
   int max_optin = 0;
   CKC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-  const size_t hist_bytes = (size_t)(K3_HIST_CAP + 1) * sizeof(int);
-  const size_t full = (size_t)c->cap_pts * 32 + hist_bytes;
+  // 16-bit histogram entries, two per word (k3_surface.cuh, Hist16); the same area first holds the A row counts as ints
+  const size_t hist_bytes = std::max((size_t)((K3_HIST_CAP + 2) / 2) * 4, (size_t)(A + 1) * sizeof(int));
+  const size_t full = (size_t)c->cap_pts * 16 + hist_bytes;
   c->pts_in_smem = (full + 2048 <= (size_t)max_optin) ? 1 : 0;
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
+  c->k4_smem = hist_bytes;
   CKC(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   // (the CA-CFAR kernel's shared-memory attribute is set by cfear_cfar_filter, which is the only place that needs it)
@@ -268,7 +272,8 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   AL(c->d_rowcloud, rows * k); AL(c->d_rowpeaks, rows * k);
   AL(c->d_cloud, (size_t)B * c->cap_pts); AL(c->d_peaks, (size_t)B * c->cap_pts);
   AL(c->d_npts, B); AL(c->d_npeaks, B); AL(c->d_status, B);
-  if (!c->pts_in_smem) { AL(c->d_bufA, (size_t)B * c->cap_pts); AL(c->d_bufB, (size_t)B * c->cap_pts); }
+  if (!c->pts_in_smem) AL(c->d_bufA, (size_t)B * c->cap_pts);
+  AL(c->d_bufB, (size_t)B * c->cap_pts);
   AL(c->d_ghist, (size_t)B * (c->g_hist_cap + 1));
   AL(c->d_celltmp, (size_t)B * c->cap_pts * 4);
   AL(c->d_mot, (size_t)B * 3);
@@ -318,7 +323,7 @@ int cfear_update_config(cfear_ctx* c, const cfear_config* cfg) {
   const cfear_config& o = c->cfg;
   if (cfg->device != o.device || cfg->max_batch != o.max_batch || cfg->azimuths != o.azimuths ||
       cfg->range_bins != o.range_bins || cfg->k_strongest != o.k_strongest || cfg->max_keyframes != o.max_keyframes ||
-      cfg->max_cellsets != o.max_cellsets || cfg->max_cells != o.max_cells) {
+      cfg->max_cellsets != o.max_cellsets || cfg->max_cells != o.max_cells || cfg->steps_in_flight != o.steps_in_flight) {
     g_err = "cfear_update_config: structural fields (device, max_batch, azimuths, range_bins, k_strongest, max_*) are fixed at create";
     return CFEAR_ERR_ARG;
   }
@@ -336,7 +341,7 @@ int cfear_sync(cfear_ctx* c) {
   if (!c) return CFEAR_ERR_ARG;
   CK(cudaSetDevice(c->cfg.device));
   if (c->inflight) {
-    for (int i = 1; i <= CFEAR_NPIPES; ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
+    for (int i = 1; i <= std::max(c->npipes, 2); ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
     c->inflight = false;
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -420,7 +425,8 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.rowcloud += o * p.A * p.k; p.rowcnt += o * p.A;
     if (p.cloud) p.cloud += o * p.cap_pts;
     p.npts += o; p.status += o; p.cell_tmp += o * p.cap_pts * 4;
-    if (p.g_bufA) { p.g_bufA += o * p.cap_pts; p.g_bufB += o * p.cap_pts; }
+    if (p.g_bufA) p.g_bufA += o * p.cap_pts;
+    p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
   k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, B.stream>>>(p);
@@ -476,7 +482,7 @@ static int check_slot(cfear_ctx* c, int slot) {
 // entry point works on the context stream and first makes it wait, on the device, for the steps still in flight.
 static int join_pipes(cfear_ctx* c) {
   if (!c->inflight) return CFEAR_OK;
-  for (int i = 1; i <= CFEAR_NPIPES; ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
+  for (int i = 1; i <= std::max(c->npipes, 2); ++i) CK(cudaStreamWaitEvent(c->stream, c->pb[i].done, 0));
   c->inflight = false;
   return CFEAR_OK;
 }
@@ -618,7 +624,7 @@ int cfear_cells_upload(cfear_ctx* c, int slot, const cfear_cell* cells, int n) {
   const int32_t s32 = slot;
   CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = 8.0f;
-  k4_build_index<<<1, K3_THREADS, (K3_HIST_CAP + 1) * sizeof(int), c->stream>>>(p);
+  k4_build_index<<<1, K3_THREADS, c->k4_smem, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
@@ -742,12 +748,19 @@ static int ensure_tickets(cfear_ctx* c) {
   return CFEAR_OK;
 }
 
+// The overlapped batch steps and the sequence replay use the internal streams / scratch sets differently: when the user
+// changes, what is in flight is joined into the context stream first (the next step then orders itself after it).
+static int set_pipe_user(cfear_ctx* c, int user) {
+  if (c->pipe_user != user) { RC(join_pipes(c)); c->pipe_user = user; }
+  return CFEAR_OK;
+}
+
 // Streams, events and the extra buffer sets of the overlapped device-resident steps, created on first use.
 static int ensure_pipes(cfear_ctx* c) {
   if (c->pipes_ready) return CFEAR_OK;
   const int A = c->cfg.azimuths, k = c->cfg.k_strongest, B = c->cfg.max_batch;
   const size_t rows = (size_t)B * A;
-  for (int i = 1; i <= CFEAR_NPIPES; ++i) {
+  for (int i = 1; i <= std::max(c->npipes, 2); ++i) {       // the sequence replay always uses two
     PipeBufs& P = c->pb[i];
     CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&P.in, cudaEventDisableTiming));
@@ -756,7 +769,8 @@ static int ensure_pipes(cfear_ctx* c) {
 #define ALP(p, n) do { int rc__ = c->alloc(&(p), (size_t)(n)); if (rc__ != CFEAR_OK) return rc__; } while (0)
     ALP(P.d_kidx, rows * k); ALP(P.d_kcnt, rows); ALP(P.d_rowcnt, rows); ALP(P.d_rowcloud, rows * k);
     ALP(P.d_npts, B); ALP(P.d_status, B);
-    if (!c->pts_in_smem) { ALP(P.d_bufA, (size_t)B * c->cap_pts); ALP(P.d_bufB, (size_t)B * c->cap_pts); }
+    if (!c->pts_in_smem) ALP(P.d_bufA, (size_t)B * c->cap_pts);
+    ALP(P.d_bufB, (size_t)B * c->cap_pts);
     ALP(P.d_ghist, (size_t)B * (c->g_hist_cap + 1));
     ALP(P.d_celltmp, (size_t)B * c->cap_pts * 4);
     ALP(P.d_slots, (size_t)B * (c->cfg.max_keyframes + 1));
@@ -781,10 +795,11 @@ int cfear_odometry_step_batch_dev_submit(cfear_ctx* c, int nprob, const uint8_t*
   if (nprob < 0 || nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
   RC(ensure_tickets(c));
   RC(ensure_pipes(c));
+  RC(set_pipe_user(c, 1));
   const int ticket = c->next_ticket++ % CFEAR_MAX_TICKETS;
   if (ticket_out) *ticket_out = ticket;
   const int pi = 1 + c->next_pipe;
-  c->next_pipe = (c->next_pipe + 1) % CFEAR_NPIPES;
+  c->next_pipe = (c->next_pipe + 1) % c->npipes;
   PipeBufs& B = c->pb[pi];
   CK(cudaEventRecord(B.in, c->stream));
   CK(cudaStreamWaitEvent(B.stream, B.in, 0));
@@ -997,14 +1012,16 @@ struct cfear_seq {
   cfear_ctx* ctx;
   SeqParams p;
   int slot_base;
+  int parity = 0;                                   // K1 output set of the next step
+  cudaEvent_t k1_done[2] = {nullptr, nullptr}, k3_done[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
 };
 
 void cfear_seq_destroy(cfear_seq* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->cfg.device);
-  cudaStreamSynchronize(s->ctx->stream);
+  cfear_sync(s->ctx);
   for (void* q : s->allocs) cudaFree(q);
+  for (int i = 0; i < 2; ++i) { if (s->k1_done[i]) cudaEventDestroy(s->k1_done[i]); if (s->k3_done[i]) cudaEventDestroy(s->k3_done[i]); }
   delete s;
 }
 
@@ -1029,6 +1046,10 @@ int cfear_seq_create(cfear_ctx* c, int nseq, int slot_base, int max_steps, const
             al((void**)&P.traj_stats, sizeof(cfear_reg_stats) * (size_t)nseq * max_steps);
   if (!ok) { g_err = "cudaMalloc failed"; cfear_seq_destroy(s); return CFEAR_ERR_CUDA; }
   P.mot = c->d_mot; P.cur_slots = c->d_curslots; P.slots = c->d_slots; P.poses = c->d_poses; P.stats = c->d_stats;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&s->k1_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->k3_done[i], cudaEventDisableTiming) != cudaSuccess) { g_err = "cudaEventCreate failed"; cfear_seq_destroy(s); return CFEAR_ERR_CUDA; }
+  }
   k6_init<<<(nseq + 127) / 128, 128, 0, c->stream>>>(P, slot_base);
   c->launches++;
   CK(cudaGetLastError());
@@ -1039,37 +1060,61 @@ int cfear_seq_create(cfear_ctx* c, int nseq, int slot_base, int max_steps, const
   return CFEAR_OK;
 }
 
-static int seq_step_common(cfear_seq* s, const uint8_t* d_polar) {
+// One time step of every sequence.  The filter of scan t+1 needs nothing from scan t (src/offline_odometry.cpp:103: the
+// CallbackOffline of the next frame), only Compensate and the registration do (previous motion, keyframe window), so K1
+// runs on its own stream, one step ahead, into alternating output sets, and hides under the registration of the previous
+// scan:   filter stream:  [H2D] K1(t) | [H2D] K1(t+1) ...        main stream:  k6_pre(t) K3(t) K5(t) k6_post(t) | ...
+static int seq_step_common(cfear_seq* s, const uint8_t* polar, bool host) {
   cfear_ctx* c = s->ctx;
   const SeqParams& P = s->p;
   const int B = P.nseq;
-  c->last_pipe = 0;
-  k6_pre<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
+  RC(ensure_pipes(c));
+  RC(set_pipe_user(c, 2));
+  PipeBufs& F = c->pb[1];                              // filter stream
+  PipeBufs& M = c->pb[2];                              // everything that depends on the previous scan
+  const int par = s->parity; s->parity ^= 1;
+  PipeBufs W = c->pb[1 + par];                         // K1 -> K3 -> K5 scratch of this step
+  CK(cudaEventRecord(F.in, c->stream));                // inputs are ordered after the context stream's work so far
+  CK(cudaStreamWaitEvent(F.stream, F.in, 0));
+  CK(cudaStreamWaitEvent(M.stream, F.in, 0));
+  CK(cudaStreamWaitEvent(F.stream, s->k3_done[par], 0));   // this output set was last read by K3 two steps ago
+  const uint8_t* d_polar = polar;
+  if (host) {
+    c->polar_dirty = true;
+    CK(cudaMemcpyAsync(c->d_polar, polar, (size_t)B * c->cfg.azimuths * c->cfg.range_bins, cudaMemcpyHostToDevice, F.stream));
+    d_polar = c->d_polar;
+  }
+  c->last_pipe = 1 + par;
+  W.stream = F.stream;
+  RC(launch_k1(c, W, d_polar, B));
+  CK(cudaEventRecord(s->k1_done[par], F.stream));
+  k6_pre<<<(B + 127) / 128, 128, 0, M.stream>>>(P);
   c->launches++;
   CK(cudaGetLastError());
-  RC(launch_k1(c, c->pb[0], d_polar, B));
-  RC(launch_k3(c, c->pb[0], 0, B, c->d_mot, c->d_curslots, false));
-  RC(launch_k5(c, c->pb[0], B, P.kmax + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, P.nscans_pp));
-  k6_post<<<(B + 127) / 128, 128, 0, c->stream>>>(P);
+  CK(cudaStreamWaitEvent(M.stream, s->k1_done[par], 0));
+  W.stream = M.stream;
+  RC(launch_k3(c, W, 0, B, c->d_mot, c->d_curslots, false));
+  CK(cudaEventRecord(s->k3_done[par], M.stream));
+  RC(launch_k5(c, W, B, P.kmax + 1, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, nullptr, 0, P.nscans_pp));
+  k6_post<<<(B + 127) / 128, 128, 0, M.stream>>>(P);
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(F.done, F.stream));
+  CK(cudaEventRecord(M.done, M.stream));
+  c->inflight = true;
   return CFEAR_OK;
 }
 
 int cfear_seq_step_dev(cfear_seq* s, const uint8_t* d_polar) {
   if (!s || !d_polar) { g_err = "null argument"; return CFEAR_ERR_ARG; }
-  ENTER(s->ctx);
-  return seq_step_common(s, d_polar);
+  ENTER_NOJOIN(s->ctx);
+  return seq_step_common(s, d_polar, false);
 }
 
 int cfear_seq_step(cfear_seq* s, const uint8_t* polar) {
   if (!s || !polar) { g_err = "null argument"; return CFEAR_ERR_ARG; }
-  cfear_ctx* c = s->ctx;
-  ENTER(c);
-  const size_t bytes = (size_t)s->p.nseq * c->cfg.azimuths * c->cfg.range_bins;
-  c->polar_dirty = true;
-  CK(cudaMemcpyAsync(c->d_polar, polar, bytes, cudaMemcpyHostToDevice, c->stream));   // stream-ordered: the previous step's K1 is done
-  return seq_step_common(s, c->d_polar);
+  ENTER_NOJOIN(s->ctx);
+  return seq_step_common(s, polar, true);
 }
 
 int cfear_seq_read(cfear_seq* s, int step_from, int nsteps, double* poses_out, int32_t* keyframe_out, cfear_reg_stats* stats_out) {

@@ -27,7 +27,12 @@
 namespace cfear {
 
 #ifndef CFEAR_K3_THREADS
-#define CFEAR_K3_THREADS 768   // 24 warps, 80 registers; 512: 0.142 ms, 768: 0.129, 1024: 0.135
+#define CFEAR_K3_THREADS 512   // 16 warps, 64 registers: two CTAs per SM (109 KB of shared memory each), 256 scans in one wave.  Alone:
+                               // 384 x 2: 0.112 ms / 256 scans, 512 x 2: 0.105, 768 x 1: 0.123, 256 x 2: 0.129; with four steps in flight
+                               // the whole step takes 0.379 / 0.373 / 0.398 ms (profiles/r02e_inflight_k3_ab.txt)
+#endif
+#ifndef CFEAR_K3_MINBLOCKS
+#define CFEAR_K3_MINBLOCKS 2
 #endif
 constexpr int K3_THREADS = CFEAR_K3_THREADS;
 #ifndef CFEAR_K3_LPC
@@ -117,10 +122,40 @@ __device__ __forceinline__ float block_min_f(float v, float* s_red) {
 }
 __device__ __forceinline__ float block_max_f(float v, float* s_red) { return -block_min_f(-v, s_red); }
 
+// Histogram / prefix-sum table with 16-bit entries (counts and offsets are bounded by the points of one scan, <= 65535),
+// two per 32-bit word so that shared-memory atomics can update them: half the footprint of an int table.
+struct Hist16 {
+  uint32_t* w;
+  __device__ __forceinline__ int get(int v) const { return reinterpret_cast<const uint16_t*>(w)[v]; }
+  __device__ __forceinline__ void set(int v, int x) const { reinterpret_cast<uint16_t*>(w)[v] = (uint16_t)x; }
+  // += 1, returns the previous value
+  __device__ __forceinline__ int inc(int v) const {
+    const int sh = (v & 1) << 4;
+    return (int)((atomicAdd(&w[v >> 1], 1u << sh) >> sh) & 0xffffu);
+  }
+  // entries [0, n) <- 0 (whole words: entry n, if it shares the last word, is cleared too)
+  __device__ __forceinline__ void zero(int n) const {
+    for (int i = threadIdx.x; i < (n + 1) >> 1; i += blockDim.x) w[i] = 0u;
+  }
+  // in-place exclusive scan of entries [0, n); returns the total.  Whole block, contains __syncthreads().
+  __device__ inline int excl_scan(int n, int* s_warp) const {
+    const int T = blockDim.x;
+    const int chunk = (((n + T - 1) / T) + 1) & ~1;                 // even: no two threads share a word
+    const int lo = min((int)threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += get(i);
+    int total;
+    int base = block_excl_scan(s, s_warp, &total);
+    for (int i = lo; i < hi; ++i) { const int t = get(i); set(i, base); base += t; }
+    __syncthreads();
+    return total;
+  }
+};
+
 // Build the bucket grid over n fp32 means (fm in shared or global memory) into slot arrays.
 // hist: >= hist_cap+1 ints of scratch.  Whole block participates.
 __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float2* fm, int n, float nn_cell,
-                                     int* hist, int hist_cap, int* s_warp, float* s_red) {
+                                     Hist16 hist, int hist_cap, int* s_warp, float* s_red) {
   const int tid = threadIdx.x, T = blockDim.x;
   float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
   for (int i = tid; i < n; i += T) {
@@ -139,25 +174,25 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
   }
   const float inv = 1.0f / g;
   const int nb = nx * ny;
-  for (int b = tid; b <= nb; b += T) hist[b] = 0;
+  hist.zero(nb + 1);
   __syncthreads();
   for (int i = tid; i < n; i += T) {
     const float2 p = fm[i];
     int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
     bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
-    atomicAdd(&hist[bx + by * nx], 1);
+    hist.inc(bx + by * nx);
   }
   __syncthreads();
-  block_array_excl_scan(hist, nb + 1, s_warp);      // hist[b] = start of bucket b, hist[nb] = n
+  hist.excl_scan(nb + 1, s_warp);                   // hist[b] = start of bucket b, hist[nb] = n
   uint16_t* gstart = pool.gstart + (size_t)slot * pool.grid_stride;
-  for (int b = tid; b <= nb; b += T) gstart[b] = (uint16_t)hist[b];
+  for (int b = tid; b <= nb; b += T) gstart[b] = (uint16_t)hist.get(b);
   __syncthreads();
   float4* gpt = pool.gpt + (size_t)slot * pool.max_cells;
   for (int i = tid; i < n; i += T) {
     const float2 p = fm[i];
     int bx = (int)floorf((p.x - mnx) * inv), by = (int)floorf((p.y - mny) * inv);
     bx = min(max(bx, 0), nx - 1); by = min(max(by, 0), ny - 1);
-    const int pos = atomicAdd(&hist[bx + by * nx], 1);
+    const int pos = hist.inc(bx + by * nx);
     // .w: the cell's normal as two fp16 -- lets the registration's 30 degree normal gate decide from shared memory in
     // all but the borderline cases (k5_register.cuh, normal_gate)
     const double2 nrm = pool.normal[(size_t)slot * pool.max_cells + i];
@@ -178,7 +213,7 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
 #define K3P(i)
 #endif
 
-__global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Params p) {
+__global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_points(const K3Params p) {
 #ifdef CFEAR_K3_PROFILE
   long long k3t[16];
 #endif
@@ -194,14 +229,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   const int slot = p.slots[scan];
   const int cap = p.cap_pts;
 
-  float4* bufA; float4* bufB; int* s_hist;
+  // bufA (the points, read over and over by the neighbourhood pass) lives in shared memory when a scan's cloud fits;
+  // bufB (scatter target of the voxel sort, then the centroid / cell-mean lists: touched a few times per element) is
+  // global scratch that stays in L2.  With the 16-bit histogram that is 109 KB per CTA: two CTAs per SM.
+  float4* bufA; float4* bufB = p.g_bufB + (size_t)scan * cap; int* s_hist;
   if (p.pts_in_smem) {
     bufA = reinterpret_cast<float4*>(dyn_smem);
-    bufB = bufA + cap;
-    s_hist = reinterpret_cast<int*>(bufB + cap);
+    s_hist = reinterpret_cast<int*>(bufA + cap);
   } else {
     bufA = p.g_bufA + (size_t)scan * cap;
-    bufB = p.g_bufB + (size_t)scan * cap;
     s_hist = reinterpret_cast<int*>(dyn_smem);
   }
 
@@ -305,31 +341,31 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   const int minby = (int)floorf(mny * inv), maxby = (int)floorf(mxy * inv);
   const int divx = maxbx - minbx + 1, divy = maxby - minby + 1;
   const long long nbins_ll = (long long)divx * divy;
-  int* hist = s_hist;
+  Hist16 hist; hist.w = reinterpret_cast<uint32_t*>(s_hist);
   if (nbins_ll + 1 > K3_HIST_CAP) {
     if (nbins_ll + 1 > p.g_hist_cap) {
       if (tid == 0) { p.status[scan] = 1; p.pool.ncells[slot] = 0; }
       return;
     }
-    hist = p.g_hist + (size_t)scan * (p.g_hist_cap + 1);
+    hist.w = reinterpret_cast<uint32_t*>(p.g_hist + (size_t)scan * (p.g_hist_cap + 1));
   }
   const int nbins = (int)nbins_ll;
-  for (int b = tid; b <= nbins; b += T) hist[b] = 0;
+  hist.zero(nbins + 1);
   __syncthreads();
   const float fminbx = (float)minbx, fminby = (float)minby;
   for (int i = tid; i < n; i += T) {
     const float4 q = bufA[i];
     const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
-    atomicAdd(&hist[i0 + i1 * divx], 1);
+    hist.inc(i0 + i1 * divx);
   }
   __syncthreads();
   K3P(3)
-  block_array_excl_scan(hist, nbins + 1, s_warp);          // hist[v] = start of voxel v
+  hist.excl_scan(nbins + 1, s_warp);                       // hist[v] = start of voxel v
   K3P(4)
   for (int i = tid; i < n; i += T) {
     float4 q = bufA[i];
     const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
-    const int pos = atomicAdd(&hist[i0 + i1 * divx], 1);   // afterwards hist[v] = end of voxel v
+    const int pos = hist.inc(i0 + i1 * divx);              // afterwards hist[v] = end of voxel v
     q.z = __int_as_float(i);                               // z is identically 0 on this path: carry the input index
     bufB[pos] = q;
   }
@@ -341,7 +377,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     const float4 q = bufB[a];
     const int i0 = (int)(floorf(q.x * inv) - fminbx), i1 = (int)(floorf(q.y * inv) - fminby);
     const int v = i0 + i1 * divx;
-    const int s = v ? hist[v - 1] : 0, e = hist[v];
+    const int s = v ? hist.get(v - 1) : 0, e = hist.get(v);
     const int me = __float_as_int(q.z);
     int rank = 0;
     for (int b = s; b < e; ++b) rank += (__float_as_int(bufB[b].z) < me);
@@ -358,11 +394,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     const int chunk = (nbins + T - 1) / T;
     const int lo = min(tid * chunk, nbins), hi = min(lo + chunk, nbins);
     int nonempty = 0;
-    for (int v = lo; v < hi; ++v) nonempty += (hist[v] > (v ? hist[v - 1] : 0));
+    for (int v = lo; v < hi; ++v) nonempty += (hist.get(v) > (v ? hist.get(v - 1) : 0));
     int total;
     int base = block_excl_scan(nonempty, s_warp, &total);
     for (int v = lo; v < hi; ++v)
-      if (hist[v] > (v ? hist[v - 1] : 0)) vlist[base++] = v;
+      if (hist.get(v) > (v ? hist.get(v - 1) : 0)) vlist[base++] = v;
     if (tid == 0) s_misc[0] = total;
     __syncthreads();
   }
@@ -370,7 +406,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   const int nvox = s_misc[0];
   for (int c = tid; c < nvox; c += T) {
     const int v = vlist[c];
-    const int s = v ? hist[v - 1] : 0, e = hist[v];
+    const int s = v ? hist.get(v - 1) : 0, e = hist.get(v);
     float sx = 0.f, sy = 0.f;
     for (int a = s; a < e; ++a) { sx += pts[a].x; sy += pts[a].y; }
     const float cnt = (float)(e - s);
@@ -410,7 +446,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
     double S0 = 0.0, S1x = 0.0, S1y = 0.0, Sxx = 0.0, Sxy = 0.0, Syy = 0.0;
     for (int by = by0; by <= by1; ++by) {
       const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
-      const int s = b_lo ? hist[b_lo - 1] : 0, e = hist[b_hi];
+      const int s = b_lo ? hist.get(b_lo - 1) : 0, e = hist.get(b_hi);
       for (int a = s + sl; a < e; a += LPC) {
         const float4 pt = pts[a];
         const float dx = q.x - pt.x, dy = q.y - pt.y;
@@ -484,7 +520,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
   __syncthreads();
 
   // ---- NN index over the fp32 means --------------------------------------------------------------
-  build_nn_grid(p.pool, slot, cxy, ncells, p.nn_cell, s_hist, min(K3_HIST_CAP, p.pool.grid_cap) - 1, s_warp, s_red);
+  Hist16 ghist; ghist.w = reinterpret_cast<uint32_t*>(s_hist);
+  build_nn_grid(p.pool, slot, cxy, ncells, p.nn_cell, ghist, min(K3_HIST_CAP, p.pool.grid_cap) - 1, s_warp, s_red);
 #ifdef CFEAR_K3_PROFILE
   K3P(11)
   if (tid == 0 && (scan & 63) == 5)
@@ -497,13 +534,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_surface_points(const K3Param
 // NN index for an uploaded cell set (cfear_cells_upload): one CTA per slot.
 struct K4Params { CellPool pool; const int32_t* slots; float nn_cell; };
 
-__global__ void __launch_bounds__(K3_THREADS, 1) k4_build_index(const K4Params p) {
+__global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k4_build_index(const K4Params p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ float s_red[32];
   const int slot = p.slots[blockIdx.x];
   const int n = p.pool.ncells[slot];
-  int* s_hist = reinterpret_cast<int*>(dyn_smem);
+  Hist16 s_hist; s_hist.w = reinterpret_cast<uint32_t*>(dyn_smem);
   float2* fm = p.pool.fm_scratch + (size_t)slot * p.pool.max_cells;
   const double2* mean = p.pool.mean + (size_t)slot * p.pool.max_cells;
   for (int i = threadIdx.x; i < n; i += blockDim.x) fm[i] = make_float2((float)mean[i].x, (float)mean[i].y);

@@ -352,6 +352,24 @@ __device__ __forceinline__ bool chol3_solve(const double A[6], const double b[3]
   return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
 }
 
+// The same solve by the adjugate (explicit FMAs): every cofactor is independent, so the dependent chain is
+// products -> determinant -> one reciprocal -> scale, a third of the Cholesky chain (three reciprocal square roots in
+// sequence).  Positive definiteness is checked on the leading principal minors (the Cholesky pivots' signs).  Used in the
+// LM loop, where the damped, Jacobi-scaled matrix is well conditioned; CFEAR_K5_CHOL restores the Cholesky solve there.
+__device__ __forceinline__ bool adj3_solve(const double A[6], const double b[3], double y[3]) {
+  const double a00 = A[0], a01 = A[1], a02 = A[2], a11 = A[3], a12 = A[4], a22 = A[5];
+  const double c00 = fma(a11, a22, -(a12 * a12)), c01 = fma(a02, a12, -(a01 * a22)), c02 = fma(a01, a12, -(a02 * a11));
+  const double c11 = fma(a00, a22, -(a02 * a02)), c12 = fma(a01, a02, -(a00 * a12)), c22 = fma(a00, a11, -(a01 * a01));
+  const double det = fma(a00, c00, fma(a01, c01, a02 * c02));
+  if (!(a00 > 0.0) || !(c22 > 0.0) || !(det > 0.0) || !isfinite(det)) return false;
+  const double inv = rcp_normal(det);
+  const double n0 = fma(c00, b[0], fma(c01, b[1], c02 * b[2]));
+  const double n1 = fma(c01, b[0], fma(c11, b[1], c12 * b[2]));
+  const double n2 = fma(c02, b[0], fma(c12, b[1], c22 * b[2]));
+  y[0] = n0 * inv; y[1] = n1 * inv; y[2] = n2 * inv;
+  return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
+}
+
 struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usable; };
 
 // Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc); executed by
@@ -411,7 +429,11 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
     const double A[6] = {Hs[0] + diag[0] * inv_radius, Hs[1], Hs[2], Hs[3] + diag[1] * inv_radius, Hs[4], Hs[5] + diag[2] * inv_radius};
     double y[3];
     const double nb[3] = {-gs[0], -gs[1], -gs[2]};
+#ifdef CFEAR_K5_CHOL
     const bool ok = chol3_solve(A, nb, y);
+#else
+    const bool ok = adj3_solve(A, nb, y);
+#endif
     reuse_diagonal = true;
     double model_change = 0.0;
     if (ok) {
@@ -432,6 +454,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
     invalid_in_a_row = 0;
     const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
+    const double inv_model_change = rcp_normal(model_change);       // model_change > 0; off the chain that follows the evaluation
     EvalOut evc;
     request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
     const double cand_cost = evc.cost;
@@ -442,7 +465,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
     }
     const double cost_change = x_cost - cand_cost;
     if (fabs(cost_change) <= kFunctionTol * x_cost) return;
-    const double rel = cost_change * rcp_normal(model_change);      // model_change > 0
+    const double rel = cost_change * inv_model_change;
     sum.n_iterations++; sum.last_rel = rel;
     if (rel > kMinRelDecrease) {
       x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
@@ -619,10 +642,25 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
     const int nt = min(tile, npairs - t0);
     PROF_T(tp0);
     // ---- phase 1 ----
+    // pair t = i * n_src + j, advanced by T per round: (i, j) are carried along (no division) and the relative transform
+    // is recomputed only when the keyframe changes
+#ifndef CFEAR_K5_P1DIV
+    int pi = (t0 + tid) / n_src, pj = (t0 + tid) - pi * n_src;
+    const int di = T / n_src, dj = T - di * n_src;
+    int ri = -1;
+    RelT R;
+#endif
     for (int u = tid; u < nt; u += T) {
       PROF_T(tq0);
+#ifdef CFEAR_K5_P1DIV
       const int t = t0 + u, i = t / n_src, j = t - i * n_src;
       const RelT R = rel_transform(C, i);
+#else
+      const int i = pi, j = pj;
+      pi += di; pj += dj;
+      if (pj >= n_src) { pj -= n_src; ++pi; }
+      if (i != ri) { R = rel_transform(C, i); ri = i; }
+#endif
       const double2 mu = C.src_mean[j];
       const double2 nsrc = C.src_normal[j];
       const double qx = R.rc * mu.x - R.rs * mu.y + R.tx, qy = R.rs * mu.x + R.rc * mu.y + R.ty;   // :240

@@ -83,7 +83,7 @@ typedef struct cfear_config {
   int32_t max_keyframes;     /* K max = submap_scan_size */
   int32_t max_cellsets;      /* number of device-resident cell-set slots */
   int32_t max_cells;         /* capacity of one cell set; 0 -> azimuths*k_strongest */
-  int32_t reserved;
+  int32_t steps_in_flight;   /* cfear_odometry_step_batch_dev_submit: internal streams / scratch sets to rotate through (0 -> 4, max 8) */
 } cfear_config;
 
 /* pcl::PointXYZI as written by getPeaksFilteredPointCloud (radar_filters.cpp:328-333) */
@@ -198,7 +198,8 @@ int cfear_odometry_step_batch_wait(cfear_ctx* ctx, int32_t ticket);
 int cfear_odometry_step_batch_dev(cfear_ctx* ctx, int nprob, const uint8_t* d_polar, const double* d_mot,
                                   const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
                                   double* d_poses, double* d_cov36, cfear_reg_stats* d_stats);
-/* The same step, overlapped with its neighbours: step i runs on internal stream i mod 2 with its own scratch, so that the
+/* The same step, overlapped with its neighbours: step i runs on internal stream i mod cfear_config.steps_in_flight with its
+ * own scratch, so that the
  * filter / surface-point kernels of step i+1 execute while the registration of step i is in its tail (the radarReader loop
  * of src/offline_odometry.cpp:103-108 has no dependency from CallbackOffline of frame t+1 on the pose of frame t; for
  * independent batches neither has the MapPointNormal build).  Ordering contract:
@@ -206,7 +207,8 @@ int cfear_odometry_step_batch_dev(cfear_ctx* ctx, int nprob, const uint8_t* d_po
  *   - every buffer of the step (d_polar .. d_stats) and the cell-set slots it names belong to the step until it is
  *     complete: cfear_odometry_step_batch_wait(ticket) on the host, cfear_stream_wait_ticket(ticket) on the context
  *     stream, or cfear_join / cfear_sync / any other entry point (all of which join first);
- *   - d_cur_slots of a step must not name a slot (keyframe or current) of a step still in flight: rotate two sets.
+ *   - d_cur_slots of a step must not name a slot (keyframe or current) of a step still in flight: rotate as many sets
+ *     as steps are kept in flight.
  * cfear_odometry_step_batch_dev == this + cfear_join, i.e. fully ordered on the context stream. */
 int cfear_odometry_step_batch_dev_submit(cfear_ctx* ctx, int nprob, const uint8_t* d_polar, const double* d_mot,
                                          const int32_t* d_kf_slots, int K, const int32_t* d_cur_slots,
@@ -259,7 +261,10 @@ typedef struct cfear_seq cfear_seq;
 /* Sequence b owns the cell-set slots [slot_base + b*(max_keyframes+1), +max_keyframes+1). */
 int  cfear_seq_create(cfear_ctx* ctx, int nseq, int slot_base, int max_steps, const cfear_seq_params* params, cfear_seq** out);
 void cfear_seq_destroy(cfear_seq* seq);
-/* One time step for every sequence: polar [nseq][A][R] (HOST / DEVICE).  Asynchronous on the context stream. */
+/* One time step for every sequence: polar [nseq][A][R] (HOST / DEVICE).  Asynchronous: the step is enqueued on the
+ * library's internal streams (the filter of a scan runs one step ahead, under the registration of the previous scan) after
+ * whatever the context stream holds at the time of the call; the image buffer must stay valid and untouched until the
+ * step is complete (cfear_join / cfear_sync / cfear_seq_read or any other entry point). */
 int  cfear_seq_step(cfear_seq* seq, const uint8_t* polar);
 int  cfear_seq_step_dev(cfear_seq* seq, const uint8_t* d_polar);
 /* Waits for the enqueued steps and copies out steps [step_from, step_from+nsteps): poses_out [nseq][nsteps][3],

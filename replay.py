@@ -75,6 +75,7 @@ def main():
                 S.step_dev(t_imgs[t].data_ptr())
             else:
                 S.step(h[t])
+        ctx.join()                                     # the context stream waits for the steps on the library's streams
         e1.record(ext)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
