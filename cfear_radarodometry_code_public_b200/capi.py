@@ -35,7 +35,7 @@ class Config(C.Structure):
 class RegStats(C.Structure):
     _fields_ = [("success", C.c_int32), ("outer_iterations", C.c_int32), ("inner_iterations", C.c_int32),
                 ("num_residuals", C.c_int32), ("num_blocks", C.c_int32), ("usable", C.c_int32),
-                ("final_cost", C.c_double), ("score", C.c_double)]
+                ("final_cost", C.c_double), ("score", C.c_double), ("pose_written", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CfarParams(C.Structure):
@@ -52,13 +52,13 @@ CELL_DTYPE = np.dtype([("mean", np.float64, 2), ("normal", np.float64, 2), ("cov
                        ("pad", np.int32)])
 STATS_DTYPE = np.dtype([("success", np.int32), ("outer_iterations", np.int32), ("inner_iterations", np.int32),
                         ("num_residuals", np.int32), ("num_blocks", np.int32), ("usable", np.int32),
-                        ("final_cost", np.float64), ("score", np.float64)])
+                        ("final_cost", np.float64), ("score", np.float64), ("pose_written", np.int32), ("reserved", np.int32)])
 
 # every symbol include/cfear_b200.h declares
 SYMBOLS = ["cfear_default_config", "cfear_create", "cfear_destroy", "cfear_update_config", "cfear_last_error", "cfear_version",
            "cfear_launch_count", "cfear_kstrongest", "cfear_filter", "cfear_compensate", "cfear_surface_points",
            "cfear_scans_to_cells_batch", "cfear_cells_count", "cfear_cells_download", "cfear_cells_upload", "cfear_nearest", "cfear_register",
-           "cfear_register_batch", "cfear_get_cost_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_odometry_step_batch_dev_submit", "cfear_stream_wait_ticket", "cfear_join", "cfear_sync",
+           "cfear_register_batch", "cfear_register_batch_ex", "cfear_get_cost_batch", "cfear_odometry_step_batch", "cfear_odometry_step_batch_submit", "cfear_odometry_step_batch_wait", "cfear_odometry_step_batch_dev", "cfear_odometry_step_batch_dev_submit", "cfear_stream_wait_ticket", "cfear_join", "cfear_sync",
            "cfear_stream", "cfear_stage_timing", "cfear_last_counts", "cfear_alloc_pinned", "cfear_free_pinned",
            "cfear_alloc_device", "cfear_free_device", "cfear_memcpy_h2d", "cfear_memcpy_d2h",
            "cfear_cfar_filter", "cfear_seq_create", "cfear_seq_destroy", "cfear_seq_step", "cfear_seq_step_dev", "cfear_seq_read"]
@@ -108,6 +108,7 @@ def load():
         lib.cfear_nearest.argtypes = [vp, i32, vp, i32, C.c_double, vp]
         lib.cfear_register.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.cfear_register_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
+        lib.cfear_register_batch_ex.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_get_cost_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cfear_odometry_step_batch_submit.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
@@ -320,15 +321,25 @@ class Context:
         return out
 
     # ---- registration ----
-    def register_batch(self, slots, poses, want_assoc=False):
+    def register_batch(self, slots, poses, want_assoc=False, want_sim=False, prior_sqrt_info=None):
+        """cfear_register_batch[_ex].  Returns (poses, cov [n,6,6], stats, assoc) -- plus the similarity table when want_sim.
+        prior_sqrt_info: (nprob, 3, 3) lower-triangular L of Register(..., soft_constraints=true)."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         nprob, ns = slots.shape
         p = np.ascontiguousarray(poses, dtype=np.float64).reshape(nprob, ns, 3).copy()
         cov = np.zeros((nprob, 36))
         st = np.zeros(nprob, STATS_DTYPE)
-        assoc = np.full((nprob, ns - 1, self.max_cells), -1, np.int32) if want_assoc else None
-        self._ck(self.lib.cfear_register_batch(self.h, nprob, _ptr(slots), ns, _ptr(p), _ptr(cov), _ptr(st), _ptr(assoc)),
-                 "cfear_register_batch")
+        assoc = np.full((nprob, ns - 1, self.max_cells), -1, np.int32) if (want_assoc or want_sim) else None
+        sim = np.zeros((nprob, ns - 1, self.max_cells)) if want_sim else None
+        L = None if prior_sqrt_info is None else np.ascontiguousarray(prior_sqrt_info, dtype=np.float64).reshape(nprob, 9)
+        if sim is None and L is None:
+            self._ck(self.lib.cfear_register_batch(self.h, nprob, _ptr(slots), ns, _ptr(p), _ptr(cov), _ptr(st), _ptr(assoc)),
+                     "cfear_register_batch")
+        else:
+            self._ck(self.lib.cfear_register_batch_ex(self.h, nprob, _ptr(slots), ns, _ptr(p), _ptr(cov), _ptr(st), _ptr(assoc),
+                                                      _ptr(sim), _ptr(L)), "cfear_register_batch_ex")
+        if want_sim:
+            return p, cov.reshape(nprob, 6, 6), st, assoc, sim
         return p, cov.reshape(nprob, 6, 6), st, assoc
 
     def get_cost_batch(self, slots, poses):

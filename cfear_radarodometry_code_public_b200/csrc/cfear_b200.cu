@@ -149,6 +149,7 @@ struct cfear_ctx {
   int* d_ghist = nullptr; int32_t* d_status = nullptr; double2* d_celltmp = nullptr;
   double* d_mot = nullptr; int32_t *d_slots = nullptr, *d_curslots = nullptr, *d_kfslots = nullptr;
   double *d_poses = nullptr, *d_cov36 = nullptr; cfear_reg_stats* d_stats = nullptr; int32_t* d_assoc = nullptr;
+  double *d_assoc_sim = nullptr, *d_softL = nullptr;
   double2* d_res = nullptr; double* d_queries = nullptr; int32_t* d_qout = nullptr; CellAoS* d_cellaos = nullptr;
   CellPool pool;
   std::vector<double2> h_cs;
@@ -437,10 +438,10 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
 
 static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, const int32_t* d_slots, double* d_poses, double* d_cov36,
                      cfear_reg_stats* d_stats, int32_t* d_assoc, int off = 0, const int32_t* d_nscans_pp = nullptr,
-                     int solver_mode_override = -1) {
+                     int solver_mode_override = -1, double* d_assoc_sim = nullptr, const double* d_softL = nullptr) {
   RegParams p;
   p.pool = c->pool; p.nprob = nprob; p.nscans = nscans; p.nscans_pp = d_nscans_pp; p.slots = d_slots; p.poses = d_poses; p.cov36 = d_cov36;
-  p.stats = d_stats; p.assoc = d_assoc; p.res = B.d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
+  p.stats = d_stats; p.assoc = d_assoc; p.assoc_sim = d_assoc_sim; p.soft_L = d_softL; p.res = B.d_res + (size_t)off * c->res_cap * 4; p.res_cap = c->res_cap;
   p.cost = c->cfg.cost; p.loss = c->cfg.loss; p.weight_opt = c->cfg.weight_opt; p.solver_mode = c->cfg.solver_mode;
   p.max_outer = c->cfg.max_outer; p.min_outer = c->cfg.min_outer; p.max_inner = c->cfg.max_inner; p.gn_iters = c->cfg.gn_iters;
   p.loss_limit = c->cfg.loss_limit; p.cov_scale = c->cfg.cov_scale; p.regularization = c->cfg.regularization;
@@ -650,31 +651,45 @@ int cfear_nearest(cfear_ctx* c, int slot, const double* queries_xy, int nq, doub
   return CFEAR_OK;
 }
 
-int cfear_register_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nscans, double* poses, double* cov36,
-                         cfear_reg_stats* stats, int32_t* assoc_out) {
+int cfear_register_batch_ex(cfear_ctx* c, int nprob, const int32_t* slots, int nscans, double* poses, double* cov36,
+                            cfear_reg_stats* stats, int32_t* assoc_out, double* assoc_sim_out, const double* prior_sqrt_info) {
   ENTER(c);
   if (nprob < 0 || !slots || !poses) { g_err = "null argument"; return CFEAR_ERR_ARG; }
   if (nscans < 2 || nscans > c->cfg.max_keyframes + 1) { g_err = "nscans must be in [2, max_keyframes+1]"; return CFEAR_ERR_ARG; }   // n_scan_normal.cpp:190
   if (nprob > c->cfg.max_batch) { g_err = "nprob exceeds max_batch"; return CFEAR_ERR_CAPACITY; }
+  if (prior_sqrt_info && c->cfg.solver_mode != CFEAR_SOLVER_CERES_LM) { g_err = "the soft prior belongs to Register()'s ceres_lm loop"; return CFEAR_ERR_ARG; }
   if (nprob == 0) return CFEAR_OK;
   for (size_t i = 0; i < (size_t)nprob * nscans; ++i) RC(check_slot(c, slots[i]));
   CK(cudaMemcpyAsync(c->d_slots, slots, (size_t)nprob * nscans * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_poses, poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const size_t assoc_cap = (size_t)c->cfg.max_batch * c->cfg.max_keyframes * c->max_cells;
   const size_t assoc_n = (size_t)nprob * (nscans - 1) * c->max_cells;
-  if (assoc_out) {
-    if (!c->d_assoc) {
-      int rc = c->alloc(&c->d_assoc, (size_t)c->cfg.max_batch * c->cfg.max_keyframes * c->max_cells);
-      if (rc != CFEAR_OK) return rc;
-    }
+  if (assoc_out || assoc_sim_out) {                    // the similarity is only meaningful next to the association table
+    if (!c->d_assoc) RC(c->alloc(&c->d_assoc, assoc_cap));
     CK(cudaMemsetAsync(c->d_assoc, 0xff, assoc_n * sizeof(int32_t), c->stream));
   }
-  RC(launch_k5(c, c->pb[0], nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, assoc_out ? c->d_assoc : nullptr));
+  if (assoc_sim_out) {
+    if (!c->d_assoc_sim) RC(c->alloc(&c->d_assoc_sim, assoc_cap));
+    CK(cudaMemsetAsync(c->d_assoc_sim, 0, assoc_n * sizeof(double), c->stream));
+  }
+  if (prior_sqrt_info) {
+    if (!c->d_softL) RC(c->alloc(&c->d_softL, (size_t)c->cfg.max_batch * 9));
+    CK(cudaMemcpyAsync(c->d_softL, prior_sqrt_info, (size_t)nprob * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  RC(launch_k5(c, c->pb[0], nprob, nscans, c->d_slots, c->d_poses, c->d_cov36, c->d_stats, (assoc_out || assoc_sim_out) ? c->d_assoc : nullptr,
+               0, nullptr, -1, assoc_sim_out ? c->d_assoc_sim : nullptr, prior_sqrt_info ? c->d_softL : nullptr));
   CK(cudaMemcpyAsync(poses, c->d_poses, (size_t)nprob * nscans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (cov36) CK(cudaMemcpyAsync(cov36, c->d_cov36, (size_t)nprob * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (stats) CK(cudaMemcpyAsync(stats, c->d_stats, (size_t)nprob * sizeof(cfear_reg_stats), cudaMemcpyDeviceToHost, c->stream));
   if (assoc_out) CK(cudaMemcpyAsync(assoc_out, c->d_assoc, assoc_n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (assoc_sim_out) CK(cudaMemcpyAsync(assoc_sim_out, c->d_assoc_sim, assoc_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return CFEAR_OK;
+}
+
+int cfear_register_batch(cfear_ctx* c, int nprob, const int32_t* slots, int nscans, double* poses, double* cov36,
+                         cfear_reg_stats* stats, int32_t* assoc_out) {
+  return cfear_register_batch_ex(c, nprob, slots, nscans, poses, cov36, stats, assoc_out, nullptr, nullptr);
 }
 
 // n_scan_normal_reg::GetCost for nprob independent (cell sets, poses) problems in one launch.
@@ -1033,6 +1048,7 @@ int cfear_seq_create(cfear_ctx* c, int nseq, int slot_base, int max_steps, const
   if (sp->submap_scan_size < 1 || sp->submap_scan_size > c->cfg.max_keyframes) { g_err = "submap_scan_size must be in [1, max_keyframes]"; return CFEAR_ERR_ARG; }
   const int kmax = c->cfg.max_keyframes;
   if (slot_base < 0 || slot_base + nseq * (kmax + 1) > c->cfg.max_cellsets) { g_err = "sequences need nseq*(max_keyframes+1) cell-set slots from slot_base"; return CFEAR_ERR_CAPACITY; }
+  RC(ensure_pipes(c));                      // streams / scratch sets of the replay are created here, not in the first step
   cfear_seq* s = new (std::nothrow) cfear_seq();
   if (!s) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
   s->ctx = c; s->slot_base = slot_base;

@@ -23,7 +23,8 @@ cudaError_t K5_CAT(k5_set_smem_cost, CFEAR_K5_TU_COST)(int bytes) {
 }
 
 bool K5_CAT(k5_launch_cost, CFEAR_K5_TU_COST)(const RegParams& p, int nprob, int smem, cudaStream_t stream) {
-  const bool aux = p.solver_mode != 0;            // gn_fixed / cost only
+  // gn_fixed / cost only, and the ceres_lm loop with association outputs or the soft prior: the AUX instantiations
+  const bool aux = p.solver_mode != 0 || p.assoc != nullptr || p.assoc_sim != nullptr || p.soft_L != nullptr;
   switch (p.loss) {
 #define K5_CASE(LO)                                                                                       \
   case LO:                                                                                                \

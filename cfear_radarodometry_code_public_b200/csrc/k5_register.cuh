@@ -37,7 +37,9 @@ struct RegParams {
   double* poses;                 // [nprob][nscans][3] in/out
   double* cov36;                 // [nprob][36]
   void* stats;                   // [nprob] cfear_reg_stats
-  int32_t* assoc;                // [nprob][nscans-1][max_cells] or null
+  int32_t* assoc;                // [nprob][nscans-1][max_cells] or null   } association outputs and the soft prior are served by
+  double* assoc_sim;             // same shape: direction similarity of the pair  } the AUX instantiations only (k5_launch_cost*)
+  const double* soft_L;          // [nprob][9] or null: row-major lower-triangular sqrt information of the guess prior
   double2* res;                  // [nprob][4][res_cap] residual scratch, SoA: (px,py) (qx,qy) (a,b) (c,w)
   int res_cap;
   int smem_bytes;                // dynamic shared memory given to the kernel
@@ -49,6 +51,7 @@ struct RegParams {
 struct RegStatsDev {             // == cfear_reg_stats
   int32_t success, outer_iterations, inner_iterations, num_residuals, num_blocks, usable;
   double final_cost, score;
+  int32_t pose_written, reserved;
 };
 
 // 1 / sqrt(s) for s in the normal range (callers guarantee s > loss_limit^2 > 0): the 22-bit hardware seed and two
@@ -204,6 +207,10 @@ struct LMShared {
   double out_x[3];         // results broadcast at the end of a solve
   double out_final_cost, out_last_rel;
   int out_niter, out_usable, out_success, out_inner;
+  // soft-constraint prior on the free block (n_scan_normal.cpp:373-377, mahalanobisDistanceError n_scan_normal.h:259-290):
+  // r = alpha L (guess - x), alpha = sqrt(#source cells), no loss.  M = alpha^2 L^T L is its constant J^T J.
+  int soft, pad2;
+  double guess[3], aL[6], M[6];          // aL = alpha * (l00 l10 l11 l20 l21 l22), M packed like EvalOut::H
 };
 
 // Named barriers A / B of the evaluation service.  Warp 0 and the serving warps reach them from different places in
@@ -284,7 +291,7 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
 }
 
 // warp 0 only: evaluate cost + normal equations at y
-template <int COST, int LOSS>
+template <int COST, int LOSS, bool AUX = false>
 __device__ __forceinline__ void request_eval(double loss_limit, const ResList& res, int nres, const double y[3], EvalOut& ev,
                                              LMShared* sh, double* s_part PROF_PARAM) {
   PROF_T(te0);
@@ -311,6 +318,19 @@ __device__ __forceinline__ void request_eval(double loss_limit, const ResList& r
   for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
+  if constexpr (AUX) {
+    if (sh->soft) {                              // + the prior's residual block (3 rows, Jacobian -alpha L)
+      const double d0 = sh->guess[0] - y[0], d1 = sh->guess[1] - y[1], d2 = sh->guess[2] - y[2];
+      const double* L = sh->aL;
+      const double r0 = L[0] * d0, r1 = L[1] * d0 + L[2] * d1, r2 = L[3] * d0 + L[4] * d1 + L[5] * d2;
+      ev.cost += 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ev.H[i] += sh->M[i];
+      ev.g[0] -= L[0] * r0 + L[1] * r1 + L[3] * r2;
+      ev.g[1] -= L[2] * r1 + L[4] * r2;
+      ev.g[2] -= L[5] * r2;
+    }
+  }
 }
 
 // warps 1..: serve evaluations until warp 0 signals completion
@@ -376,22 +396,22 @@ struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usa
 // warp 0 (all lanes redundantly), evaluations through request_eval.  The candidate point is evaluated with its
 // Jacobian in the same pass, so an accepted step needs no second pass over the residuals (the sums are the ones a
 // re-evaluation would give).
-template <int COST, int LOSS>
+template <int COST, int LOSS, bool AUX>
 __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
                                               LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM);
 
 // Hout: J^T J (loss-corrected, unscaled) at the returned x -- what GetCovariance needs, so the caller does not have to
 // evaluate the final point again.
-template <int COST, int LOSS>
+template <int COST, int LOSS, bool AUX>
 __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
                                          LMShared* sh, double* s_part, double Hout[6] PROF_PARAM) {
   EvalOut ev;
-  lm_solve_impl<COST, LOSS>(P, res, nres, x, sum, sh, s_part, ev PROF_ARG);
+  lm_solve_impl<COST, LOSS, AUX>(P, res, nres, x, sum, sh, s_part, ev PROF_ARG);
 #pragma unroll
   for (int i = 0; i < 6; ++i) Hout[i] = ev.H[i];
 }
 
-template <int COST, int LOSS>
+template <int COST, int LOSS, bool AUX>
 __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
                                               LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
@@ -405,7 +425,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
   int invalid_in_a_row = 0;
   sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
 
-  request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
+  request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
   double x_cost = ev.cost;
   double scale[3];
   scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
@@ -456,7 +476,7 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
     const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
     const double inv_model_change = rcp_normal(model_change);       // model_change > 0; off the chain that follows the evaluation
     EvalOut evc;
-    request_eval<COST, LOSS>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
+    request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
     const double cand_cost = evc.cost;
     // parameter tolerance |delta| <= tol (|x| + tol): the square roots are only taken when the squares come close
     const double step_n2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
@@ -630,8 +650,8 @@ __device__ __forceinline__ void make_record(const RegParams& P, const RelT& T, d
 //   2. one block scan gives every accepted pair its position, in (keyframe, cell) order; the residual records are then
 //      built position by position (two in flight per thread) and stored straight into the residual list.
 // Returns the number of residual blocks (block-uniform).
-template <int COST>
-__device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx& C, const ResList& res, int32_t* assoc,
+template <int COST, bool AUX>
+__device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx& C, const ResList& res, int32_t* assoc, double* assoc_sim,
                                              int* s_warp, uint16_t* s_nn, uint16_t* s_list, int tile PROF_PARAM) {
   const int T = K5_THREADS, tid = threadIdx.x;
   const int n_src = C.n_src, npairs = C.K * n_src;
@@ -679,7 +699,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
         valid = normal_gate(ntx, nty, n16, P.pool.normal + (size_t)C.slots[i] * P.pool.max_cells + m, angle_outlier);   // :246-247
       }
       s_nn[u] = valid ? (uint16_t)m : K5_NONE;
-      if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
+      if constexpr (AUX) { if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1; }
 #ifdef CFEAR_K5_PROFILE
       prof[15] += clock64() - tq2;
 #endif
@@ -699,7 +719,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
     PROF_T(tp3);
     // ---- phase 2 ----
     for (int r0 = tid; r0 < total; r0 += 2 * T) {
-      int ii[2] = {0, 0};
+      int ii[2] = {0, 0}, jj[2] = {0, 0};
       bool have[2];
       double2 mu[2], nsrc[2], tm[2], ntar[2];
       double4 Cv[2];
@@ -711,6 +731,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
         const int u = have[h] ? s_list[r] : s_list[r0];
         const int t = t0 + u, i = t / n_src, j = t - i * n_src;
         ii[h] = i;
+        if constexpr (AUX) jj[h] = j;
         const size_t sb = C.sbase + j;
         const size_t tb = (size_t)C.slots[i] * P.pool.max_cells + s_nn[u];
         // everything the record may need is requested at once: one L2 round trip for both pairs
@@ -728,6 +749,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
           const RelT R = rel_transform(C, ii[h]);
           const double ntx = R.rc * nsrc[h].x - R.rs * nsrc[h].y, nty = R.rs * nsrc[h].x + R.rc * nsrc[h].y;
           const double sim = fmax(ntx * ntar[h].x + nty * ntar[h].y, 0.0);
+          if constexpr (AUX) { if (assoc_sim) assoc_sim[(size_t)ii[h] * P.pool.max_cells + jj[h]] = sim; }
           double2 rp, rq, rab, rcw;
           make_record<COST>(P, R, sim, mu[h], tm[h], ntar[h], Cv[h], n1[h], n2[h], p1[h], p2[h], rp, rq, rab, rcw);
           const int pos = nres + r;
@@ -819,7 +841,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   if (ns < 2) {                      // nothing to register against (first scan of a sequence): Register() would assert
     if (tid == 0) {
       RegStatsDev st; st.success = 0; st.outer_iterations = 0; st.inner_iterations = 0; st.num_residuals = 0; st.num_blocks = 0;
-      st.usable = 0; st.final_cost = 0.0; st.score = 0.0;
+      st.usable = 0; st.final_cost = 0.0; st.score = 0.0; st.pose_written = 0; st.reserved = 0;
       reinterpret_cast<RegStatsDev*>(P.stats)[prob] = st;
       for (int i = 0; i < 36; ++i) P.cov36[(size_t)prob * 36 + i] = 0.0;
     }
@@ -887,7 +909,8 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     res.s = reinterpret_cast<double2*>(U + g_end); res.cap_s = min(((int)u_room - (int)g_end) / 64, P.res_cap);
     if (res.cap_s < 0) res.cap_s = 0;
   }
-  int32_t* assoc = P.assoc ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
+  int32_t* assoc = (AUX && P.assoc) ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
+  double* assoc_sim = (AUX && P.assoc_sim) ? P.assoc_sim + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
   const bool w0 = warp_id() == 0;              // the warp that runs the scalar solver logic (see "evaluation service")
   LMShared* sh = &s_lm;
@@ -905,7 +928,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     C.x[0] = x[0]; C.x[1] = x[1]; C.x[2] = x[2];
     sincos(x[2], &C.sn_s, &C.cs_s);
     C.radius = (itr == 1) ? 2 * P.radius : P.radius;
-    const int n = build_problem<COST>(P, C, res, assoc, s_warp, s_nn, s_list, tile PROF_ARG);
+    const int n = build_problem<COST, AUX>(P, C, res, assoc, assoc_sim, s_warp, s_nn, s_list, tile PROF_ARG);
     if (overlay) grids_resident = false;
     PROF_T(ta2);
     PROF_ADD(prof[2], ta0, ta1); PROF_ADD(prof[0], ta1, ta2);
@@ -915,7 +938,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
   double lastH[6] = {0, 0, 0, 0, 0, 0};        // warp 0: J^T J at x from the last solve; valid while have_H (block-uniform)
   bool have_H = false;
-  bool success = true;
+  bool success = true, pose_written = false;
   int inner_total = 0, nres = 0, outer = 0;
   if (AUX && P.solver_mode == 2) {
     // cost only -- n_scan_normal_reg::GetCost (n_scan_normal.cpp:187-213): one association at the registration radius
@@ -960,6 +983,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
       sum.final_cost = sh->out_final_cost;
       __syncthreads();                           // outputs consumed before the next episode rewrites them
       if (!ok) { success = false; break; }
+      pose_written = true;
       inner_total++;
     }
     outer = it;
@@ -980,12 +1004,30 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     double prev_score = 1.7976931348623157e308;
     int itr;
     have_H = true;
+    if constexpr (AUX) {
+      if (tid == 0) {
+        sh->soft = P.soft_L != nullptr;
+        if (P.soft_L) {                                                         // :373-377
+          const double* Lr = P.soft_L + (size_t)prob * 9;
+          const double alpha = sqrt((double)C.n_src);
+          const double l00 = Lr[0], l10 = Lr[3], l11 = Lr[4], l20 = Lr[6], l21 = Lr[7], l22 = Lr[8];
+          sh->guess[0] = x[0]; sh->guess[1] = x[1]; sh->guess[2] = x[2];
+          sh->aL[0] = alpha * l00; sh->aL[1] = alpha * l10; sh->aL[2] = alpha * l11;
+          sh->aL[3] = alpha * l20; sh->aL[4] = alpha * l21; sh->aL[5] = alpha * l22;
+          const double a2 = alpha * alpha;                                      // M = alpha^2 L^T L  (xx xy xt yy yt tt)
+          sh->M[0] = a2 * (l00 * l00 + l10 * l10 + l20 * l20); sh->M[1] = a2 * (l10 * l11 + l20 * l21); sh->M[2] = a2 * (l20 * l22);
+          sh->M[3] = a2 * (l11 * l11 + l21 * l21); sh->M[4] = a2 * (l21 * l22); sh->M[5] = a2 * (l22 * l22);
+        }
+      }
+      __syncthreads();
+    }
     for (itr = 1; itr <= P.max_outer && success; ++itr) {                       // n_scan_normal.cpp:102
       nres = associate(itr);
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
       PROF_T(ts0);
+      const double x_in[3] = {x[0], x[1], x[2]};
       if (w0) {
-        lm_solve<COST, LOSS>(P, res, nres, x, sum, sh, s_part, lastH PROF_ARG);         // :117
+        lm_solve<COST, LOSS, AUX>(P, res, nres, x, sum, sh, s_part, lastH PROF_ARG);    // :117
         if (lane_id() == 0) {
           sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
           sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
@@ -1002,6 +1044,9 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
       PROF_T(ts1);
       PROF_ADD(prof[1], ts0, ts1);
       success = sum.usable;
+      // an unusable solution is not written back (ceres restores the parameter blocks): the pose of the last good solve stays
+      if (!success) { x[0] = x_in[0]; x[1] = x_in[1]; x[2] = x_in[2]; }
+      else pose_written = true;                                                 // :119-121
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;
       const double rel_improvement = (prev_score - current_score) / prev_score;
@@ -1019,7 +1064,9 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   RegStatsDev st;
   st.outer_iterations = outer; st.inner_iterations = inner_total;
   st.num_blocks = nres; st.num_residuals = nres * per_block;
+  if constexpr (AUX) { if (P.solver_mode == 0 && P.soft_L && nres * per_block > 1) { st.num_blocks += 1; st.num_residuals += 3; } }   // the prior's block
   st.usable = sum.usable ? 1 : 0; st.final_cost = sum.final_cost; st.score = 0.0; st.success = 0;
+  st.pose_written = pose_written ? 1 : 0; st.reserved = 0;
   double cov[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) cov[i] = 0.0;
@@ -1035,7 +1082,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
 #pragma unroll
         for (int i = 0; i < 6; ++i) ev.H[i] = lastH[i];
       } else {
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
+        request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
         finish_evals(sh);
       }
       double inv[9]; bool ok = true;

@@ -58,7 +58,7 @@ struct SeqParams {
   void* traj_stats;               // [nseq][max_steps] cfear_reg_stats
 };
 
-struct RegStatsK6 { int32_t success, outer_iterations, inner_iterations, num_residuals, num_blocks, usable; double final_cost, score; };
+struct RegStatsK6 { int32_t success, outer_iterations, inner_iterations, num_residuals, num_blocks, usable; double final_cost, score; int32_t pose_written, reserved; };
 
 // before the scan is processed: previous motion for Compensate, guess, registration tables
 __global__ void k6_pre(const SeqParams P) {
@@ -98,9 +98,9 @@ __global__ void k6_post(const SeqParams P) {
     S.nkf = 1; fuse = 1;
     S.cur_slot = S.cur_slot + 1;                                                // slots of a sequence are contiguous
   } else {
-    // Tsrc is rewritten from the parameters only after a usable solve (n_scan_normal.cpp:119-121, 177-178);
-    // the fuser ignores Register()'s return value (:184-186)
-    const bool wrote = st.num_residuals > 1 && st.usable;
+    // Tsrc is rewritten from the parameters after every usable solve (n_scan_normal.cpp:119-121, 177-178) and keeps the
+    // last such pose if a later outer iteration fails; the fuser ignores Register()'s return value (:184-186)
+    const bool wrote = st.pose_written != 0;
     const double* p = P.poses + ((size_t)b * stride + S.nkf) * 3;
     Tcurrent = wrote ? t2_from(p[0], p[1], p[2]) : S.Tguess;                    // :195
     const T2 Tmot_current = t2_mul(t2_inv(S.T_prev), Tcurrent);

@@ -110,6 +110,9 @@ typedef struct cfear_reg_stats {
   int32_t usable;            /* summary_.IsSolutionUsable() of the last solve */
   double  final_cost;        /* summary_.final_cost */
   double  score;             /* score_ = final_cost / num_residuals */
+  int32_t pose_written;      /* 1 if some solve of this Register() call was usable, i.e. Tsrc was rewritten from the parameters
+                                (n_scan_normal.cpp:119-121); 0: the pose handed in is returned untouched */
+  int32_t reserved;
 } cfear_reg_stats;
 
 typedef struct cfear_ctx cfear_ctx;
@@ -164,6 +167,18 @@ int cfear_register(cfear_ctx* ctx, const int32_t* slots, int nscans, double* pos
  * last outer iteration's association per (keyframe, src cell), -1 = none (scan_associations_, registration.h:105). */
 int cfear_register_batch(cfear_ctx* ctx, int nprob, const int32_t* slots, int nscans, double* poses,
                          double* cov36, cfear_reg_stats* stats, int32_t* assoc_out);
+
+/* The same with the rest of Register()'s observable state:
+ *   assoc_sim_out (may be NULL)  [nprob][nscans-1][max_cells]: the direction similarity max(n_src' . n_tar, 0) of each
+ *       associated pair -- with assoc_out, the cell sets' Nsamples_ / planarity this is the content of the public members
+ *       scan_associations_ / weight_associations_ (registration.h:103-106, n_scan_normal.cpp:255-256);
+ *   prior_sqrt_info (may be NULL) [nprob][9]: row-major 3x3 lower-triangular factor L of the guess prior, Register(...,
+ *       soft_constraints = true): L = Cov6to3(reg_cov.back()).inverse().llt().matrixL() (n_scan_normal.cpp:373-377); the block
+ *       r = sqrt(#source cells) L (guess - x) (mahalanobisDistanceError, n_scan_normal.h:259-290) joins every outer iteration's
+ *       problem, guess = the pose handed in for the last scan. */
+int cfear_register_batch_ex(cfear_ctx* ctx, int nprob, const int32_t* slots, int nscans, double* poses,
+                            double* cov36, cfear_reg_stats* stats, int32_t* assoc_out, double* assoc_sim_out,
+                            const double* prior_sqrt_info);
 
 /* n_scan_normal_reg::GetCost (n_scan_normal.h:41, n_scan_normal.cpp:187-213) for nprob independent problems: associate
  * once at the poses given (all fixed, the last set is the source) with the registration radius, return the robustified

@@ -27,11 +27,13 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cfear_b200.h"
@@ -321,6 +323,13 @@ class MapPointNormal {
     if (cfear_nearest(Backend::get().ctx(), slot_, q, 1, d, &idx) != CFEAR_OK) fail("cfear_nearest");
     return idx >= 0 ? std::vector<int>{idx} : std::vector<int>();
   }
+  // pointnormal.cpp:139-143 with GetRelTimeStamp of utils.h:28-32: where in the sweep (-0.5 .. 0.5) the cell was observed
+  double GetCellRelTimeStamp(const size_t index, const bool ccw) {
+    const double x = cells[index].u_(0), y = cells[index].u_(1);
+    const double a = std::atan2(y, x);
+    const double d = ((a > 0.00001 ? a : (2 * M_PI + a)) / (2 * M_PI));
+    return ccw ? -(d - 0.5) : (d - 0.5);
+  }
   int slot() const { return slot_; }
 
  private:
@@ -340,12 +349,38 @@ struct SolverSummary {            // the fields of ceres::Solver::Summary the re
   bool IsSolutionUsable() const { return usable; }
 };
 
+typedef std::pair<int, int> int_pair;     // registration.h:44
+
 class Registration {
  public:
   virtual ~Registration() {}
   virtual bool Register(std::vector<MapNormalPtr>& scans, std::vector<Affine3d>& Tsrc, std::vector<Matrix6d>& reg_cov, bool soft_constraints = false) = 0;
   virtual double getScore() { return score_; }
+  class Weights {                         // registration.h:88-101, registration.cpp:67-76
+   public:
+    Weights(double N1, double N2, double sim_dir, double plan1, double plan2) : N1_(N1), N2_(N2), sim_dir_(sim_dir), plan1_(plan1), plan2_(plan2) {}
+    double GetWeight(const weightoption opt) {
+      switch (opt) {
+        case Uniform: return 1.0;
+        case Sim_N: return Similarity(N1_, N2_);
+        case Sim_direciton: return sim_dir_;
+        case Sim_scale: return Similarity(plan1_, plan2_);
+        case Combined_weights: return GetWeight(Sim_N) + GetWeight(Sim_direciton) + GetWeight(Sim_scale);
+        default: return 1.0;
+      }
+    }
+    double Similarity(const double x, const double y) { return 2 * std::min(x, y) / (x + y); }
+    double N1_, N2_;
+    double sim_dir_;
+    double plan1_, plan2_;
+  };
   weightoption weight_opt_ = Uniform;
+  // the last outer iteration's data association, keyed (target scan index, source scan index): pairs (target cell, source
+  // cell) and their weight terms, in source-cell order (registration.h:103-106, n_scan_normal.cpp:255-256).  Filled by
+  // Register() when keep_associations_ is set (they cost a device->host copy the pose path does not need).
+  std::map<int_pair, std::vector<Weights> > weight_associations_;
+  std::map<int_pair, std::vector<int_pair> > scan_associations_;
+  bool keep_associations_ = false;
   size_t itr_ = 0;
   SolverSummary summary_;
 
@@ -373,7 +408,6 @@ class n_scan_normal_reg : public Registration {
   bool Register(std::vector<MapNormalPtr>& scans, std::vector<Affine3d>& Tsrc, std::vector<Matrix6d>& reg_cov, bool soft_constraints = false) {
     const size_t n_scans = scans.size();
     assert(Tsrc.size() == n_scans && reg_cov.size() == n_scans);
-    if (soft_constraints) throw std::runtime_error("n_scan_normal_reg: soft_constraints is not supported (off in every reference preset)");
     Backend& b = Backend::get();
     cfear_config& cfg = b.cfg();
     cfg.cost = cost_ == P2P ? CFEAR_COST_P2P : (cost_ == P2L ? CFEAR_COST_P2L : CFEAR_COST_P2D);
@@ -393,15 +427,37 @@ class n_scan_normal_reg : public Registration {
     }
     double cov36[36];
     cfear_reg_stats st;
-    if (cfear_register(b.ctx(), slots.data(), (int)n_scans, poses.data(), cov36, &st) != CFEAR_OK)
-      throw std::runtime_error(std::string("cfear_register: ") + cfear_last_error());
+    double L9[9];
+    if (soft_constraints && !PriorSqrtInformation(reg_cov.back(), L9))        // :374 Cov6to3(cov).inverse().llt().matrixL()
+      throw std::runtime_error("n_scan_normal_reg: the covariance of the guess is not positive definite");
+    scan_associations_.clear(); weight_associations_.clear();                 // :103-104
+    std::vector<int32_t> assoc; std::vector<double> sim;
+    const size_t max_cells = (size_t)(cfg.max_cells > 0 ? cfg.max_cells : cfg.azimuths * cfg.k_strongest);
+    if (keep_associations_) { assoc.assign((n_scans - 1) * max_cells, -1); sim.assign((n_scans - 1) * max_cells, 0.0); }
+    if (cfear_register_batch_ex(b.ctx(), 1, slots.data(), (int)n_scans, poses.data(), cov36, &st, keep_associations_ ? assoc.data() : nullptr,
+                                keep_associations_ ? sim.data() : nullptr, soft_constraints ? L9 : nullptr) != CFEAR_OK)
+      throw std::runtime_error(std::string("cfear_register_batch_ex: ") + cfear_last_error());
+    if (keep_associations_) {
+      MapNormalPtr& src = scans[n_scans - 1];
+      for (size_t i = 0; i + 1 < n_scans; ++i) {
+        const int_pair scan_pair((int)i, (int)n_scans - 1);
+        for (size_t j = 0; j < src->GetSize(); ++j) {
+          const int m = assoc[i * max_cells + j];
+          if (m < 0) continue;
+          weight_associations_[scan_pair].push_back(Weights((double)src->GetCell(j).Nsamples_, (double)scans[i]->GetCell(m).Nsamples_,
+                                                            sim[i * max_cells + j], src->GetCell(j).GetPlanarity(), scans[i]->GetCell(m).GetPlanarity()));
+          scan_associations_[scan_pair].push_back(std::make_pair(m, (int)j));
+        }
+      }
+    }
     itr_ = (size_t)st.outer_iterations;
     summary_.final_cost = st.final_cost; summary_.num_residuals = st.num_residuals; summary_.num_residual_blocks = st.num_blocks;
     summary_.num_inner_iterations = st.inner_iterations; summary_.usable = st.usable != 0;
-    // Tsrc[i] = vectorToAffine3d(parameters[i]) happens after every successful solve (:119-121,177-178)
-    if (st.num_residuals > 1 && st.usable)
+    // Tsrc[i] = vectorToAffine3d(parameters[i]) happens after every successful solve (:119-121,177-178); a later failing
+    // iteration leaves the pose of the last good one in place
+    if (st.pose_written)
       for (size_t i = 0; i < n_scans; ++i) Tsrc[i] = vectorToAffine3d(poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]);
-    const bool reached_cov = st.num_residuals > 1 && st.usable;   // the `if(success)` block at :163
+    const bool reached_cov = st.num_residuals > 1 && st.usable;   // the `if(success)` block at :163 (the loop ended without a failure)
     if (reached_cov) {
       score_ = st.score;
       Matrix6d d; d(0, 0) = 0.01; d(1, 1) = 0.01; d(5, 5) = 0.0001;   // :171-175
@@ -456,6 +512,27 @@ class n_scan_normal_reg : public Registration {
         throw std::runtime_error(std::string("cfear_get_cost_batch: ") + cfear_last_error());
     }
     for (size_t s = 0; s < ns; ++s) { num_residuals[s] = nr[s]; ok[s] = okv[s] != 0; }
+  }
+  // Cov6to3 (registration.cpp:123-129) -> inverse -> lower Cholesky factor, row-major 3x3; false if not positive definite
+  static bool PriorSqrtInformation(const Matrix6d& C, double L[9]) {
+    const double a = C(0, 0), b = C(0, 1), c = C(0, 5), d = C(1, 0), e = C(1, 1), f = C(1, 5), g = C(5, 0), h = C(5, 1), i = C(5, 5);
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return false;
+    const double I[9] = {(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det,
+                         (f * g - d * i) / det, (a * i - c * g) / det, (c * d - a * f) / det,
+                         (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
+    for (int k = 0; k < 9; ++k) L[k] = 0.0;
+    if (!(I[0] > 0.0)) return false;                        // llt() reads the lower triangle
+    L[0] = std::sqrt(I[0]);
+    L[3] = I[3] / L[0]; L[6] = I[6] / L[0];
+    const double d1 = I[4] - L[3] * L[3];
+    if (!(d1 > 0.0)) return false;
+    L[4] = std::sqrt(d1);
+    L[7] = (I[7] - L[6] * L[3]) / L[4];
+    const double d2 = I[8] - L[6] * L[6] - L[7] * L[7];
+    if (!(d2 > 0.0)) return false;
+    L[8] = std::sqrt(d2);
+    return true;
   }
   // n_scan_normal.cpp:435-441 (summary_ of the last Register; three parameters in the reduced problem)
   bool GetCovarianceScaler(double& cov_scale) {

@@ -48,7 +48,7 @@ def _p(a, t=None):
 class RegStats(C.Structure):
     _fields_ = [("success", C.c_int32), ("outer_iterations", C.c_int32), ("inner_iterations", C.c_int32),
                 ("num_residuals", C.c_int32), ("num_blocks", C.c_int32), ("usable", C.c_int32),
-                ("final_cost", C.c_double), ("score", C.c_double)]
+                ("final_cost", C.c_double), ("score", C.c_double), ("pose_written", C.c_int32), ("reserved", C.c_int32)]
 
 
 def kstrongest(img: np.ndarray, z_min: int, k: int):
@@ -137,10 +137,13 @@ def concat_cellsets(sets):
             cat("planarity", np.float64).ravel(), cat("nsamples", np.int32).ravel())
 
 
-def register(sets, poses, cfg, want_assoc=False):
+def register(sets, poses, cfg, want_assoc=False, prior_sqrt_info=None, want_sim=False):
     """sets: list of K+1 cell dicts (last = current scan); poses: (K+1,3) (x,y,yaw), last = guess.
-    Returns (success, poses_out, cov6x6, RegStats, assoc or None)."""
+    prior_sqrt_info: 3x3 lower-triangular L of Register(..., soft_constraints=true) (n_scan_normal.cpp:373-377) or None.
+    Returns (success, poses_out, cov6x6, RegStats, assoc or None) (+ the direction-similarity table when want_sim)."""
     ci, cd = cfg
+    if prior_sqrt_info is not None or want_sim:
+        return _register_ex(sets, poses, cfg, prior_sqrt_info, want_sim)
     offs, mean, normal, cov, plan, ns = concat_cellsets(sets)
     p = np.ascontiguousarray(poses, dtype=np.float64).copy()
     cov36 = np.zeros(36)
@@ -150,6 +153,30 @@ def register(sets, poses, cfg, want_assoc=False):
     ok = lib().orc_register(_p(ci), _p(cd), len(sets), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
                             _p(p), _p(cov36), C.byref(st), _p(assoc))
     return bool(ok), p, cov36.reshape(6, 6), st, assoc
+
+
+def _register_ex(sets, poses, cfg, prior_sqrt_info, want_sim):
+    ci, cd = cfg
+    offs, mean, normal, cov, plan, ns = concat_cellsets(sets)
+    p = np.ascontiguousarray(poses, dtype=np.float64).copy()
+    cov36 = np.zeros(36)
+    st = RegStats()
+    n_src = sets[-1]["mean"].shape[0]
+    assoc = np.full((len(sets) - 1, n_src), -1, np.int32)
+    sim = np.zeros((len(sets) - 1, n_src))
+    L = None if prior_sqrt_info is None else np.ascontiguousarray(prior_sqrt_info, dtype=np.float64).reshape(9)
+    ok = lib().orc_register_ex(_p(ci), _p(cd), len(sets), _p(offs), _p(mean), _p(normal), _p(cov), _p(plan), _p(ns),
+                               _p(p), _p(cov36), C.byref(st), _p(assoc), _p(sim), _p(L))
+    if want_sim:
+        return bool(ok), p, cov36.reshape(6, 6), st, assoc, sim
+    return bool(ok), p, cov36.reshape(6, 6), st, assoc
+
+
+def prior_sqrt_information(cov6):
+    """Cov6to3(cov).inverse().llt().matrixL() (n_scan_normal.cpp:374, registration.cpp:123-129)."""
+    c = np.asarray(cov6, dtype=np.float64).reshape(6, 6)
+    c3 = c[np.ix_([0, 1, 5], [0, 1, 5])]
+    return np.linalg.cholesky(np.linalg.inv(c3))
 
 
 def get_cost(sets, poses, cfg):

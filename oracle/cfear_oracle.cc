@@ -297,6 +297,12 @@ struct RegCfg {
   int max_outer, min_outer, max_inner;  // 8, 3, 20
   int solver_mode;     // 0 ceres_lm, 1 gn_fixed
   int gn_iters;
+  // Register(..., soft_constraints = true), n_scan_normal.cpp:373-377: residual block alpha * L * (guess - x) without a loss
+  // (mahalanobisDistanceError, n_scan_normal.h:259-290; applyOnTheLeft(L), i.e. L and not L^T as in P2D), L =
+  // Cov6to3(cov).inverse().llt().matrixL() row-major 3x3, alpha = sqrt(#source cells), guess = the pose handed in.
+  const double* prior_L = nullptr;
+  double prior_guess[3] = {0, 0, 0};
+  double prior_alpha = 0.0;
 };
 
 struct Residual {      // one residual block  (n_scan_normal.cpp:266-320)
@@ -379,6 +385,19 @@ void evaluate(const RegCfg& cfg, const std::vector<Residual>& res, const double 
         H[0] += wr * J1[0] * J1[0]; H[1] += wr * J1[0] * J1[1]; H[2] += wr * J1[0] * J1[2];
         H[3] += wr * J1[1] * J1[1]; H[4] += wr * J1[1] * J1[2]; H[5] += wr * J1[2] * J1[2];
         g[0] += wr * J1[0] * r1; g[1] += wr * J1[1] * r1; g[2] += wr * J1[2] * r1;
+      }
+    }
+  }
+  if (cfg.prior_L) {                                  // the soft prior's 3 rows: r = alpha L (guess - x), J = -alpha L
+    const double* L = cfg.prior_L; const double al = cfg.prior_alpha;
+    const double d[3] = {cfg.prior_guess[0] - x[0], cfg.prior_guess[1] - x[1], cfg.prior_guess[2] - x[2]};
+    for (int row = 0; row < 3; ++row) {
+      const double J[3] = {-al * L[3 * row + 0], -al * L[3 * row + 1], -al * L[3 * row + 2]};
+      const double r = -(J[0] * d[0] + J[1] * d[1] + J[2] * d[2]);
+      cost += 0.5 * r * r;
+      if (with_jac) {
+        H[0] += J[0] * J[0]; H[1] += J[0] * J[1]; H[2] += J[0] * J[2]; H[3] += J[1] * J[1]; H[4] += J[1] * J[2]; H[5] += J[2] * J[2];
+        g[0] += J[0] * r; g[1] += J[1] * r; g[2] += J[2] * r;
       }
     }
   }
@@ -525,7 +544,8 @@ double assoc_weight(int opt, double n1, double n2, double simdir, double p1, dou
 
 // A.4  AddScanPairCost for every keyframe  (n_scan_normal.cpp:215-326, 359-367)
 void build_problem(const RegCfg& cfg, const std::vector<CellSet*>& scans, const std::vector<double>& poses,
-                   int itr, std::vector<Residual>& res, std::vector<int32_t>* assoc /* per (kf, src) tar idx */) {
+                   int itr, std::vector<Residual>& res, std::vector<int32_t>* assoc /* per (kf, src) tar idx */,
+                   std::vector<double>* assoc_sim = nullptr /* per (kf, src) direction similarity, Weights::sim_dir_ */) {
   res.clear();
   const int ns = (int)scans.size();
   const CellSet& src = *scans[ns - 1];
@@ -534,6 +554,7 @@ void build_problem(const RegCfg& cfg, const std::vector<CellSet*>& scans, const 
   const double angle_outlier = std::cos(M_PI / 6.0);
   const double curr_radius = (itr == 1) ? 2 * cfg.radius : cfg.radius;     // :222
   if (assoc) assoc->assign((size_t)(ns - 1) * src.n, -1);
+  if (assoc_sim) assoc_sim->assign((size_t)(ns - 1) * src.n, 0.0);
   for (int i = 0; i < ns - 1; ++i) {
     const CellSet& tar = *scans[i];
     const double* xt = &poses[3 * i];
@@ -582,6 +603,7 @@ void build_problem(const RegCfg& cfg, const std::vector<CellSet*>& scans, const 
       }
       res.push_back(r);
       if (assoc) (*assoc)[(size_t)i * src.n + j] = m;
+      if (assoc_sim) (*assoc_sim)[(size_t)i * src.n + j] = sim;
     }
   }
 }
@@ -597,14 +619,22 @@ struct RegStats {
   int32_t usable;
   double final_cost;
   double score;
+  int32_t pose_written;     // some solve was usable: Tsrc rewritten from the parameters (n_scan_normal.cpp:119-121)
+  int32_t reserved;
 };
 
 // A.5  n_scan_normal_reg::Register   (n_scan_normal.cpp:82-187)
-bool do_register(const RegCfg& cfg, std::vector<CellSet*>& scans, std::vector<double>& poses, double cov36[36],
-                 RegStats& st, std::vector<int32_t>* last_assoc) {
+bool do_register(const RegCfg& cfg_in, std::vector<CellSet*>& scans, std::vector<double>& poses, double cov36[36],
+                 RegStats& st, std::vector<int32_t>* last_assoc, std::vector<double>* last_sim = nullptr) {
   const int ns = (int)scans.size();
   st = RegStats();
   double* x = &poses[3 * (ns - 1)];
+  RegCfg cfg = cfg_in;
+  if (cfg.prior_L) {                                                       // :95-96 guess, :375 alpha
+    cfg.prior_guess[0] = x[0]; cfg.prior_guess[1] = x[1]; cfg.prior_guess[2] = x[2];
+    cfg.prior_alpha = std::sqrt((double)scans[ns - 1]->n);
+    if (cfg.solver_mode != 0) cfg.prior_L = nullptr;                       // Register()'s ceres_lm loop only
+  }
   std::vector<Residual> res;
   SolveSummary sum;
   bool success = true;
@@ -614,12 +644,13 @@ bool do_register(const RegCfg& cfg, std::vector<CellSet*>& scans, std::vector<do
     // (BASELINE config 2).  Not a reference mode; defined by this repo.
     int it;
     for (it = 1; it <= cfg.gn_iters; ++it) {
-      build_problem(cfg, scans, poses, it, res, last_assoc);
+      build_problem(cfg, scans, poses, it, res, last_assoc, last_sim);
       if (num_scalar_residuals(cfg, res.size()) <= 1) { success = false; break; }
       Eval ev; evaluate(cfg, res, x, true, ev);
       double y[3], nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
       if (!chol3_solve(ev.H, nb, y)) { success = false; break; }
       x[0] += y[0]; x[1] += y[1]; x[2] += y[2];
+      st.pose_written = 1;
       sum.final_cost = ev.cost;
       inner_total++;
     }
@@ -630,10 +661,14 @@ bool do_register(const RegCfg& cfg, std::vector<CellSet*>& scans, std::vector<do
     double prev_score = DBL_MAX;
     int itr;
     for (itr = 1; itr <= cfg.max_outer && success; ++itr) {               // :102
-      build_problem(cfg, scans, poses, itr, res, last_assoc);            // :105
+      build_problem(cfg, scans, poses, itr, res, last_assoc, last_sim);  // :105
       if (num_scalar_residuals(cfg, res.size()) <= 1) { success = false; break; }   // :370, :114
+      const double x_in[3] = {x[0], x[1], x[2]};
       ceres_lm_solve(cfg, res, x, sum);                                  // :117
       success = sum.usable;                                              // :451
+      // ceres writes the state back to the parameter blocks only if the solution is usable (solver.cc Minimize)
+      if (!success) { x[0] = x_in[0]; x[1] = x_in[1]; x[2] = x_in[2]; }
+      else st.pose_written = 1;                                          // :119-121
       inner_total += sum.n_iterations - 1;
       const double current_score = sum.final_cost;                       // :123
       const double rel_improvement = (prev_score - current_score) / prev_score;
@@ -650,6 +685,7 @@ bool do_register(const RegCfg& cfg, std::vector<CellSet*>& scans, std::vector<do
   st.inner_iterations = inner_total;
   st.num_blocks = (int)res.size();
   st.num_residuals = num_scalar_residuals(cfg, res.size());
+  if (cfg.prior_L && st.num_residuals > 1) { st.num_blocks += 1; st.num_residuals += 3; }   // summary_.num_residuals counts the prior
   st.usable = sum.usable ? 1 : 0;
   st.final_cost = sum.final_cost;
   for (int i = 0; i < 36; ++i) cov36[i] = 0.0;
@@ -862,6 +898,37 @@ int orc_register(const int32_t* cfg_i, const double* cfg_d, int nscans, const in
   for (int i = 0; i < 3 * nscans; ++i) poses[i] = p[i];
   if (stats_out) std::memcpy(stats_out, &st, sizeof(RegStats));
   if (assoc_out) std::copy(assoc.begin(), assoc.end(), assoc_out);
+  return ok ? 1 : 0;
+}
+
+// orc_register plus the similarity table and the soft prior (prior_L: row-major 3x3 lower-triangular, may be null)
+int orc_register_ex(const int32_t* cfg_i, const double* cfg_d, int nscans, const int32_t* offsets, const double* mean,
+                    const double* normal, const double* cov, const double* planarity, const int32_t* nsamples,
+                    double* poses, double* cov36, void* stats_out, int32_t* assoc_out, double* sim_out, const double* prior_L) {
+  RegCfg cfg;
+  cfg.cost = cfg_i[0]; cfg.loss = cfg_i[1]; cfg.weight_opt = cfg_i[2];
+  cfg.max_outer = cfg_i[3]; cfg.min_outer = cfg_i[4]; cfg.max_inner = cfg_i[5];
+  cfg.solver_mode = cfg_i[6]; cfg.gn_iters = cfg_i[7];
+  cfg.loss_limit = cfg_d[0]; cfg.cov_scale = cfg_d[1]; cfg.regularization = cfg_d[2]; cfg.radius = cfg_d[3];
+  cfg.prior_L = prior_L;
+  std::vector<CellSet> sets(nscans);
+  std::vector<CellSet*> ptrs(nscans);
+  for (int i = 0; i < nscans; ++i) {
+    const int o = offsets[i];
+    sets[i].n = offsets[i + 1] - o;
+    sets[i].mean = mean + 2 * (size_t)o; sets[i].normal = normal + 2 * (size_t)o; sets[i].cov = cov + 4 * (size_t)o;
+    sets[i].planarity = planarity + o; sets[i].nsamples = nsamples + o;
+    if (i < nscans - 1) sets[i].build_index();
+    ptrs[i] = &sets[i];
+  }
+  std::vector<double> p(poses, poses + 3 * (size_t)nscans);
+  RegStats st;
+  std::vector<int32_t> assoc; std::vector<double> sim;
+  bool ok = do_register(cfg, ptrs, p, cov36, st, &assoc, &sim);
+  for (int i = 0; i < 3 * nscans; ++i) poses[i] = p[i];
+  if (stats_out) std::memcpy(stats_out, &st, sizeof(RegStats));
+  if (assoc_out) std::copy(assoc.begin(), assoc.end(), assoc_out);
+  if (sim_out) std::copy(sim.begin(), sim.end(), sim_out);
   return ok ? 1 : 0;
 }
 
@@ -1081,8 +1148,9 @@ int orc_odometry_sequence(int nscans, const int32_t* pipe_i, const float* pipe_f
     double cov36[36];
     const std::vector<double> poses_in = poses;
     do_register(cfg, scans, poses, cov36, st, nullptr);                    // :186 (return value ignored :184-186)
-    // Tsrc is rewritten from the parameters only after a usable solve (n_scan_normal.cpp:119-121,177-178)
-    const bool wrote = st.num_residuals > 1 && st.usable;
+    // Tsrc is rewritten from the parameters after every usable solve (n_scan_normal.cpp:119-121,177-178) and keeps the
+    // pose of the last one if a later outer iteration fails
+    const bool wrote = st.pose_written != 0;
     const size_t L = poses.size() - 3;
     Tcurrent = wrote ? t2_from(poses[L], poses[L + 1], poses[L + 2]) : Tguess;       // :195
     const T2 Tmot_current = t2_mul(t2_inv(T_prev), Tcurrent);

@@ -177,6 +177,37 @@ def test_oracle_lm_reaches_scipy_optimum(orc):
     assert np.hypot(*(op[1, :2] - sol.x[:2])) < 2e-4 and abs(op[1, 2] - sol.x[2]) < 2e-5
 
 
+def test_oracle_soft_prior_reaches_scipy_optimum(orc):
+    """Register(..., soft_constraints=true): the prior block alpha * L * (guess - x) (no loss) joins the Huber-robustified
+    P2L blocks; scipy minimises the same objective when the robust blocks are replaced by their Huber square roots."""
+    from scipy.optimize import least_squares
+    im, tp = helpers.scan_images(3, 1)
+    sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(2)]
+    P = tp[:2].copy(); P[1] = tp[1] + [0.15, -0.1, 0.01]
+    c6 = np.eye(6); c6[0, 0] = 4.0; c6[1, 1] = 9.0; c6[0, 1] = c6[1, 0] = 1.0; c6[5, 5] = 0.04; c6[0, 5] = c6[5, 0] = 0.1
+    L = orc.prior_sqrt_information(c6)
+    c3 = c6[np.ix_([0, 1, 5], [0, 1, 5])]
+    np.testing.assert_allclose(L @ L.T, np.linalg.inv(c3), rtol=1e-12)
+    cfg = orc.reg_cfg(cost="P2L", loss="Huber", max_outer=1, max_inner=50)
+    ok, op, _, st, assoc = orc.register(sets, P, cfg, prior_sqrt_info=L)
+    ok0, op0, _, st0, _ = orc.register(sets, P, cfg, want_assoc=True)
+    assert ok and st.num_residuals == st0.num_residuals + 3 and st.num_blocks == st0.num_blocks + 1
+    j = np.nonzero(assoc[0] >= 0)[0]; m = assoc[0][j]
+    p = sets[1]["mean"][j]; q = sets[0]["mean"][m]; n = sets[0]["normal"][m]
+    alpha = np.sqrt(sets[1]["mean"].shape[0])
+
+    def fun(x):
+        c, s = np.cos(x[2]), np.sin(x[2])
+        ex = c * p[:, 0] - s * p[:, 1] + x[0] - q[:, 0]; ey = s * p[:, 0] + c * p[:, 1] + x[1] - q[:, 1]
+        r = ex * n[:, 0] + ey * n[:, 1]
+        a = np.abs(r)
+        hub = np.where(a <= 0.1, r, np.sign(r) * np.sqrt(np.maximum(2 * 0.1 * a - 0.01, 0)))    # sqrt(rho(r^2)) with sign
+        return np.concatenate([hub, alpha * (L @ (P[1] - x))])
+    sol = least_squares(fun, P[1], xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    assert np.hypot(*(op[1, :2] - sol.x[:2])) < 2e-4 and abs(op[1, 2] - sol.x[2]) < 2e-5
+    assert np.hypot(*(op[1, :2] - op0[1, :2])) > 1e-3                    # and the prior did pull the solution toward the guess
+
+
 # ---- golden vectors ------------------------------------------------------------------------------------------
 def test_golden_vectors(orc):
     g = np.load(os.path.join(GOLD, "cfear_golden_v1.npz"))
@@ -241,7 +272,7 @@ def test_config_struct_layout_matches_header():
     assert abs(cfg.z_min - 60) < 1e-6 and abs(cfg.range_res - 0.0438) < 1e-6 and abs(cfg.radius - 3.5) < 1e-6
     assert (cfg.cost, cfg.loss, cfg.max_outer, cfg.min_outer, cfg.max_inner) == (1, 1, 8, 3, 20)
     assert cfg.reg_radius == 2.0 and cfg.loss_limit == 0.1 and cfg.regularization == 1.0
-    assert ctypes.sizeof(capi.RegStats) == capi.STATS_DTYPE.itemsize == 40
+    assert ctypes.sizeof(capi.RegStats) == capi.STATS_DTYPE.itemsize == 48
     assert capi.CELL_DTYPE.itemsize == 88
 
 

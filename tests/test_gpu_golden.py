@@ -14,6 +14,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def test_gpu_reproduces_golden_v1():
     g = np.load(os.path.join(GOLD, "cfear_golden_v1.npz"))
     img = synth.make_problem_images(int(g["seed"]), 1)[0]
+    assert np.array_equal(img[1, ::8, ::8], g["img_sub"]), "the synthetic generator drifted (numpy RNG / rendering): regenerate the goldens"
     c = capi.Context(max_batch=2, max_cellsets=4, max_keyframes=1, cost="P2L", radius=3.5)
     idx, cnt = c.kstrongest(img[1][None])
     assert np.array_equal(idx[0], g["kidx"]) and np.array_equal(cnt[0], g["kcnt"])            # bit-exact index sets
@@ -37,6 +38,7 @@ def test_gpu_reproduces_golden_v2():
     g = np.load(os.path.join(GOLD, "cfear_golden_v2.npz"))
     K = 2
     img = synth.make_problem_images(int(g["seed"]), K)[0]
+    assert np.array_equal(img[K, ::8, ::8], g["img_sub"]), "the synthetic generator drifted (numpy RNG / rendering): regenerate the goldens"
     c = capi.Context(max_batch=32, max_cellsets=K + 1, max_keyframes=K, cost="P2D", loss="Huber", weight_opt=4, regularization=0.1,
                      radius=3.0)
     out = c.filter(img[:K + 1])
@@ -57,4 +59,29 @@ def test_gpu_reproduces_golden_v2():
     cost, nres, ok = c.get_cost_batch(np.repeat(slots, S.shape[0], 0), poses)
     assert ok.all()
     np.testing.assert_allclose(cost, S[:, 3], rtol=1e-8)
+    # covariance by sampling (odometrykeyframefuser.cpp:261-380) from the GPU's costs: quadric fit -> 2 H^-1 * scaler
+    x, y, z = S[:, 0], S[:, 1], S[:, 2]
+    A = np.stack([x * x, y * y, z * z, x * y, y * z, z * x, x, y, z, np.ones_like(x)], 1)
+    q = np.linalg.lstsq(A, cost, rcond=None)[0]
+    H = np.array([[2 * q[0], q[3], q[5]], [q[3], 2 * q[1], q[4]], [q[5], q[4], 2 * q[2]]])
+    c3 = 2.0 * np.linalg.inv(H) * (st["final_cost"][0] / (st["num_residuals"][0] - 3)) * 4.0
+    gs = g["sampled_cov"]
+    np.testing.assert_allclose(c3[:2, :2], gs[:2, :2], rtol=1e-4)
+    np.testing.assert_allclose([c3[2, 2], c3[0, 2], c3[1, 2]], [gs[5, 5], gs[0, 5], gs[1, 5]], rtol=1e-4, atol=1e-12)
     c.close()
+
+
+def test_gpu_reproduces_golden_v2_sequence_replay():
+    """The frozen OdometryKeyframeFuser replay (8 scans, P2L, window 3) through the device-side fuser (cfear_seq_*)."""
+    g = np.load(os.path.join(GOLD, "cfear_golden_v2.npz"))
+    seq, _ = synth.make_sequence(int(g["seq_seed"]), 8)
+    assert np.array_equal(seq[-1, ::8, ::8], g["seq_sub"]), "the synthetic generator drifted (numpy RNG / rendering): regenerate the goldens"
+    c = capi.Context(max_batch=1, max_cellsets=5, max_keyframes=4, cost="P2L", weight_opt=0, radius=3.5, weight_intensity=1)
+    S = capi.Sequences(c, 1, 8, submap_scan_size=3)
+    for t in range(8):
+        S.step(seq[t][None])
+    poses, kf, _ = S.read(0, 8)
+    assert np.array_equal(kf[0], g["seq_keyframe"])
+    d = poses[0] - g["seq_poses"]
+    assert np.hypot(d[:, 0], d[:, 1]).max() < 1e-4 and np.abs(d[:, 2]).max() < 1e-5
+    S.close(); c.close()

@@ -24,8 +24,11 @@ def exe(tmp_path_factory):
     return out
 
 
-@pytest.mark.parametrize("cost,loss,wopt,K", [("P2L", "Huber", 0, 1), ("P2D", "Huber", 4, 4), ("P2P", "Cauchy", 4, 3)])
-def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K):
+@pytest.mark.parametrize("cost,loss,wopt,K,flags", [("P2L", "Huber", 0, 1, 0), ("P2D", "Huber", 4, 4, 2), ("P2P", "Cauchy", 4, 3, 0),
+                                                      ("P2D", "Huber", 4, 3, 3), ("P2L", "Huber", 1, 2, 1)])
+def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K, flags):
+    """flags: 1 = Register(..., soft_constraints = true) with a non-trivial guess covariance, 2 = the public
+    scan_associations_ / weight_associations_ tables are filled and checked."""
     im, tp = helpers.scan_images(31, K)
     radius, reg = 3.5, 0.1
     P = tp.copy(); P[K] = tp[K - 1]
@@ -33,7 +36,7 @@ def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K):
     ci, li = orc.COST[cost], orc.LOSS[loss]
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(fin, "wb") as f:
-        f.write(struct.pack("<iiifiiid", K + 1, im.shape[1], im.shape[2], radius, ci, li, wopt, reg))
+        f.write(struct.pack("<iiifiiidi", K + 1, im.shape[1], im.shape[2], radius, ci, li, wopt, reg, flags))
         f.write(im[:K + 1].tobytes()); f.write(P.astype(np.float64).tobytes()); f.write(mot.astype(np.float64).tobytes())
     subprocess.check_call([exe, fin, fout])
     raw = open(fout, "rb").read()
@@ -42,13 +45,36 @@ def test_mirror_matches_oracle(exe, orc, tmp_path, cost, loss, wopt, K):
     score = np.frombuffer(raw, np.float64, 1, 44)[0]
     cov = np.frombuffer(raw, np.float64, 36, 52).reshape(6, 6)
     near = struct.unpack_from("<i", raw, 52 + 288)[0]
+    n_assoc = struct.unpack_from("<i", raw, 52 + 288 + 4)[0]
+    sums = np.frombuffer(raw, np.float64, 4, 52 + 288 + 8)
+    stamps = np.frombuffer(raw, np.float64, 2, 52 + 288 + 8 + 32)
     # oracle, same call sequence
     sets = []
     for i in range(K + 1):
         cl, s = helpers.oracle_cells(orc, im[i], radius=radius, mot=(mot if i == K else None))
         sets.append(s)
-    o_ok, op, ocov, ost, _ = orc.register(sets, P, orc.reg_cfg(cost=cost, loss=loss, weight_opt=wopt, regularization=reg))
+    L = None
+    if flags & 1:
+        c6 = np.eye(6); c6[0, 0] = 0.04; c6[1, 1] = 0.09; c6[0, 1] = c6[1, 0] = 0.01; c6[5, 5] = 0.0004; c6[0, 5] = c6[5, 0] = 0.001
+        L = orc.prior_sqrt_information(c6)
+    o_ok, op, ocov, ost, oassoc, osim = orc.register(sets, P, orc.reg_cfg(cost=cost, loss=loss, weight_opt=wopt, regularization=reg),
+                                                     prior_sqrt_info=L, want_sim=True)
     assert bool(ok) == o_ok and itr == ost.outer_iterations and nres == ost.num_residuals
+    if flags & 2:
+        tar, src = np.nonzero(oassoc >= 0)
+        assert n_assoc == tar.size > 100
+        assert sums[0] == oassoc[oassoc >= 0].sum() and sums[1] == src.sum()
+        np.testing.assert_allclose(sums[2], osim[oassoc >= 0].sum(), rtol=1e-12)
+        nsrc = sets[-1]["nsamples"][src].astype(float); ntar = np.array([sets[t]["nsamples"][m] for t, m in zip(tar, oassoc[oassoc >= 0])], float)
+        psrc = sets[-1]["planarity"][src]; ptar = np.array([sets[t]["planarity"][m] for t, m in zip(tar, oassoc[oassoc >= 0])])
+        sim_n, sim_p = 2 * np.minimum(nsrc, ntar) / (nsrc + ntar), 2 * np.minimum(psrc, ptar) / (psrc + ptar)
+        w = {0: np.ones_like(sim_n), 1: sim_n, 2: osim[oassoc >= 0], 3: sim_p, 4: sim_n + osim[oassoc >= 0] + sim_p}[wopt]
+        np.testing.assert_allclose(sums[3], w.sum(), rtol=1e-12)
+    else:
+        assert n_assoc == 0
+    m0 = sets[-1]["mean"][0]
+    a = np.arctan2(m0[1], m0[0]); dd = (a if a > 1e-5 else 2 * np.pi + a) / (2 * np.pi)
+    np.testing.assert_allclose(stamps, [dd - 0.5, -(dd - 0.5)], atol=1e-12)
     assert ncells == sets[-1]["mean"].shape[0] and npts == cl.shape[0]
     d = pose - op[K]
     assert np.hypot(d[0], d[1]) < 1e-4 and abs(d[2]) < 1e-5

@@ -198,6 +198,39 @@ def test_register_parity(orc, imgs, cost, loss, wopt, K, solver):
     c.close()
 
 
+@pytest.mark.parametrize("cost,wopt,K", [("P2D", 4, 3), ("P2L", 1, 1), ("P2P", 2, 2)])
+def test_register_soft_prior_and_association_tables(orc, imgs, cost, wopt, K):
+    """cfear_register_batch_ex: Register(..., soft_constraints = true) (prior block alpha L (guess - x), n_scan_normal.cpp:373-377)
+    and the content of scan_associations_ / weight_associations_ (target index + direction similarity per source cell)."""
+    im, poses = imgs
+    sets, P = _problem(orc, im, poses, K, 3.0)
+    reg = 0.1 if cost == "P2D" else 1.0
+    c = capi.Context(max_batch=2, max_cellsets=8, max_keyframes=4, cost=cost, loss="Huber", weight_opt=wopt, regularization=reg, radius=3.0)
+    for i, s in enumerate(sets):
+        c.cells_upload(i, s)
+    slots = np.arange(K + 1, dtype=np.int32)[None]
+    ocfg = orc.reg_cfg(cost=cost, loss="Huber", weight_opt=wopt, regularization=reg)
+    c6 = np.eye(6); c6[0, 0] = 4.0; c6[1, 1] = 9.0; c6[0, 1] = c6[1, 0] = 1.0; c6[5, 5] = 0.04; c6[0, 5] = c6[5, 0] = 0.1
+    n_src = sets[-1]["mean"].shape[0]
+    for L in (None, orc.prior_sqrt_information(c6), np.eye(3)):
+        gp, gcov, gst, gassoc, gsim = c.register_batch(slots, P[None], want_sim=True, prior_sqrt_info=None if L is None else L[None])
+        ok, op, ocov, ost, oassoc, osim = orc.register(sets, P, ocfg, prior_sqrt_info=L, want_sim=True)
+        assert bool(gst["success"][0]) == ok and gst["pose_written"][0] == ost.pose_written == 1
+        assert gst["outer_iterations"][0] == ost.outer_iterations and gst["inner_iterations"][0] == ost.inner_iterations
+        assert gst["num_residuals"][0] == ost.num_residuals and gst["num_blocks"][0] == ost.num_blocks
+        d = gp[0, K] - op[K]
+        assert np.hypot(d[0], d[1]) < POS_TOL and abs(d[2]) < ROT_TOL, d
+        assert np.array_equal(gassoc[0, :, :n_src], oassoc)
+        np.testing.assert_allclose(gsim[0, :, :n_src], osim, rtol=0, atol=1e-13)
+        assert (gsim[0, :, :n_src][oassoc >= 0] > np.cos(np.pi / 6)).all() and (gsim[0, :, :n_src][oassoc < 0] == 0).all()
+        np.testing.assert_allclose(gst["final_cost"][0], ost.final_cost, rtol=1e-6)
+        np.testing.assert_allclose(gcov[0], ocov, rtol=1e-5, atol=1e-12)
+    nores = c.register_batch(slots, P[None])                        # the plain call is unaffected by the calls before
+    ok, op, _, ost, _ = orc.register(sets, P, ocfg)
+    assert nores[2]["num_residuals"][0] == ost.num_residuals and np.abs(nores[0][0, K] - op[K]).max() < 1e-9
+    c.close()
+
+
 def test_get_cost_batch_matches_oracle(orc, imgs):
     """cfear_get_cost_batch (n_scan_normal_reg::GetCost): 27 pose samples around a registered pose in one launch vs one
     oracle GetCost per sample; a sample that sees nothing returns ok = 0."""
