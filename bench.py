@@ -399,11 +399,26 @@ def main():
             t = torch.tensor([el], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
+        # the ceiling of this arm: nothing but the images' host->device copies (same pinned buffer, same bytes per step,
+        # every rank at once) -- what the PCIe link / the host's memory system give this many GPUs copying concurrently
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.h2d(t_polar.data_ptr(), h_polar)
+        torch.cuda.synchronize()
+        el_copy = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el_copy], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el_copy = float(t.item())
         h2d = h_polar.nbytes + batch["mot"].nbytes + kf_slots.nbytes + cur_slots.nbytes + batch["poses"].nbytes
         d2h = h_out["poses"].nbytes + h_out["cov"].nbytes + h_out["stats"].nbytes + h_out["npts"].nbytes
         e2e = {"value": world * nprob * e2e_steps / el, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps, "host_numa_binding": numa,
-               "api": "cfear_odometry_step_batch_submit / _wait, two steps in flight, pinned host buffers"}
+               "api": "cfear_odometry_step_batch_submit / _wait, two steps in flight, pinned host buffers",
+               "h2d_only": {"ms_per_step": 1e3 * el_copy / e2e_steps, "gbytes_per_s_per_gpu": h_polar.nbytes * e2e_steps / el_copy / 1e9,
+                            "note": "the same image bytes copied host->device and nothing else, all ranks concurrently (max over ranks)"},
+               "frac_of_h2d_only": el_copy / el}
         assert np.allclose(h_out["poses"], poses_dev, atol=1e-12), "e2e and device-resident arms disagree"
 
     clocks = sampler.stop(tw0, time.time())      # samples taken during the device-resident and end-to-end timed regions

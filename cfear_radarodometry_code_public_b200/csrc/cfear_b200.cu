@@ -78,7 +78,7 @@ __global__ void k4b_nearest(CellPool pool, int slot, const double* q, int nq, do
   if (i >= nq) return;
   const NNGrid G = pool.grid[slot];
   GridView V; V.gs = pool.gstart + (size_t)slot * pool.grid_stride; V.gp = pool.gpt + (size_t)slot * pool.max_cells;
-  uint32_t n16; out[i] = nn_query(V, G, q[2 * i], q[2 * i + 1], radius, &n16);
+  uint32_t n16; out[i] = nn_query(V, G, q[2 * i], q[2 * i + 1], nn_radius(radius), &n16);
 }
 
 // AoS cfear_cell <-> pool SoA
@@ -113,6 +113,9 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
+#ifndef CFEAR_NN_CELL
+#define CFEAR_NN_CELL 8.0f             // bucket size (metres) of the nearest-neighbour grid over a cell set's means
+#endif
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
 constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 4)
 
@@ -418,7 +421,7 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
   p.slots = d_slots; p.radius = c->cfg.radius;
   p.leaf = (float)((double)c->cfg.radius / c->cfg.downsample_factor);        // pointnormal.cpp:279
   p.weight_intensity = c->cfg.weight_intensity; p.origin_x = 0.0; p.origin_y = 0.0;   // odometrykeyframefuser.cpp:161
-  p.nn_cell = 8.0f;
+  p.nn_cell = CFEAR_NN_CELL;
   p.pts_in_smem = c->pts_in_smem; p.g_bufA = B.d_bufA; p.g_bufB = B.d_bufB;
   p.g_hist = B.d_ghist; p.g_hist_cap = c->g_hist_cap; p.status = B.d_status; p.cell_tmp = B.d_celltmp; p.pool = c->pool;
   if (off) {   // sub-batch: every per-scan array starts at scan `off` (d_mot / d_slots are passed already offset)
@@ -624,7 +627,7 @@ int cfear_cells_upload(cfear_ctx* c, int slot, const cfear_cell* cells, int n) {
   CK(cudaGetLastError());
   const int32_t s32 = slot;
   CK(cudaMemcpyAsync(c->d_curslots, &s32, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = 8.0f;
+  K4Params p; p.pool = c->pool; p.slots = c->d_curslots; p.nn_cell = CFEAR_NN_CELL;
   k4_build_index<<<1, K3_THREADS, c->k4_smem, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());

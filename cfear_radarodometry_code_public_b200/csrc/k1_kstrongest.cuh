@@ -19,7 +19,8 @@ namespace cfear {
 #endif
 constexpr int K1_WARPS = 8;       // warps (rows) per CTA
 constexpr int K1_CAP = 256;       // candidate keys per warp kept in shared memory
-constexpr int K1_TILES = 7;       // uint4 per lane per super-tile (7*512 B = 3584 B >= one 3360-bin Navtech row in registers)
+constexpr int K1_TILES = 7;       // uint4 per lane per super-tile (7*512 B = 3584 B >= one 3360-bin Navtech row in registers);
+constexpr int K1_TILES_WIDE = 8;  // rows of up to 4096 bytes (Oxford: 3768 bins) in one super-tile
 constexpr int K1_MAXK = 64;       // k_strongest <= 64
 
 struct K1Params {
@@ -78,12 +79,16 @@ __device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc) {
 }
 
 // ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
-template <bool ALIGNED, bool ZHI>
-__global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstrongest(const K1Params p) {
+#ifndef CFEAR_K1_MINBLOCKS_UNALIGNED
+#define CFEAR_K1_MINBLOCKS_UNALIGNED 5   // the head / tail masks and the 8-tile form need 48 registers: at 40 they spill (3768-bin rows:
+                                         // 0.371 ns per KB of image with 6 CTAs and spills, 0.316 with 5 CTAs; aligned 3360-bin rows: 0.282)
+#endif
+template <bool ALIGNED, bool ZHI, int TILES = K1_TILES>
+__global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : CFEAR_K1_MINBLOCKS_UNALIGNED) k1_kstrongest(const K1Params p) {
   __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
   __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
   __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
-  __shared__ uint2 s_queue[K1_WARPS][K1_TILES * 32];      // vectors of one super-tile that hold candidates
+  __shared__ uint2 s_queue[K1_WARPS][TILES * 32];      // vectors of one super-tile that hold candidates
   const int grow = blockIdx.x * K1_WARPS + warp_id();
   if (grow >= p.nrows) return;                 // no block-level sync in this kernel
   const int lane = lane_id();
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
   const uint8_t* base = row - off;
   const int nvec = (off + R + 15) >> 4;
   const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
+  const bool edge_row = grow == 0 || grow == p.nrows - 1;      // warp-uniform
 
   // ---- pass 1: stream the row, collect the candidates ---------------------------------------------
   // Candidates are sparse (a few vectors per row hold any), so they are emitted cooperatively: every lane whose vector
@@ -111,29 +117,34 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
   uint2* q = s_queue[warp_id()];
   const bool hi = lane >= 16;
   int C = 0;                                   // warp-uniform candidate count
-  for (int v0 = 0; v0 < nvec; v0 += 32 * K1_TILES) {
-    uint32_t g[K1_TILES];
+  for (int v0 = 0; v0 < nvec; v0 += 32 * TILES) {
+    uint32_t g[TILES];
     {
-      uint4 d[K1_TILES];
+      uint4 d[TILES];
 #pragma unroll
-      for (int i = 0; i < K1_TILES; ++i) {
+      for (int i = 0; i < TILES; ++i) {
         const int v = v0 + i * 32 + lane;
-        if (ALIGNED) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
+        // only the first vector of the first row and the last vector of the last row can reach outside the buffer
+        if (ALIGNED || !edge_row) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
         else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int i = 0; i < K1_TILES; ++i) {
+      for (int i = 0; i < TILES; ++i) {
+        // a super-tile past the end of the row (3768-bin Oxford rows need 236 vectors: one full super-tile of 224 and 12
+        // more) skips the flag arithmetic of its empty tiles (warp-uniform test)
+        if (!ALIGNED && v0 + i * 32 >= nvec) { g[i] = 0; continue; }
         const int v = v0 + i * 32 + lane;
         uint32_t m = ge_flags16<ZHI>(d[i], addc);
         const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
         if (v >= nvec) m = 0;
         else if (!ALIGNED && (b0 < 0 || b0 + 16 > R)) {        // row head / tail: drop bytes of neighbouring rows
+          // valid bytes j in [jlo, jhi) -> 16-bit mask -> the packed flag layout (byte b of word w at bit 8b + 7 - w):
+          // a nibble's bits go to the four byte lanes by one multiply (n * 0x00204081 puts bit b at 8b)
+          const int jlo = max(0, -b0), jhi = min(16, R - b0);
+          const uint32_t jm = (jhi > jlo) ? ((0xffffu >> (16 - jhi)) & (0xffffu << jlo)) : 0u;
           uint32_t keep = 0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int r = b0 + j;
-            if (r >= 0 && r < R) keep |= 1u << (8 * (j & 3) + 7 - (j >> 2));
-          }
+          for (int w = 0; w < 4; ++w) keep |= ((((jm >> (4 * w)) & 0xfu) * 0x00204081u) & 0x01010101u) << (7 - w);
           m &= keep;
         }
         g[i] = m;
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, CFEAR_K1_MINBLOCKS) k1_kstronge
     }
     int nq = 0;                                // warp-uniform queue length
 #pragma unroll
-    for (int i = 0; i < K1_TILES; ++i) {
+    for (int i = 0; i < TILES; ++i) {
       const bool has = g[i] != 0;
       const uint32_t bal = __ballot_sync(FULL, has);
       if (bal) {                                 // warp-uniform
@@ -267,7 +278,9 @@ inline void k1_launch(const K1Params& p, cudaStream_t stream) {
   const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
   const bool aligned = ((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0;
   const bool zhi = p.zmin >= 128;
+  const bool wide = ((15 + p.R + 15) >> 4) > 32 * K1_TILES;      // a row (plus its alignment slack) exceeds one 7-tile super-tile
   if (aligned) { if (zhi) k1_kstrongest<true, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<true, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
+  else if (wide) { if (zhi) k1_kstrongest<false, true, K1_TILES_WIDE><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<false, false, K1_TILES_WIDE><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
   else { if (zhi) k1_kstrongest<false, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<false, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
 }
 

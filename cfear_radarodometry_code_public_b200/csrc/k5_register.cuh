@@ -211,33 +211,18 @@ struct LMShared {
   // r = alpha L (guess - x), alpha = sqrt(#source cells), no loss.  M = alpha^2 L^T L is its constant J^T J.
   int soft, pad2;
   double guess[3], aL[6], M[6];          // aL = alpha * (l00 l10 l11 l20 l21 l22), M packed like EvalOut::H
+  // normal equations at the accepted point of the running LM solve: kept here rather than in warp 0's registers (they are
+  // read once per linear solve; 20 registers less for every thread of the kernel)
+  double acc_H[6], acc_g[3];
 };
 
-// Named barriers A / B of the evaluation service.  Warp 0 and the serving warps reach them from different places in
-// the code, each warp converged (the __syncwarp makes that explicit) -- the producer / consumer use of bar.sync the
-// PTX ISA documents: .aligned constrains the threads of a WARP to execute the same barrier instruction, not the warps
-// of a block.  compute-sanitizer's synccheck nevertheless reports "divergent thread(s) in block" for this form; the
-// two forms it accepts (CFEAR_K5_BAR=0: unaligned `barrier.sync`; =2: bar.sync inside one non-inlined function, so
-// every warp executes the same instruction) cost 5 % of the kernel (0.387 vs 0.368 ms) and are kept as build options.
-#ifndef CFEAR_K5_BAR
-#define CFEAR_K5_BAR 1
-#endif
-
-#if CFEAR_K5_BAR == 0
-__device__ __forceinline__ void bar_a() { asm volatile("barrier.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_b() { asm volatile("barrier.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
-#elif CFEAR_K5_BAR == 1
-#ifdef CFEAR_K5_NO_SYNCWARP
-#define K5_SYNCWARP
-#else
-#define K5_SYNCWARP __syncwarp();
-#endif
-__device__ __forceinline__ void bar_a() { K5_SYNCWARP asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_b() { K5_SYNCWARP asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
-#else
-__device__ __noinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __noinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
-#endif
+// Barriers A ("the point to evaluate -- or the stop mark -- is published") and B ("every warp's partial sums are stored")
+// of an evaluation round.  Every warp of the block executes them from the SAME place (eval_round below, inside loops
+// that all warps run): round 1 used a producer / consumer form in which warp 0 and the serving warps reached the same
+// named barrier from different code locations -- legal PTX, but compute-sanitizer's synccheck reports it as "divergent
+// thread(s) in block".  With the shared loop all three sanitizer tools are clean.
+__device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
 
 // Warp reduction of the 10 sums by recursive halving: at each step a lane hands the half of its values its partner
 // keeps to that partner, so 5+3+2+1+1 = 12 exchanges replace the 50 of ten separate butterflies.  Ends with sum i in the
@@ -290,65 +275,58 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
   warp_reduce10(acc, s_part + warp_id() * 10);
 }
 
-// warp 0 only: evaluate cost + normal equations at y
-template <int COST, int LOSS, bool AUX = false>
-__device__ __forceinline__ void request_eval(double loss_limit, const ResList& res, int nres, const double y[3], EvalOut& ev,
-                                             LMShared* sh, double* s_part PROF_PARAM) {
+// One evaluation round, executed by EVERY warp of the block.  Warp 0 owns the point y (all its lanes hold it) and the
+// decision to stop; it publishes either in shared memory, barrier A, every warp accumulates its share of the residual
+// list and stores its 10 partial sums, barrier B, warp 0 adds the K5_WARPS partials in fixed order (bit-reproducible) and,
+// in the AUX instantiations, the soft prior's block.  Returns false (block-uniform) on the stop mark; `ev` is valid in warp 0.
+template <int COST, int LOSS, bool AUX>
+__device__ __forceinline__ bool eval_round(double loss_limit, const ResList& res, int nres, bool w0, bool stop, const double y[3],
+                                           EvalOut& ev, LMShared* sh, double* s_part PROF_PARAM) {
   PROF_T(te0);
-  double cs, sn; sincos(y[2], &sn, &cs);
-  if (lane_id() == 0) { sh->bc[0] = y[0]; sh->bc[1] = y[1]; sh->bc[2] = y[2]; sh->bc[3] = cs; sh->bc[4] = sn; sh->ctl = 1; }
+  double yy[3] = {y[0], y[1], y[2]}, cs = 1.0, sn = 0.0;
+  if (w0) {
+    if (!stop) sincos(yy[2], &sn, &cs);
+    if (lane_id() == 0) { sh->bc[0] = yy[0]; sh->bc[1] = yy[1]; sh->bc[2] = yy[2]; sh->bc[3] = cs; sh->bc[4] = sn; sh->ctl = stop ? 0 : 1; }
+  }
   PROF_T(te1);
   bar_a();
-  eval_contrib<COST, LOSS>(loss_limit, res, nres, y, cs, sn, s_part);
+  if (sh->ctl == 0) return false;
+  if (!w0) { yy[0] = sh->bc[0]; yy[1] = sh->bc[1]; yy[2] = sh->bc[2]; cs = sh->bc[3]; sn = sh->bc[4]; }
+  eval_contrib<COST, LOSS>(loss_limit, res, nres, yy, cs, sn, s_part);
   PROF_T(te2);
   bar_b();
   PROF_T(te3);
   PROF_ADD(prof[4], te0, te1); PROF_ADD(prof[5], te1, te2); PROF_ADD(prof[6], te2, te3); PROF_ADD(prof[7], 0, 1);
-  // every lane adds the K5_WARPS partials of every sum in warp order (broadcast shared-memory reads, no shuffles)
-  double tot[10];
+  if (w0) {
+    // every lane adds the K5_WARPS partials of every sum in warp order (broadcast shared-memory reads, no shuffles)
+    double tot[10];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) tot[i] = s_part[i];
+    for (int i = 0; i < 10; ++i) tot[i] = s_part[i];
 #pragma unroll
-  for (int w = 1; w < K5_WARPS; ++w) {
+    for (int w = 1; w < K5_WARPS; ++w) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) tot[i] += s_part[w * 10 + i];
-  }
-  ev.cost = tot[0];
+      for (int i = 0; i < 10; ++i) tot[i] += s_part[w * 10 + i];
+    }
+    ev.cost = tot[0];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
+    for (int i = 0; i < 6; ++i) ev.H[i] = tot[1 + i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
-  if constexpr (AUX) {
-    if (sh->soft) {                              // + the prior's residual block (3 rows, Jacobian -alpha L)
-      const double d0 = sh->guess[0] - y[0], d1 = sh->guess[1] - y[1], d2 = sh->guess[2] - y[2];
-      const double* L = sh->aL;
-      const double r0 = L[0] * d0, r1 = L[1] * d0 + L[2] * d1, r2 = L[3] * d0 + L[4] * d1 + L[5] * d2;
-      ev.cost += 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
+    for (int i = 0; i < 3; ++i) ev.g[i] = tot[7 + i];
+    if constexpr (AUX) {
+      if (sh->soft) {                              // + the prior's residual block (3 rows, Jacobian -alpha L)
+        const double d0 = sh->guess[0] - yy[0], d1 = sh->guess[1] - yy[1], d2 = sh->guess[2] - yy[2];
+        const double* L = sh->aL;
+        const double r0 = L[0] * d0, r1 = L[1] * d0 + L[2] * d1, r2 = L[3] * d0 + L[4] * d1 + L[5] * d2;
+        ev.cost += 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) ev.H[i] += sh->M[i];
-      ev.g[0] -= L[0] * r0 + L[1] * r1 + L[3] * r2;
-      ev.g[1] -= L[2] * r1 + L[4] * r2;
-      ev.g[2] -= L[5] * r2;
+        for (int i = 0; i < 6; ++i) ev.H[i] += sh->M[i];
+        ev.g[0] -= L[0] * r0 + L[1] * r1 + L[3] * r2;
+        ev.g[1] -= L[2] * r1 + L[4] * r2;
+        ev.g[2] -= L[5] * r2;
+      }
     }
   }
-}
-
-// warps 1..: serve evaluations until warp 0 signals completion
-template <int COST, int LOSS>
-__device__ __forceinline__ void serve_evals(double loss_limit, const ResList& res, int nres, LMShared* sh, double* s_part) {
-  for (;;) {
-    bar_a();
-    if (sh->ctl == 0) break;
-    const double y[3] = {sh->bc[0], sh->bc[1], sh->bc[2]};
-    eval_contrib<COST, LOSS>(loss_limit, res, nres, y, sh->bc[3], sh->bc[4], s_part);
-    bar_b();
-  }
-}
-
-// warp 0 only: end of a serving episode
-__device__ __forceinline__ void finish_evals(LMShared* sh) {
-  if (lane_id() == 0) sh->ctl = 0;
-  bar_a();
+  return true;
 }
 
 // Symmetric positive-definite 3x3 solve (xx,xy,xt,yy,yt,tt) by Cholesky; one reciprocal square root per pivot.
@@ -392,28 +370,27 @@ __device__ __forceinline__ bool adj3_solve(const double A[6], const double b[3],
 
 struct SolveSum { double final_cost; int n_iterations; double last_rel; bool usable; };
 
-// Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc); executed by
-// warp 0 (all lanes redundantly), evaluations through request_eval.  The candidate point is evaluated with its
-// Jacobian in the same pass, so an accepted step needs no second pass over the residuals (the sums are the ones a
-// re-evaluation would give).
-template <int COST, int LOSS, bool AUX>
-__device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                              LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM);
-
-// Hout: J^T J (loss-corrected, unscaled) at the returned x -- what GetCovariance needs, so the caller does not have to
-// evaluate the final point again.
-template <int COST, int LOSS, bool AUX>
-__device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                         LMShared* sh, double* s_part, double Hout[6] PROF_PARAM) {
-  EvalOut ev;
-  lm_solve_impl<COST, LOSS, AUX>(P, res, nres, x, sum, sh, s_part, ev PROF_ARG);
+// warp 0 (all lanes hold the same values): the accepted point's normal equations -> shared memory
+__device__ __forceinline__ void store_accepted(LMShared* sh, const EvalOut& e) {
+  __syncwarp();                                  // earlier reads of the previous values are done
+  if (lane_id() == 0) {
 #pragma unroll
-  for (int i = 0; i < 6; ++i) Hout[i] = ev.H[i];
+    for (int i = 0; i < 6; ++i) sh->acc_H[i] = e.H[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sh->acc_g[i] = e.g[i];
+  }
+  __syncwarp();
 }
 
+// Trust-region LM with Ceres defaults (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc).  Called by EVERY
+// warp: the loop body is one evaluation round (all warps) followed by the scalar trust-region logic, which only warp 0
+// executes (all lanes redundantly) -- the others go straight to the next round's barrier.  The candidate point is
+// evaluated with its Jacobian in the same pass, so an accepted step needs no second pass over the residuals.  x and sum
+// are valid in warp 0; LMShared::acc_H is left holding J^T J (loss-corrected, unscaled) at the returned x, which is what
+// GetCovariance needs.
 template <int COST, int LOSS, bool AUX>
-__device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList& res, int nres, double x[3], SolveSum& sum,
-                                              LMShared* sh, double* s_part, EvalOut& ev PROF_PARAM) {
+__device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, bool w0, double x[3], SolveSum& sum,
+                                         LMShared* sh, double* s_part PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
   const double kMinRelDecrease = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32;
   const double kMaxRadius = 1e16, kMinRadius = 1e-32;
@@ -421,93 +398,100 @@ __device__ __forceinline__ void lm_solve_impl(const RegParams& P, const ResList&
   // 1 / radius is carried along multiplicatively (the oracle divides the diagonal by the radius; both are the same damping
   // to an ulp) so that no division sits between an accepted step and the next linear solve
   double inv_radius = 1e-4;
-  bool reuse_diagonal = false;
-  int invalid_in_a_row = 0;
-  sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0;
-
-  request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-  double x_cost = ev.cost;
-  double scale[3];
-  scale[0] = 1.0 / (1.0 + sqrt(ev.H[0]));
-  scale[1] = 1.0 / (1.0 + sqrt(ev.H[3]));
-  scale[2] = 1.0 / (1.0 + sqrt(ev.H[5]));
-  double x_n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
-  double min_cost = x_cost;
-  double gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
-  sum.final_cost = min_cost;
-  if (gmax <= kGradientTol) return;
-  double diag[3] = {0, 0, 0};
-  for (int it = 1;; ++it) {
-    const double Hs[6] = {ev.H[0] * scale[0] * scale[0], ev.H[1] * scale[0] * scale[1], ev.H[2] * scale[0] * scale[2],
-                          ev.H[3] * scale[1] * scale[1], ev.H[4] * scale[1] * scale[2], ev.H[5] * scale[2] * scale[2]};
-    const double gs[3] = {ev.g[0] * scale[0], ev.g[1] * scale[1], ev.g[2] * scale[2]};
-    if (!reuse_diagonal) {
-      diag[0] = fmin(fmax(Hs[0], kMinDiag), kMaxDiag);
-      diag[1] = fmin(fmax(Hs[3], kMinDiag), kMaxDiag);
-      diag[2] = fmin(fmax(Hs[5], kMinDiag), kMaxDiag);
-    }
-    const double A[6] = {Hs[0] + diag[0] * inv_radius, Hs[1], Hs[2], Hs[3] + diag[1] * inv_radius, Hs[4], Hs[5] + diag[2] * inv_radius};
-    double y[3];
-    const double nb[3] = {-gs[0], -gs[1], -gs[2]};
-#ifdef CFEAR_K5_CHOL
-    const bool ok = chol3_solve(A, nb, y);
-#else
-    const bool ok = adj3_solve(A, nb, y);
-#endif
-    reuse_diagonal = true;
-    double model_change = 0.0;
-    if (ok) {
-      const double Hy0 = Hs[0] * y[0] + Hs[1] * y[1] + Hs[2] * y[2];
-      const double Hy1 = Hs[1] * y[0] + Hs[3] * y[1] + Hs[4] * y[2];
-      const double Hy2 = Hs[2] * y[0] + Hs[4] * y[1] + Hs[5] * y[2];
-      model_change = -(y[0] * gs[0] + y[1] * gs[1] + y[2] * gs[2]) - 0.5 * (y[0] * Hy0 + y[1] * Hy1 + y[2] * Hy2);
-    }
-    if (!ok || !(model_change > 0.0)) {
-      if (++invalid_in_a_row >= 5) { sum.usable = false; return; }
-      radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-      sum.n_iterations++; sum.last_rel = 0.0;
-      min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
-      if (it >= P.max_inner) return;
-      if (radius <= kMinRadius) return;
-      continue;
-    }
-    invalid_in_a_row = 0;
-    const double delta[3] = {y[0] * scale[0], y[1] * scale[1], y[2] * scale[2]};
-    const double xc[3] = {x[0] + delta[0], x[1] + delta[1], x[2] + delta[2]};
-    const double inv_model_change = rcp_normal(model_change);       // model_change > 0; off the chain that follows the evaluation
-    EvalOut evc;
-    request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, xc, evc, sh, s_part PROF_ARG);
-    const double cand_cost = evc.cost;
-    // parameter tolerance |delta| <= tol (|x| + tol): the square roots are only taken when the squares come close
-    const double step_n2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
-    if (step_n2 <= 4.0 * kParameterTol * kParameterTol * (x_n2 + kParameterTol * kParameterTol)) {      // (a+b)^2 <= 2a^2+2b^2, doubled again
-      if (sqrt(step_n2) <= kParameterTol * (sqrt(x_n2) + kParameterTol)) return;
-    }
-    const double cost_change = x_cost - cand_cost;
-    if (fabs(cost_change) <= kFunctionTol * x_cost) return;
-    const double rel = cost_change * inv_model_change;
-    sum.n_iterations++; sum.last_rel = rel;
-    if (rel > kMinRelDecrease) {
-      x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
+  bool reuse_diagonal = false, first = true, stop = false;
+  int invalid_in_a_row = 0, it = 0;
+  sum.usable = true; sum.n_iterations = 1; sum.last_rel = 0.0; sum.final_cost = 0.0;
+  double scale[3] = {1, 1, 1}, diag[3] = {0, 0, 0};
+  double x_cost = 0.0, x_n2 = 0.0, min_cost = 0.0, model_change = 0.0, inv_model_change = 0.0;
+  double xc[3] = {x[0], x[1], x[2]}, delta[3] = {0, 0, 0};              // the first round evaluates x itself
+  for (;;) {
+    EvalOut evc;                                                        // (dead across the round: not loop-carried)
+    if (!eval_round<COST, LOSS, AUX>(P.loss_limit, res, nres, w0, stop, xc, evc, sh, s_part PROF_ARG)) break;
+    if (!w0) continue;
+    if (first) {                                                        // iteration 0: cost, gradient, Jacobi scaling at x
+      first = false;
+      store_accepted(sh, evc);
+      x_cost = evc.cost;
+      scale[0] = 1.0 / (1.0 + sqrt(evc.H[0]));
+      scale[1] = 1.0 / (1.0 + sqrt(evc.H[3]));
+      scale[2] = 1.0 / (1.0 + sqrt(evc.H[5]));
       x_n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
-      ev = evc;
-      x_cost = ev.cost;
-      gmax = fmax(fabs(ev.g[0]), fmax(fabs(ev.g[1]), fabs(ev.g[2])));
-      // radius /= max(1/3, 1 - (2 rel - 1)^3).  A step with rel >= 0.94 has (2 rel - 1)^3 > 2/3, i.e. the maximum picks
-      // 1/3 whatever the last bits of rel are: that case needs neither the quotient nor the cube.
-      double f = 1.0 / 3.0;
-      if (!(cost_change >= 0.94 * model_change)) { const double t = 2.0 * rel - 1.0; f = fmax(1.0 / 3.0, 1.0 - t * t * t); }
-      radius = fmin(kMaxRadius, radius * rcp_normal(f));           // f in [1/3, 2]
-      inv_radius = fmax(1.0 / kMaxRadius, inv_radius * f);
-      decrease_factor = 2.0; reuse_diagonal = false;
-      min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
-      if (it >= P.max_inner) return;
-      if (gmax <= kGradientTol) return;
-    } else {
-      radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-      min_cost = fmin(min_cost, cand_cost); sum.final_cost = min_cost;
-      if (it >= P.max_inner) return;
-      if (radius <= kMinRadius) return;
+      min_cost = x_cost;
+      sum.final_cost = min_cost;
+      if (fmax(fabs(evc.g[0]), fmax(fabs(evc.g[1]), fabs(evc.g[2]))) <= kGradientTol) { stop = true; continue; }
+    } else {                                                            // the candidate of iteration `it` has been evaluated
+      const double cand_cost = evc.cost;
+      // parameter tolerance |delta| <= tol (|x| + tol): the square roots are only taken when the squares come close
+      const double step_n2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
+      if (step_n2 <= 4.0 * kParameterTol * kParameterTol * (x_n2 + kParameterTol * kParameterTol)) {      // (a+b)^2 <= 2a^2+2b^2, doubled again
+        if (sqrt(step_n2) <= kParameterTol * (sqrt(x_n2) + kParameterTol)) { stop = true; continue; }
+      }
+      const double cost_change = x_cost - cand_cost;
+      if (fabs(cost_change) <= kFunctionTol * x_cost) { stop = true; continue; }
+      const double rel = cost_change * inv_model_change;
+      sum.n_iterations++; sum.last_rel = rel;
+      if (rel > kMinRelDecrease) {
+        x[0] = xc[0]; x[1] = xc[1]; x[2] = xc[2];
+        x_n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+        store_accepted(sh, evc);
+        x_cost = evc.cost;
+        const double gmax = fmax(fabs(evc.g[0]), fmax(fabs(evc.g[1]), fabs(evc.g[2])));
+        // radius /= max(1/3, 1 - (2 rel - 1)^3).  A step with rel >= 0.94 has (2 rel - 1)^3 > 2/3, i.e. the maximum picks
+        // 1/3 whatever the last bits of rel are: that case needs neither the quotient nor the cube.
+        double f = 1.0 / 3.0;
+        if (!(cost_change >= 0.94 * model_change)) { const double t = 2.0 * rel - 1.0; f = fmax(1.0 / 3.0, 1.0 - t * t * t); }
+        radius = fmin(kMaxRadius, radius * rcp_normal(f));           // f in [1/3, 2]
+        inv_radius = fmax(1.0 / kMaxRadius, inv_radius * f);
+        decrease_factor = 2.0; reuse_diagonal = false;
+        min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
+        if (it >= P.max_inner || gmax <= kGradientTol) { stop = true; continue; }
+      } else {
+        radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        min_cost = fmin(min_cost, cand_cost); sum.final_cost = min_cost;
+        if (it >= P.max_inner || radius <= kMinRadius) { stop = true; continue; }
+      }
+    }
+    // the next candidate: linear solves until a valid step comes out (an invalid one shrinks the radius and counts as an iteration)
+    for (;;) {
+      ++it;
+      const double* aH = sh->acc_H; const double* ag = sh->acc_g;
+      const double Hs[6] = {aH[0] * scale[0] * scale[0], aH[1] * scale[0] * scale[1], aH[2] * scale[0] * scale[2],
+                            aH[3] * scale[1] * scale[1], aH[4] * scale[1] * scale[2], aH[5] * scale[2] * scale[2]};
+      const double gs[3] = {ag[0] * scale[0], ag[1] * scale[1], ag[2] * scale[2]};
+      if (!reuse_diagonal) {
+        diag[0] = fmin(fmax(Hs[0], kMinDiag), kMaxDiag);
+        diag[1] = fmin(fmax(Hs[3], kMinDiag), kMaxDiag);
+        diag[2] = fmin(fmax(Hs[5], kMinDiag), kMaxDiag);
+      }
+      const double A[6] = {Hs[0] + diag[0] * inv_radius, Hs[1], Hs[2], Hs[3] + diag[1] * inv_radius, Hs[4], Hs[5] + diag[2] * inv_radius};
+      double y[3];
+      const double nb[3] = {-gs[0], -gs[1], -gs[2]};
+#ifdef CFEAR_K5_CHOL
+      const bool ok = chol3_solve(A, nb, y);
+#else
+      const bool ok = adj3_solve(A, nb, y);
+#endif
+      reuse_diagonal = true;
+      model_change = 0.0;
+      if (ok) {
+        const double Hy0 = Hs[0] * y[0] + Hs[1] * y[1] + Hs[2] * y[2];
+        const double Hy1 = Hs[1] * y[0] + Hs[3] * y[1] + Hs[4] * y[2];
+        const double Hy2 = Hs[2] * y[0] + Hs[4] * y[1] + Hs[5] * y[2];
+        model_change = -(y[0] * gs[0] + y[1] * gs[1] + y[2] * gs[2]) - 0.5 * (y[0] * Hy0 + y[1] * Hy1 + y[2] * Hy2);
+      }
+      if (!ok || !(model_change > 0.0)) {
+        if (++invalid_in_a_row >= 5) { sum.usable = false; stop = true; break; }
+        radius /= decrease_factor; inv_radius *= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        sum.n_iterations++; sum.last_rel = 0.0;
+        min_cost = fmin(min_cost, x_cost); sum.final_cost = min_cost;
+        if (it >= P.max_inner || radius <= kMinRadius) { stop = true; break; }
+        continue;
+      }
+      invalid_in_a_row = 0;
+      delta[0] = y[0] * scale[0]; delta[1] = y[1] * scale[1]; delta[2] = y[2] * scale[2];
+      xc[0] = x[0] + delta[0]; xc[1] = x[1] + delta[1]; xc[2] = x[2] + delta[2];
+      inv_model_change = rcp_normal(model_change);       // model_change > 0; off the chain that follows the evaluation
+      break;
     }
   }
 }
@@ -522,11 +506,23 @@ struct GridView { const uint16_t* gs; const float4* gp; };
 // are taken four at a time through one flattened index (four independent loads in flight), and the running minimum
 // is a single 64-bit key  d2 bits : cell index : position  whose unsigned order is exactly "smaller distance, then
 // smaller cell index" (d2 >= 0, so its bit pattern is monotonic).
-__device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, double radius, uint32_t* nrm16) {
+// The acceptance test of pointnormal.cpp:250, (double)d2 < radius * radius with d2 a float, as a float comparison: d2 < T
+// with T the smallest float >= radius^2 (any float below T is below radius^2, and T itself is not).
+struct NNRadius { float rq, thr; };
+__device__ __forceinline__ NNRadius nn_radius(double radius) {
+  NNRadius r;
+  r.rq = (float)radius * 1.0001f + 1e-3f;                   // bucket-range margin only
+  const double r2 = radius * radius;
+  float t = (float)r2;
+  if ((double)t < r2) t = __uint_as_float(__float_as_uint(t) + 1u);      // next float up (r2 > 0, finite)
+  r.thr = t;
+  return r;
+}
+__device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, double pxd, double pyd, NNRadius rad, uint32_t* nrm16) {
   const float qx = (float)pxd, qy = (float)pyd;             // pointnormal.cpp:241-242
-  const float rq = (float)radius * 1.0001f + 1e-3f;         // bucket-range margin only
-  int bx0 = (int)floorf((qx - rq - G.ox) * G.inv_g), bx1 = (int)floorf((qx + rq - G.ox) * G.inv_g);
-  int by0 = (int)floorf((qy - rq - G.oy) * G.inv_g), by1 = (int)floorf((qy + rq - G.oy) * G.inv_g);
+  const float rq = rad.rq;
+  int bx0 = __float2int_rd((qx - rq - G.ox) * G.inv_g), bx1 = __float2int_rd((qx + rq - G.ox) * G.inv_g);
+  int by0 = __float2int_rd((qy - rq - G.oy) * G.inv_g), by1 = __float2int_rd((qy + rq - G.oy) * G.inv_g);
   bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, G.nx - 1); by1 = min(by1, G.ny - 1);
   *nrm16 = 0;
   if (bx0 > bx1) return -1;
@@ -559,7 +555,7 @@ __device__ __forceinline__ int nn_query(const GridView& V, const NNGrid& G, doub
   const float bd2 = __uint_as_float((uint32_t)(best >> 32));
   const int besti = (int)((best >> 16) & 0xffffu);
   *nrm16 = __float_as_uint(V.gp[(int)(best & 0xffffu)].w);
-  if ((double)bd2 < radius * radius) return besti;          // pointnormal.cpp:250
+  if (bd2 < rad.thr) return besti;                          // pointnormal.cpp:250
   return -1;
 }
 
@@ -595,6 +591,7 @@ struct AssocCtx {
   const double2* src_normal;  //         else the pool's arrays
   double x[3], cs_s, sn_s;    // pose of the current scan
   double radius;              // association radius of this outer iteration
+  NNRadius nnr;               // its float forms (nn_radius)
 };
 
 // Relative transform Ttar^-1 * Tsrc of pair (keyframe i): rotation (rc, rs) and translation (tx, ty).   n_scan_normal.cpp:224
@@ -688,7 +685,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
 #ifdef CFEAR_K5_PROFILE
       const long long tq1 = clock64() + (long long)(__double_as_longlong(qx) & 0);               // after the transform
 #endif
-      const int m = nn_query(C.view[i], C.grid[i], qx, qy, C.radius, &n16);                       // :241
+      const int m = nn_query(C.view[i], C.grid[i], qx, qy, C.nnr, &n16);                          // :241
 #ifdef CFEAR_K5_PROFILE
       const long long tq2 = clock64() + (long long)(m & 0);
       prof[13] += tq1 - tq0; prof[14] += tq2 - tq1; prof[16] += 1;
@@ -699,7 +696,10 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
         valid = normal_gate(ntx, nty, n16, P.pool.normal + (size_t)C.slots[i] * P.pool.max_cells + m, angle_outlier);   // :246-247
       }
       s_nn[u] = valid ? (uint16_t)m : K5_NONE;
-      if constexpr (AUX) { if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1; }
+      if constexpr (AUX) {                     // tables of THIS pass: pairs an earlier pass accepted and this one does not are cleared
+        if (assoc) assoc[(size_t)i * P.pool.max_cells + j] = valid ? m : -1;
+        if (assoc_sim) assoc_sim[(size_t)i * P.pool.max_cells + j] = 0.0;
+      }
 #ifdef CFEAR_K5_PROFILE
       prof[15] += clock64() - tq2;
 #endif
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   int32_t* assoc = (AUX && P.assoc) ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   double* assoc_sim = (AUX && P.assoc_sim) ? P.assoc_sim + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   constexpr int per_block = (COST == 1) ? 1 : 2;
-  const bool w0 = warp_id() == 0;              // the warp that runs the scalar solver logic (see "evaluation service")
+  const bool w0 = warp_id() == 0;              // the warp that runs the scalar solver logic (see eval_round / lm_solve)
   LMShared* sh = &s_lm;
 
   // association at pose x for outer iteration itr (radius doubled on the first, n_scan_normal.cpp:222)
@@ -928,6 +928,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     C.x[0] = x[0]; C.x[1] = x[1]; C.x[2] = x[2];
     sincos(x[2], &C.sn_s, &C.cs_s);
     C.radius = (itr == 1) ? 2 * P.radius : P.radius;
+    C.nnr = nn_radius(C.radius);
     const int n = build_problem<COST, AUX>(P, C, res, assoc, assoc_sim, s_warp, s_nn, s_list, tile PROF_ARG);
     if (overlay) grids_resident = false;
     PROF_T(ta2);
@@ -936,8 +937,7 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   };
 
   SolveSum sum; sum.final_cost = 0.0; sum.n_iterations = 0; sum.last_rel = 0.0; sum.usable = true;
-  double lastH[6] = {0, 0, 0, 0, 0, 0};        // warp 0: J^T J at x from the last solve; valid while have_H (block-uniform)
-  bool have_H = false;
+  bool have_H = false;                         // LMShared::acc_H holds J^T J at x (block-uniform)
   bool success = true, pose_written = false;
   int inner_total = 0, nres = 0, outer = 0;
   if (AUX && P.solver_mode == 2) {
@@ -948,14 +948,10 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     outer = 0;
     if (nres * per_block <= 1) success = false;                                 // :205-208
     else {
-      if (w0) {
-        EvalOut ev;
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-        if (lane_id() == 0) sh->out_final_cost = ev.cost;
-        finish_evals(sh);
-      } else {
-        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
-      }
+      EvalOut ev;
+      eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+      if (tid == 0) sh->out_final_cost = ev.cost;
+      __syncthreads();
       sum.final_cost = sh->out_final_cost;
       __syncthreads();
     }
@@ -965,18 +961,18 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     for (it = 1; it <= P.gn_iters; ++it) {
       nres = associate(it);
       if (nres * per_block <= 1) { success = false; break; }
-      if (w0) {
+      {
         EvalOut ev;
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-        double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
-        const bool ok = chol3_solve(ev.H, nb, y);
-        if (lane_id() == 0) {
-          sh->out_success = ok ? 1 : 0; sh->out_final_cost = ev.cost;
-          sh->out_x[0] = x[0] + (ok ? y[0] : 0.0); sh->out_x[1] = x[1] + (ok ? y[1] : 0.0); sh->out_x[2] = x[2] + (ok ? y[2] : 0.0);
+        eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+        if (w0) {
+          double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
+          const bool okw = chol3_solve(ev.H, nb, y);
+          if (lane_id() == 0) {
+            sh->out_success = okw ? 1 : 0; sh->out_final_cost = ev.cost;
+            sh->out_x[0] = x[0] + (okw ? y[0] : 0.0); sh->out_x[1] = x[1] + (okw ? y[1] : 0.0); sh->out_x[2] = x[2] + (okw ? y[2] : 0.0);
+          }
         }
-        finish_evals(sh);
-      } else {
-        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+        __syncthreads();
       }
       const bool ok = sh->out_success != 0;
       x[0] = sh->out_x[0]; x[1] = sh->out_x[1]; x[2] = sh->out_x[2];
@@ -988,14 +984,10 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
     }
     outer = it;
     if (success) {
-      if (w0) {
-        EvalOut ev;
-        request_eval<COST, LOSS>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-        if (lane_id() == 0) sh->out_final_cost = ev.cost;
-        finish_evals(sh);
-      } else {
-        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
-      }
+      EvalOut ev;
+      eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+      if (tid == 0) sh->out_final_cost = ev.cost;
+      __syncthreads();
       sum.final_cost = sh->out_final_cost;
       __syncthreads();
     }
@@ -1026,17 +1018,13 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
       PROF_T(ts0);
       const double x_in[3] = {x[0], x[1], x[2]};
-      if (w0) {
-        lm_solve<COST, LOSS, AUX>(P, res, nres, x, sum, sh, s_part, lastH PROF_ARG);    // :117
-        if (lane_id() == 0) {
-          sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
-          sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
-          sh->out_niter = sum.n_iterations; sh->out_usable = sum.usable ? 1 : 0;
-        }
-        finish_evals(sh);
-      } else {
-        serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
+      lm_solve<COST, LOSS, AUX>(P, res, nres, w0, x, sum, sh, s_part PROF_ARG);          // :117
+      if (tid == 0) {
+        sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
+        sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
+        sh->out_niter = sum.n_iterations; sh->out_usable = sum.usable ? 1 : 0;
       }
+      __syncthreads();
       x[0] = sh->out_x[0]; x[1] = sh->out_x[1]; x[2] = sh->out_x[2];
       sum.final_cost = sh->out_final_cost; sum.last_rel = sh->out_last_rel;
       sum.n_iterations = sh->out_niter; sum.usable = sh->out_usable != 0;
@@ -1076,15 +1064,14 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
   } else if (success) {
     st.score = sum.final_cost / st.num_residuals;                               // :166
     cov[0] = 0.01; cov[7] = 0.01; cov[35] = 0.0001;                             // :171-175
-    if (w0) {
-      EvalOut ev;                                                               // GetCovariance :392-433
-      if (have_H) {                            // the last solve ended at x: its normal equations are the ones wanted
+    EvalOut ev;                                                                 // GetCovariance :392-433
+    if (have_H) {                              // the last solve ended at x: its normal equations are the ones wanted
 #pragma unroll
-        for (int i = 0; i < 6; ++i) ev.H[i] = lastH[i];
-      } else {
-        request_eval<COST, LOSS, AUX>(P.loss_limit, res, nres, x, ev, sh, s_part PROF_ARG);
-        finish_evals(sh);
-      }
+      for (int i = 0; i < 6; ++i) ev.H[i] = sh->acc_H[i];
+    } else {                                   // (block-uniform) one more round at the restored pose
+      eval_round<COST, LOSS, AUX>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+    }
+    if (w0) {
       double inv[9]; bool ok = true;
       for (int c = 0; c < 3 && ok; ++c) {
         double e[3] = {0, 0, 0}, y[3]; e[c] = 1.0;
@@ -1100,8 +1087,6 @@ __global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_regis
         cov[35] = f * inv[8]; cov[5] = f * inv[2]; cov[30] = f * inv[6];
         st.success = 1;
       }
-    } else if (!have_H) {
-      serve_evals<COST, LOSS>(P.loss_limit, res, nres, sh, s_part);
     }
   }
   if (tid == 0) {
