@@ -114,7 +114,7 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
 #ifndef CFEAR_NN_CELL
-#define CFEAR_NN_CELL 8.0f             // bucket size (metres) of the nearest-neighbour grid over a cell set's means
+#define CFEAR_NN_CELL 4.0f             // bucket size (metres) of the nearest-neighbour grid over a cell set's means: 4 m -> K5 0.343 ms, 6 m 0.349, 8 m 0.353 (profiles/r02m_nn_cell_ab.txt)
 #endif
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
 constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 4)

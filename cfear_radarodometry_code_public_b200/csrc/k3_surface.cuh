@@ -36,7 +36,7 @@ namespace cfear {
 #endif
 constexpr int K3_THREADS = CFEAR_K3_THREADS;
 #ifndef CFEAR_K3_LPC
-#define CFEAR_K3_LPC 4
+#define CFEAR_K3_LPC 2
 #endif
 constexpr int K3_LANES_PER_CENTROID = CFEAR_K3_LPC;   // 8 -> 4: 0.164 -> 0.142 ms (fixed cost per centroid amortised over twice as many per warp); 2: 0.140, 1: 0.160, 16: 0.218
 constexpr int K3_HIST_CAP = 16384;        // voxel / NN-grid bins kept in shared memory

@@ -22,9 +22,12 @@
 namespace cfear {
 
 #ifndef CFEAR_K5_THREADS
-#define CFEAR_K5_THREADS 192
+#define CFEAR_K5_THREADS 128
 #endif
-constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 6 warps per problem, 2 problems resident per SM, 168 registers
+constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, 2 problems resident per SM (shared memory), 202 registers, no spills.
+                                               // Alone 192 threads (168 registers) are as fast (0.343 vs 0.347 ms / 256 problems); with four steps in
+                                               // flight the smaller CTA leaves registers for a K1 CTA beside two K5 CTAs: 0.356 vs 0.370 ms per step
+                                               // (96: 0.382, 64: 0.422, 256: 0.375; capped at 168 registers: 0.369 -- profiles/r02q_k5_threads_ab.txt)
 constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
 constexpr int K5_SMEM_BYTES = 106 * 1024;   // dynamic smem per CTA (2 CTAs + 6 KB static each fit the 228 KB of an SM)
@@ -820,8 +823,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // AUX = false: the ceres_lm solver only (the product path).  AUX = true: the two auxiliary modes -- gn_fixed and cost
 // only -- which live in their own instantiation so that their code does not cost the main kernel registers.
+#ifndef CFEAR_K5_MINBLOCKS
+#define CFEAR_K5_MINBLOCKS (K5_THREADS > 256 ? 1 : 2)
+#endif
 template <int COST, int LOSS, bool AUX>
-__global__ void __launch_bounds__(K5_THREADS, K5_THREADS > 256 ? 1 : 2) k5_register(const RegParams P) {
+__global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ double s_part[K5_WARPS * 10];
