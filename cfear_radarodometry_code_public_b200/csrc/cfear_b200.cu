@@ -477,6 +477,20 @@ static int begin_timed_step(cfear_ctx* c) {
   return CFEAR_OK;
 }
 
+// Stream-ordered temporaries that are released on every exit path of an entry point (CK / RC return early on errors).
+struct TempBufs {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit TempBufs(cudaStream_t s) : stream(s) {}
+  template <typename T> cudaError_t get(T** p, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(bytes, 1), stream);
+    if (e == cudaSuccess) { ptrs.push_back(q); *p = reinterpret_cast<T*>(q); }
+    return e;
+  }
+  ~TempBufs() { for (void* q : ptrs) cudaFreeAsync(q, stream); }
+};
+
 static int check_slot(cfear_ctx* c, int slot) {
   if (slot < 0 || slot >= c->cfg.max_cellsets) { g_err = "cell-set slot out of range"; return CFEAR_ERR_ARG; }
   return CFEAR_OK;
@@ -640,16 +654,15 @@ int cfear_nearest(cfear_ctx* c, int slot, const double* queries_xy, int nq, doub
   RC(check_slot(c, slot));
   if (nq < 0 || (nq > 0 && (!queries_xy || !out_idx))) { g_err = "bad queries"; return CFEAR_ERR_ARG; }
   if (nq == 0) return CFEAR_OK;
+  TempBufs tmp(c->stream);
   double* dq = nullptr; int32_t* dout = nullptr;
-  CK(cudaMallocAsync(&dq, (size_t)nq * 2 * sizeof(double), c->stream));
-  CK(cudaMallocAsync(&dout, (size_t)nq * sizeof(int32_t), c->stream));
+  CK(tmp.get(&dq, (size_t)nq * 2 * sizeof(double)));
+  CK(tmp.get(&dout, (size_t)nq * sizeof(int32_t)));
   CK(cudaMemcpyAsync(dq, queries_xy, (size_t)nq * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   k4b_nearest<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->pool, slot, dq, nq, radius, dout);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_idx, dout, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaFreeAsync(dq, c->stream));
-  CK(cudaFreeAsync(dout, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return CFEAR_OK;
 }
@@ -989,11 +1002,12 @@ int cfear_cfar_filter(cfear_ctx* c, const uint8_t* polar, int nscans, const cfea
   if (nscans == 0) return CFEAR_OK;
   const int A = c->cfg.azimuths, R = c->cfg.range_bins;
   const size_t rows = (size_t)nscans * A;
+  TempBufs tmp(c->stream);
   int32_t *d_cnt = nullptr, *d_off = nullptr, *d_n = nullptr; float4* d_out = nullptr;
-  CK(cudaMallocAsync(&d_cnt, rows * 4, c->stream));
-  CK(cudaMallocAsync(&d_off, rows * 4, c->stream));
-  CK(cudaMallocAsync(&d_n, (size_t)nscans * 4, c->stream));
-  CK(cudaMallocAsync(&d_out, std::max<size_t>((size_t)nscans * capacity_per_scan, 1) * sizeof(float4), c->stream));
+  CK(tmp.get(&d_cnt, rows * 4));
+  CK(tmp.get(&d_off, rows * 4));
+  CK(tmp.get(&d_n, (size_t)nscans * 4));
+  CK(tmp.get(&d_out, (size_t)nscans * capacity_per_scan * sizeof(float4)));
   c->polar_dirty = true;
   CK(cudaMemcpyAsync(c->d_polar, polar, rows * R, cudaMemcpyHostToDevice, c->stream));
   CfarParams p;
@@ -1020,7 +1034,6 @@ int cfear_cfar_filter(cfear_ctx* c, const uint8_t* polar, int nscans, const cfea
     for (int i = 0; i < nscans; ++i)
       CK(cudaMemcpyAsync(cloud_out + (size_t)i * capacity_per_scan, d_out + (size_t)i * capacity_per_scan,
                          (size_t)npts_out[i] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaFreeAsync(d_cnt, c->stream)); CK(cudaFreeAsync(d_off, c->stream)); CK(cudaFreeAsync(d_n, c->stream)); CK(cudaFreeAsync(d_out, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return rc;
 }

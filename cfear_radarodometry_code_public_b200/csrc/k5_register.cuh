@@ -30,7 +30,10 @@ constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, 2 problem
                                                // (96: 0.382, 64: 0.422, 256: 0.375; capped at 168 registers: 0.369 -- profiles/r02q_k5_threads_ab.txt)
 constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
-constexpr int K5_SMEM_BYTES = 106 * 1024;   // dynamic smem per CTA (2 CTAs + 6 KB static each fit the 228 KB of an SM)
+#ifndef CFEAR_K5_SMEM_KB
+#define CFEAR_K5_SMEM_KB 106
+#endif
+constexpr int K5_SMEM_BYTES = CFEAR_K5_SMEM_KB * 1024;   // dynamic smem per CTA (2 CTAs + 6 KB static each fit the 228 KB of an SM)
 
 struct RegParams {
   CellPool pool;
