@@ -114,7 +114,9 @@ __global__ void k_cells_scatter(CellPool pool, int slot, const CellAoS* in, int 
 static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
 
 #ifndef CFEAR_NN_CELL
-#define CFEAR_NN_CELL 4.0f             // bucket size (metres) of the nearest-neighbour grid over a cell set's means: 4 m -> K5 0.343 ms, 6 m 0.349, 8 m 0.353 (profiles/r02m_nn_cell_ab.txt)
+#define CFEAR_NN_CELL 6.0f             // bucket size (metres) of the nearest-neighbour grid over a cell set's means: the finest whose four keyframe grids
+                                       // still fit K5's shared memory at three CTAs per SM (4 m is 3 % faster per CTA but needs two CTAs per SM;
+                                       // profiles/r02m_nn_cell_ab.txt, profiles/r02v_k5_three_per_sm_ab.txt)
 #endif
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
 constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 4)
@@ -266,7 +268,12 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   CKC(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   // (the CA-CFAR kernel's shared-memory attribute is set by cfear_cfar_filter, which is the only place that needs it)
-  c->k5_smem = std::min(K5_SMEM_BYTES, (max_optin - 4096) / 2);
+  {   // K5: K5_MINBLOCKS CTAs per SM, each with 1 KB reserved by the system and ~1 KB of static shared memory
+    int per_sm = 0;
+    CKC(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
+    const int fit = per_sm / K5_MINBLOCKS - 2048;
+    c->k5_smem = std::min(K5_SMEM_BYTES > 0 ? K5_SMEM_BYTES : fit, max_optin - 1024);
+  }
   CKC(k5_set_smem_cost0(c->k5_smem)); CKC(k5_set_smem_cost1(c->k5_smem)); CKC(k5_set_smem_cost2(c->k5_smem));
 
   const size_t rows = (size_t)B * A;

@@ -24,16 +24,21 @@ namespace cfear {
 #ifndef CFEAR_K5_THREADS
 #define CFEAR_K5_THREADS 128
 #endif
-constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, 2 problems resident per SM (shared memory), 202 registers, no spills.
-                                               // Alone 192 threads (168 registers) are as fast (0.343 vs 0.347 ms / 256 problems); with four steps in
-                                               // flight the smaller CTA leaves registers for a K1 CTA beside two K5 CTAs: 0.356 vs 0.370 ms per step
-                                               // (96: 0.382, 64: 0.422, 256: 0.375; capped at 168 registers: 0.369 -- profiles/r02q_k5_threads_ab.txt)
+constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, THREE problems resident per SM: 168 registers (no spills) and 74 KB of
+                                               // shared memory per CTA (50-byte residual records, per-scan tables sized by the problem, 6 m NN grid).
+                                               // A CTA alone is slower than the 2-per-SM forms (0.381 ms / 256 problems vs 0.343 for 192 threads,
+                                               // 0.347 for 128 threads with 202 registers), but with four steps in flight the step takes 0.337 ms
+                                               // instead of 0.370 / 0.356 (profiles/r02q_k5_threads_ab.txt, profiles/r02v_k5_three_per_sm_ab.txt)
 constexpr int K5_WARPS = K5_THREADS / 32;
+#ifndef CFEAR_K5_MINBLOCKS
+#define CFEAR_K5_MINBLOCKS (CFEAR_K5_THREADS > 256 ? 1 : (CFEAR_K5_THREADS > 128 ? 2 : 3))
+#endif
+constexpr int K5_MINBLOCKS = CFEAR_K5_MINBLOCKS;   // resident CTAs per SM the register and shared-memory budgets are set for
 constexpr int K5_MAXSCANS = 65;      // K+1 <= 65
 #ifndef CFEAR_K5_SMEM_KB
-#define CFEAR_K5_SMEM_KB 106
+#define CFEAR_K5_SMEM_KB 0                     // 0: what lets CFEAR_K5_MINBLOCKS CTAs share an SM (cfear_create)
 #endif
-constexpr int K5_SMEM_BYTES = CFEAR_K5_SMEM_KB * 1024;   // dynamic smem per CTA (2 CTAs + 6 KB static each fit the 228 KB of an SM)
+constexpr int K5_SMEM_BYTES = CFEAR_K5_SMEM_KB * 1024;   // dynamic smem per CTA
 
 struct RegParams {
   CellPool pool;
@@ -121,13 +126,20 @@ __device__ __forceinline__ void loss_eval(double a, double s, double rho[3]) {
 
 struct EvalOut { double cost, H[6], g[3]; };
 
-// Residual list of one problem, SoA of double2 fields (p), (q), (a,b), (c,w): the first cap_s entries live in
-// shared memory, the overflow in the problem's global scratch.
+// Residual list of one problem: per accepted correspondence the world-frame target q, the cost's constants (a, b) and
+// (c, w) -- three double2 fields, SoA -- and the index j of its source cell (16 bits); the source mean p is read through
+// the index from the source set's means (a shared-memory copy in the normal case), so a record takes 50 bytes instead of
+// 64.  The first cap_s entries live in shared memory, the overflow in the problem's global scratch.
 struct ResList {
-  double2* s; int cap_s;       // shared part: field f at s + f*cap_s
-  double2* g; int cap_g;       // global part: field f at g + f*cap_g (indexed by the residual's global position)
+  double2* s; uint16_t* sj; int cap_s;     // shared part: field f (0 q, 1 ab, 2 cw) at s + f*cap_s, source index at sj
+  double2* g; uint16_t* gj; int cap_g;     // global part: field f at g + f*cap_g, source index at gj (indexed by the residual's global position)
+  const double2* src_mean;                 // p of residual r = src_mean[j(r)]
   __device__ __forceinline__ double2 ld(int f, int r) const { return r < cap_s ? s[f * cap_s + r] : g[(size_t)f * cap_g + r]; }
-  __device__ __forceinline__ void st(int f, int r, double2 v) const { if (r < cap_s) s[f * cap_s + r] = v; else g[(size_t)f * cap_g + r] = v; }
+  __device__ __forceinline__ double2 ldp(int r) const { return src_mean[r < cap_s ? sj[r] : gj[r]]; }
+  __device__ __forceinline__ void st(int r, int j, double2 q, double2 ab, double2 cw) const {
+    if (r < cap_s) { s[r] = q; s[cap_s + r] = ab; s[2 * cap_s + r] = cw; sj[r] = (uint16_t)j; }
+    else { g[r] = q; g[(size_t)cap_g + r] = ab; g[2 * (size_t)cap_g + r] = cw; gj[r] = (uint16_t)j; }
+  }
 };
 // -DCFEAR_K5_PROFILE: clock64 probes (thread 0's view), reported through unused covariance slots; profiles/ab_stage.py --prof
 #ifdef CFEAR_K5_PROFILE
@@ -259,24 +271,27 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
   int r = threadIdx.x;
   if (nres <= res.cap_s) {                   // the whole list is in shared memory (the normal case): no per-load path select
-    const double2* f0 = res.s, * f1 = res.s + res.cap_s, * f2 = res.s + 2 * res.cap_s, * f3 = res.s + 3 * res.cap_s;
+    const double2* f1 = res.s, * f2 = res.s + res.cap_s, * f3 = res.s + 2 * res.cap_s;
+    const uint16_t* fj = res.sj; const double2* sm = res.src_mean;
     for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
       const int r2 = r + K5_THREADS;
-      const double2 p0 = f0[r], q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
-      const double2 p1 = f0[r2], q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
+      const int j0 = fj[r], j1 = fj[r2];
+      const double2 q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
+      const double2 q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
+      const double2 p0 = sm[j0], p1 = sm[j1];
       accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
       accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
     }
-    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, f0[r], f1[r], f2[r], f3[r], acc);
+    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, sm[fj[r]], f1[r], f2[r], f3[r], acc);
   } else {
     for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
       const int r2 = r + K5_THREADS;
-      const double2 p0 = res.ld(0, r), q0 = res.ld(1, r), ab0 = res.ld(2, r), cw0 = res.ld(3, r);
-      const double2 p1 = res.ld(0, r2), q1 = res.ld(1, r2), ab1 = res.ld(2, r2), cw1 = res.ld(3, r2);
+      const double2 p0 = res.ldp(r), q0 = res.ld(0, r), ab0 = res.ld(1, r), cw0 = res.ld(2, r);
+      const double2 p1 = res.ldp(r2), q1 = res.ld(0, r2), ab1 = res.ld(1, r2), cw1 = res.ld(2, r2);
       accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
       accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p1, q1, ab1, cw1, acc);
     }
-    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ld(0, r), res.ld(1, r), res.ld(2, r), res.ld(3, r), acc);
+    if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, res.ldp(r), res.ld(0, r), res.ld(1, r), res.ld(2, r), acc);
   }
   warp_reduce10(acc, s_part + warp_id() * 10);
 }
@@ -736,8 +751,7 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
         have[h] = r < total;
         const int u = have[h] ? s_list[r] : s_list[r0];
         const int t = t0 + u, i = t / n_src, j = t - i * n_src;
-        ii[h] = i;
-        if constexpr (AUX) jj[h] = j;
+        ii[h] = i; jj[h] = j;
         const size_t sb = C.sbase + j;
         const size_t tb = (size_t)C.slots[i] * P.pool.max_cells + s_nn[u];
         // everything the record may need is requested at once: one L2 round trip for both pairs
@@ -759,7 +773,8 @@ __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx&
           double2 rp, rq, rab, rcw;
           make_record<COST>(P, R, sim, mu[h], tm[h], ntar[h], Cv[h], n1[h], n2[h], p1[h], p2[h], rp, rq, rab, rcw);
           const int pos = nres + r;
-          if (pos < cap) { res.st(0, pos, rp); res.st(1, pos, rq); res.st(2, pos, rab); res.st(3, pos, rcw); }
+          (void)rp;                                    // the source mean is re-read through its index (ResList)
+          if (pos < cap) res.st(pos, jj[h], rq, rab, rcw);
         }
       }
     }
@@ -826,19 +841,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // AUX = false: the ceres_lm solver only (the product path).  AUX = true: the two auxiliary modes -- gn_fixed and cost
 // only -- which live in their own instantiation so that their code does not cost the main kernel registers.
-#ifndef CFEAR_K5_MINBLOCKS
-#define CFEAR_K5_MINBLOCKS (K5_THREADS > 256 ? 1 : 2)
-#endif
 template <int COST, int LOSS, bool AUX>
 __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ double s_part[K5_WARPS * 10];
   __shared__ LMShared s_lm;
-  __shared__ double s_pose[K5_MAXSCANS * 5];
-  __shared__ NNGrid s_grid[K5_MAXSCANS];
-  __shared__ GridView s_view[K5_MAXSCANS];
-  __shared__ int32_t s_slots[K5_MAXSCANS];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_grid_bytes;
 
@@ -856,6 +864,13 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
     }
     return;
   }
+  // per-scan tables (pose + cos / sin, NN grid header, grid view, slot) at the start of the dynamic allocation, sized by
+  // the problem's scan count (a static array for the 65 scans the ABI allows would take 5.4 KB from every CTA)
+  double* s_pose = reinterpret_cast<double*>(dyn_smem);                         // [ns][5]
+  NNGrid* s_grid = reinterpret_cast<NNGrid*>(s_pose + 5 * ns);                  // [ns]
+  GridView* s_view = reinterpret_cast<GridView*>(s_grid + ns);                  // [ns]
+  int32_t* s_slots = reinterpret_cast<int32_t*>(s_view + ns);                   // [ns]
+  const uint32_t tab_bytes = (uint32_t)((ns * (40 + sizeof(NNGrid) + sizeof(GridView) + 4) + 127) & ~127u);
   if (tid < ns) {
     const int sl = P.slots[(size_t)prob * stride + tid];
     s_slots[tid] = sl;
@@ -868,7 +883,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
 
-  // Shared-memory plan:  [ s_nn | s_list | source means, normals | U ]  with U = the rest of the dynamic allocation.
+  // Shared-memory plan:  [ tables | s_nn | s_list | source means, normals | U ]  with U = the rest of the dynamic allocation.
   //  * problems whose pairs fit one tile (the normal case) OVERLAY U: during association it holds the keyframes' NN
   //    grids, during the LM solve the residual list (written there directly by phase 2 of the association); the grids
   //    are re-staged from L2 by TMA at the start of the next outer iteration.  Every evaluation of the solve -- the
@@ -883,9 +898,9 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
   const int npairs = K * C.n_src;
   const int tile = min(max((npairs + 7) & ~7, 8), K5_TILE_MAX);
   const bool overlay = npairs <= K5_TILE_MAX;
-  uint16_t* s_nn = reinterpret_cast<uint16_t*>(dyn_smem);
+  uint16_t* s_nn = reinterpret_cast<uint16_t*>(dyn_smem + tab_bytes);
   uint16_t* s_list = s_nn + tile;
-  uint32_t u_off = (uint32_t)((tile * 4 + 127) & ~127);
+  uint32_t u_off = tab_bytes + (uint32_t)((tile * 4 + 127) & ~127);
   // the source cells' means and normals (read by every pair of every association pass) are copied to shared memory
   // once when they take at most a quarter of the allocation
   C.src_mean = P.pool.mean + C.sbase; C.src_normal = P.pool.normal + C.sbase;
@@ -912,11 +927,14 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
   double x[3] = {s_pose[5 * K + 0], s_pose[5 * K + 1], s_pose[5 * K + 2]};
   ResList res;
   res.g = P.res + (size_t)prob * P.res_cap * 4; res.cap_g = P.res_cap;
-  if (overlay) { res.s = reinterpret_cast<double2*>(U); res.cap_s = min((int)(u_room / 64), P.res_cap); }
-  else {
-    const uint32_t g_end = (s_grid_bytes + 127) & ~127u;
-    res.s = reinterpret_cast<double2*>(U + g_end); res.cap_s = min(((int)u_room - (int)g_end) / 64, P.res_cap);
-    if (res.cap_s < 0) res.cap_s = 0;
+  res.gj = reinterpret_cast<uint16_t*>(res.g + 3 * (size_t)P.res_cap);          // the fourth field's storage holds the source indices
+  res.src_mean = C.src_mean;
+  {
+    unsigned char* lbase = U; int room = (int)u_room;
+    if (!overlay) { const uint32_t g_end = (s_grid_bytes + 127) & ~127u; lbase = U + g_end; room = (int)u_room - (int)g_end; }
+    res.cap_s = max(min((room / 50) & ~7, P.res_cap), 0);                       // 3 x 16 B + 2 B per record, field arrays 16-byte aligned
+    res.s = reinterpret_cast<double2*>(lbase);
+    res.sj = reinterpret_cast<uint16_t*>(res.s + 3 * res.cap_s);
   }
   int32_t* assoc = (AUX && P.assoc) ? P.assoc + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
   double* assoc_sim = (AUX && P.assoc_sim) ? P.assoc_sim + (size_t)prob * (stride - 1) * P.pool.max_cells : nullptr;
