@@ -81,6 +81,36 @@ if not a.no_gpu:
                           "residuals_mean": float(gst["num_residuals"].mean())}), flush=True)
         c.close()
 
+# ---- the reference's own execution model: ONE sequence, one scan at a time, through the drop-in classes -----------------
+if not a.no_gpu:
+    import re
+    import subprocess
+    import tempfile
+    from cfear_radarodometry_code_public_b200 import io as cio
+    n = 60
+    imgs, _ = synth.make_sequence(5, n)
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "offline_odometry")
+        pkg = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "offline_odometry.cpp"),
+                               "-o", exe, "-L" + pkg, "-lcfear_b200", "-Wl,-rpath," + pkg])
+        frames = os.path.join(td, "seq.cfrs")
+        cio.write_frames(frames, imgs)
+        out = subprocess.check_output([exe, "--frames", frames, "--est_directory", td, "--cost_type", "P2D", "--res", "3.0", "--submap_scan_size", "4",
+                                       "--z-min", "60", "--weight_option", "4", "--regularization", "0.1"]).decode()
+        dur = np.array([float(x) for x in re.findall(r"dur: ([0-9.eE+-]+)", out)])
+        rows = np.loadtxt(os.path.join(td, "01.txt"))
+    t0 = time.perf_counter()
+    ref = orc.odometry_sequence(imgs, orc.reg_cfg(cost="P2D", weight_opt=4, regularization=0.1), z_min=60, radius=3.0, weight_intensity=True, submap_scan_size=4)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / n
+    d = np.hypot(rows[:, 3] - ref["poses"][:, 0], rows[:, 7] - ref["poses"][:, 1])
+    print(json.dumps({"config": "single sequence, one scan at a time (the reference's execution model): examples/offline_odometry over the C++ mirror "
+                                "(radarDriver::CallbackOffline -> OdometryKeyframeFuser::pointcloudCallback per frame, every call synchronous), "
+                                f"{n} synthetic frames, P2D, window 4",
+                      "ms_per_frame_gpu_median": 1e3 * float(np.median(dur[5:])), "frames_per_s_gpu": 1.0 / float(np.median(dur[5:])),
+                      "ms_per_frame_cpu_oracle_1_thread": cpu_ms, "frames_per_s_cpu_oracle_1_thread": 1e3 / cpu_ms,
+                      "max_pos_diff_vs_oracle_replay_m": float(d.max()), "sensor_rate_hz": 4}), flush=True)
+
 print(json.dumps({"config": "configs[3]: Oxford 2019-01-10-12-32-52 full sequence replay, trajectory diff vs the reference's est/01.txt",
                   "status": "not run: neither the dataset nor the reference's est/01.txt exist in this image (no network)",
                   "how": "python -c 'from cfear_radarodometry_code_public_b200 import io ...load_oxford_png / write_frames' -> examples/offline_odometry "
