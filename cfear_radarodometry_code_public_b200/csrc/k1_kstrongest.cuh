@@ -28,6 +28,7 @@ struct K1Params {
   const uint8_t* polar_end;  // polar + nrows*R
   int nrows;                 // nscans * A
   int A, R;
+  uint32_t A_magic;          // ceil(2^32 / A): row -> azimuth without a division (k1_launch fills it)
   int zmin;                  // already uchar(int(z_min))
   int k;
   int min_range_bin;         // ceil(min_distance / range_res)
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
   __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
   __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
   __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
-  __shared__ uint2 s_queue[K1_WARPS][TILES * 32];      // vectors of one super-tile that hold candidates
+  __shared__ uint2 s_queue[K1_WARPS][TILES * 32 + 2];  // vectors of one super-tile that hold candidates (+ a zero sentinel)
   const int grow = blockIdx.x * K1_WARPS + warp_id();
   if (grow >= p.nrows) return;                 // no block-level sync in this kernel
   const int lane = lane_id();
@@ -124,9 +125,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
 #pragma unroll
       for (int i = 0; i < TILES; ++i) {
         const int v = v0 + i * 32 + lane;
-        // only the first vector of the first row and the last vector of the last row can reach outside the buffer
-        if (ALIGNED || !edge_row) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
-        else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
+        // only the first vector of the first row and the last vector of the last row can reach outside the buffer;
+        // tiles that lie entirely inside the row (warp-uniform test) load without a per-lane predicate
+        if (ALIGNED || !edge_row) {
+          if (ALIGNED && v0 + i * 32 + 32 <= nvec) d[i] = ld_stream16(base + 16 * (size_t)v);
+          else d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
+        } else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int i = 0; i < TILES; ++i) {
@@ -160,10 +164,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
         nq += __popc(bal);
       }
     }
+    if (lane == 0) q[nq] = make_uint2(0u, 0u);   // sentinel: an odd queue drains its last entry beside an empty one
     __syncwarp();
     for (int e = 0; e < nq; e += 2) {
       const uint2 e1 = q[e];
-      const uint2 e2 = (e + 1 < nq) ? q[e + 1] : make_uint2(0u, 0u);
+      const uint2 e2 = q[e + 1];
       const uint32_t mm = hi ? e2.x : e1.x;
       const int c1 = __popc(e1.x);
       if (mm & mybit) {
@@ -245,7 +250,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
   __syncwarp();
 
   // ---- outputs: index set (parity target) + cloud row ---------------------------------------------
-  const int a = grow % p.A;
+  int a = grow - (int)(__umulhi((uint32_t)grow, p.A_magic) * (uint32_t)p.A);     // grow % A (exact while grow * A < 2^32)
+  if ((uint32_t)a >= (uint32_t)p.A) a = grow % p.A;
   const double2 cs = p.cs[a];
   const double half = p.range_res / 2.0;
   int ncloud = 0;
@@ -274,7 +280,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
 
 // Launch with the instantiation the data allows: aligned rows (every row on a 16-byte boundary, no vector straddles a
 // row) and the z_min half (>= 128 or not) are compile-time.
-inline void k1_launch(const K1Params& p, cudaStream_t stream) {
+inline void k1_launch(const K1Params& p_in, cudaStream_t stream) {
+  K1Params p = p_in;
+  p.A_magic = (uint32_t)(0xffffffffull / (unsigned long long)p.A + 1ull);
   const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
   const bool aligned = ((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0;
   const bool zhi = p.zmin >= 128;

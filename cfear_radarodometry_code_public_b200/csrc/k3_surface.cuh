@@ -122,6 +122,29 @@ __device__ __forceinline__ float block_min_f(float v, float* s_red) {
 }
 __device__ __forceinline__ float block_max_f(float v, float* s_red) { return -block_min_f(-v, s_red); }
 
+// Bounding box of the block's points in one reduction: (min x, min y, max x, max y) -- the maxima travel negated, so one
+// min tree serves all four.  s_red4: >= 4 * 32 floats.  Two barriers instead of the eight of four separate reductions.
+__device__ __forceinline__ void block_bounds(float& mnx, float& mny, float& mxx, float& mxy, float* s_red4) {
+  float v0 = mnx, v1 = mny, v2 = -mxx, v3 = -mxy;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 = fminf(v0, __shfl_xor_sync(FULL, v0, d)); v1 = fminf(v1, __shfl_xor_sync(FULL, v1, d));
+    v2 = fminf(v2, __shfl_xor_sync(FULL, v2, d)); v3 = fminf(v3, __shfl_xor_sync(FULL, v3, d));
+  }
+  __syncthreads();
+  if (lane_id() == 0) { float* o = s_red4 + 4 * warp_id(); o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; }
+  __syncthreads();
+  const int nw = (int)(blockDim.x >> 5), l = lane_id();
+  const float4 r = l < nw ? *reinterpret_cast<const float4*>(s_red4 + 4 * l) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
+  v0 = r.x; v1 = r.y; v2 = r.z; v3 = r.w;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 = fminf(v0, __shfl_xor_sync(FULL, v0, d)); v1 = fminf(v1, __shfl_xor_sync(FULL, v1, d));
+    v2 = fminf(v2, __shfl_xor_sync(FULL, v2, d)); v3 = fminf(v3, __shfl_xor_sync(FULL, v3, d));
+  }
+  mnx = v0; mny = v1; mxx = -v2; mxy = -v3;
+}
+
 // Histogram / prefix-sum table with 16-bit entries (counts and offsets are bounded by the points of one scan, <= 65535),
 // two per 32-bit word so that shared-memory atomics can update them: half the footprint of an int table.
 struct Hist16 {
@@ -162,8 +185,7 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
     const float2 p = fm[i];
     mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x); mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
   }
-  mnx = block_min_f(mnx, s_red); mny = block_min_f(mny, s_red);
-  mxx = block_max_f(mxx, s_red); mxy = block_max_f(mxy, s_red);
+  block_bounds(mnx, mny, mxx, mxy, s_red);
   if (n == 0) { mnx = mny = mxx = mxy = 0.f; }
   float g = nn_cell;
   int nx, ny;
@@ -220,7 +242,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
   K3P(0)
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
-  __shared__ float s_red[32];
+  __shared__ __align__(16) float s_red[128];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_misc[4];
 
@@ -333,8 +355,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
     const float4 q = bufA[i];
     mnx = fminf(mnx, q.x); mxx = fmaxf(mxx, q.x); mny = fminf(mny, q.y); mxy = fmaxf(mxy, q.y);
   }
-  mnx = block_min_f(mnx, s_red); mny = block_min_f(mny, s_red);
-  mxx = block_max_f(mxx, s_red); mxy = block_max_f(mxy, s_red);
+  block_bounds(mnx, mny, mxx, mxy, s_red);
   K3P(2)
   const float inv = 1.0f / p.leaf;
   const int minbx = (int)floorf(mnx * inv), maxbx = (int)floorf(mxx * inv);
@@ -453,7 +474,8 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
         float d2 = dx * dx; d2 += dy * dy;                  // FLANN L2_Simple in fp32, strict d2 < r2
         if (d2 < r2) {
           ++gN;
-          const double w = wint ? fmax((double)pt.w - 60.0, 0.0) : 1.0;          // pointnormal.cpp:15
+          // pointnormal.cpp:15  max(intensity - 60, 0): intensities are small integers, so the fp32 form is the same number
+          const double w = wint ? (double)fmaxf(pt.w - 60.0f, 0.0f) : 1.0;
           const double ex = (double)pt.x - (double)q.x, ey = (double)pt.y - (double)q.y;
           const double wx = w * ex, wy = w * ey;
           S0 += w; S1x += wx; S1y += wy; Sxx = fma(wx, ex, Sxx); Sxy = fma(wx, ey, Sxy); Syy = fma(wy, ey, Syy);
@@ -537,7 +559,7 @@ struct K4Params { CellPool pool; const int32_t* slots; float nn_cell; };
 __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k4_build_index(const K4Params p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
-  __shared__ float s_red[32];
+  __shared__ __align__(16) float s_red[128];
   const int slot = p.slots[blockIdx.x];
   const int n = p.pool.ncells[slot];
   Hist16 s_hist; s_hist.w = reinterpret_cast<uint32_t*>(dyn_smem);
