@@ -465,22 +465,37 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
     bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, divx - 1); by1 = min(by1, divy - 1);
     int gN = 0;
     double S0 = 0.0, S1x = 0.0, S1y = 0.0, Sxx = 0.0, Sxy = 0.0, Syy = 0.0;
+    auto take = [&](int a) {
+      const float4 pt = pts[a];
+      const float dx = q.x - pt.x, dy = q.y - pt.y;
+      float d2 = dx * dx; d2 += dy * dy;                    // FLANN L2_Simple in fp32, strict d2 < r2
+      if (d2 < r2) {
+        ++gN;
+        // pointnormal.cpp:15  max(intensity - 60, 0): intensities are small integers, so the fp32 form is the same number
+        const double w = wint ? (double)fmaxf(pt.w - 60.0f, 0.0f) : 1.0;
+        const double ex = (double)pt.x - (double)q.x, ey = (double)pt.y - (double)q.y;
+        const double wx = w * ex, wy = w * ey;
+        S0 += w; S1x += wx; S1y += wy; Sxx = fma(wx, ex, Sxx); Sxy = fma(wx, ey, Sxy); Syy = fma(wy, ey, Syy);
+      }
+    };
+#ifndef CFEAR_K3_NESTED
+    if (by1 - by0 <= 2) {
+      // the usual 3 x 3 voxel neighbourhood (leaf = radius): the point runs of the (up to) three voxel rows are walked as ONE
+      // flattened range, so the groups of a warp -- each on its own centroid -- stay in a single loop instead of diverging
+      // at every row boundary
+      const bool h1 = by0 + 1 <= by1, h2 = by0 + 2 <= by1;
+      const int o0 = by0 * divx, o1 = o0 + divx, o2 = o1 + divx;
+      const int s0 = (bx0 + o0) ? hist.get(bx0 + o0 - 1) : 0, e0 = (by0 <= by1) ? hist.get(bx1 + o0) : s0;
+      const int s1 = h1 ? hist.get(bx0 + o1 - 1) : 0, e1 = h1 ? hist.get(bx1 + o1) : 0;
+      const int s2 = h2 ? hist.get(bx0 + o2 - 1) : 0, e2 = h2 ? hist.get(bx1 + o2) : 0;
+      const int n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
+      for (int it = sl; it < total; it += LPC) take(it < n0 ? s0 + it : (it < n01 ? s1 + (it - n0) : s2 + (it - n01)));
+    } else
+#endif
     for (int by = by0; by <= by1; ++by) {
       const int b_lo = bx0 + by * divx, b_hi = bx1 + by * divx;
       const int s = b_lo ? hist.get(b_lo - 1) : 0, e = hist.get(b_hi);
-      for (int a = s + sl; a < e; a += LPC) {
-        const float4 pt = pts[a];
-        const float dx = q.x - pt.x, dy = q.y - pt.y;
-        float d2 = dx * dx; d2 += dy * dy;                  // FLANN L2_Simple in fp32, strict d2 < r2
-        if (d2 < r2) {
-          ++gN;
-          // pointnormal.cpp:15  max(intensity - 60, 0): intensities are small integers, so the fp32 form is the same number
-          const double w = wint ? (double)fmaxf(pt.w - 60.0f, 0.0f) : 1.0;
-          const double ex = (double)pt.x - (double)q.x, ey = (double)pt.y - (double)q.y;
-          const double wx = w * ex, wy = w * ey;
-          S0 += w; S1x += wx; S1y += wy; Sxx = fma(wx, ex, Sxx); Sxy = fma(wx, ey, Sxy); Syy = fma(wy, ey, Syy);
-        }
-      }
+      for (int a = s + sl; a < e; a += LPC) take(a);
     }
 #pragma unroll
     for (int d = 1; d < LPC; d <<= 1) {
