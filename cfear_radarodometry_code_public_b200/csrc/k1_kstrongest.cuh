@@ -15,7 +15,7 @@
 namespace cfear {
 
 #ifndef CFEAR_K1_MINBLOCKS
-#define CFEAR_K1_MINBLOCKS 6   // resident CTAs per SM the register budget is set for (40 registers, no spills; 4 -> 6: 0.115 -> 0.109 ms)
+#define CFEAR_K1_MINBLOCKS 5   // resident CTAs per SM the register budget is set for: 48 registers, no spills (6 CTAs at 40 registers spill in the streaming loop: 0.076 vs 0.072 ms)
 #endif
 constexpr int K1_WARPS = 8;       // warps (rows) per CTA
 constexpr int K1_CAP = 256;       // candidate keys per warp kept in shared memory
@@ -29,6 +29,7 @@ struct K1Params {
   int nrows;                 // nscans * A
   int A, R;
   uint32_t A_magic;          // ceil(2^32 / A): row -> azimuth without a division (k1_launch fills it)
+  uint32_t one;              // 1, unknown to the compiler (k1_launch fills it): x * one + c is an IMAD on the FMA pipe
   int zmin;                  // already uchar(int(z_min))
   int k;
   int min_range_bin;         // ceil(min_distance / range_res)
@@ -59,131 +60,163 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t*
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// bit7 of each byte set iff byte >= z_min.  addc = (0x80 - (zmin&0x7f)) * 0x01010101.  ZHI: z_min >= 128.
+// Pre-test of one 16-byte vector: false only if NO byte is >= z_min (z_min >= 1; z_min == 0 is handled by the caller).
+// z_min < 128: bit 7 of (x + c) | x per byte with c = 0x80 - z_min.  A byte >= 128 passes through the "| x"; below that
+// byte + c cannot overflow, so bit 7 says byte >= z_min.  The low 7 bits are NOT masked off first, so a carry out of a
+// neighbouring byte >= 128 + z_min may add one: a byte equal to z_min - 1 can pass (a false positive, sorted out by the
+// exact per-byte test of the drain), a byte >= z_min never fails.  Two instructions per word (the add goes to the FMA
+// pipe as IMAD.IADD, the three-input OR is one LOP3) instead of three plus the merges of an exact packed flag word.
+// ZHI (z_min >= 128): bit 7 of x & ((x & 0x7f..) + c), exact.
 template <bool ZHI>
-__device__ __forceinline__ uint32_t ge_flags(uint32_t x, uint32_t addc) {
-  const uint32_t a = (x & 0x7f7f7f7fu) + addc;     // bit7: low 7 bits >= low 7 bits of zmin; no cross-byte carry
-  return ZHI ? (x & a & 0x80808080u) : ((x | a) & 0x80808080u);
+__device__ __forceinline__ bool any_maybe_ge(const uint4& d, uint32_t addc, uint32_t one) {
+  uint32_t m;
+  if (ZHI) {
+    m = d.x & ((d.x & 0x7f7f7f7fu) + addc);
+    m |= d.y & ((d.y & 0x7f7f7f7fu) + addc);
+    m |= d.z & ((d.z & 0x7f7f7f7fu) + addc);
+    m |= d.w & ((d.w & 0x7f7f7f7fu) + addc);
+  } else {
+#ifdef CFEAR_K1_IMAD_ADD
+    // the adds as multiply-adds by an opaque 1: IMAD runs on the FMA pipe, which this kernel leaves idle
+    m = (d.x * one + addc) | d.x;
+    m |= (d.y * one + addc) | d.y;
+    m |= (d.z * one + addc) | d.z;
+    m |= (d.w * one + addc) | d.w;
+#else
+    m = (d.x + addc) | d.x;
+    m |= (d.y + addc) | d.y;
+    m |= (d.z + addc) | d.z;
+    m |= (d.w + addc) | d.w;
+#endif
+  }
+  return (m & 0x80808080u) != 0u;
 }
 
-// flags of a uint4 packed in one word: byte b of word w -> bit 8b + 7 - w
-// The kernel is bound by the integer ALU pipe (LOP3 / SHF / ISETP at half rate), so the three shift-and-or merges are
-// written as multiply-high-and-add (x >> n == umulhi(x, 2^(32-n)); the flag bits of different words never collide, so
-// + is |): IMAD.HI runs on the FMA pipe, which this kernel leaves idle.
-template <bool ZHI>
-__device__ __forceinline__ uint32_t ge_flags16(const uint4& d, uint32_t addc) {
-  uint32_t m = ge_flags<ZHI>(d.x, addc);
-  m = __umulhi(ge_flags<ZHI>(d.y, addc), 0x80000000u) + m;
-  m = __umulhi(ge_flags<ZHI>(d.z, addc), 0x40000000u) + m;
-  m = __umulhi(ge_flags<ZHI>(d.w, addc), 0x20000000u) + m;
-  return m;
+constexpr int K1_QCAP = 96;       // vectors queued per warp before a drain is forced (a drain is due once more than QCAP - 32 wait)
+
+// Per-warp shared memory, one block so that a single 32-bit base address (kept in a register) reaches every part at an
+// immediate offset: the queue of vectors that may hold candidates (+ a sentinel pair), the range bin of byte 0 of each,
+// the candidate keys and the two small lists of the selection.
+struct __align__(16) K1Warp {
+  uint4 qvec[K1_QCAP + 2];
+  int qbin[K1_QCAP + 2];
+  uint32_t cand[K1_CAP];
+  uint32_t sel[K1_MAXK];
+  uint32_t out[K1_MAXK];
+};
+constexpr uint32_t K1_QBIN = (K1_QCAP + 2) * 16;            // byte offsets inside K1Warp
+constexpr uint32_t K1_CAND = K1_QBIN + (K1_QCAP + 2) * 4;
+
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <uint32_t OFF>
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0+%2], %1;" :: "r"(a), "r"(v), "n"(OFF) : "memory"); }
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+
+// Drain the queue: two queued vectors per step, lane l tests byte (l & 15) of the first (l < 16) or second (l >= 16)
+// exactly (byte >= z_min and the byte's range bin inside the row) and the accepted bytes are appended to the candidate
+// list as keys (intensity << 16 | range) by one ballot.  Entry nq is a sentinel whose bins lie outside the row.
+// wb: shared-space address of the warp's K1Warp.
+__device__ __forceinline__ void k1_drain(uint32_t wb, int nq, int& C, int zmin, int R, int lane, uint32_t lanes_below) {
+  if (lane == 0) sts32<K1_QBIN>(wb + 4u * (uint32_t)nq, (uint32_t)R);
+  __syncwarp();
+  uint32_t a_byte = wb + (uint32_t)lane;                       // byte (lane & 15) of entry e + (lane >> 4)
+  uint32_t a_bin = wb + 4u * (uint32_t)(lane >> 4);
+  const int jb = lane & 15;
+  for (int e = 0; e < nq; e += 2, a_byte += 32u, a_bin += 8u) {
+    const uint32_t byte = lds8(a_byte);
+    const int bin = (int)lds32<K1_QBIN>(a_bin) + jb;
+    const bool ok = (int)byte >= zmin && (uint32_t)bin < (uint32_t)R;
+    const uint32_t bal = __ballot_sync(FULL, ok);
+    const int pos = C + __popc(bal & lanes_below);
+    if (ok && pos < K1_CAP) sts32<K1_CAND>(wb + 4u * (uint32_t)pos, (byte << 16) | (uint32_t)bin);
+    C += __popc(bal);
+  }
+  __syncwarp();                                  // the queue is rewritten after this
 }
 
 // ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
 #ifndef CFEAR_K1_MINBLOCKS_UNALIGNED
-#define CFEAR_K1_MINBLOCKS_UNALIGNED 5   // the head / tail masks and the 8-tile form need 48 registers: at 40 they spill (3768-bin rows:
-                                         // 0.371 ns per KB of image with 6 CTAs and spills, 0.316 with 5 CTAs; aligned 3360-bin rows: 0.282)
+#define CFEAR_K1_MINBLOCKS_UNALIGNED 5   // the 8-tile form of the 3768-bin rows needs 48 registers
 #endif
 template <bool ALIGNED, bool ZHI, int TILES = K1_TILES>
 __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : CFEAR_K1_MINBLOCKS_UNALIGNED) k1_kstrongest(const K1Params p) {
-  __shared__ uint32_t s_cand[K1_WARPS][K1_CAP];
-  __shared__ uint32_t s_sel[K1_WARPS][K1_MAXK];
-  __shared__ uint32_t s_out[K1_WARPS][K1_MAXK];
-  __shared__ uint2 s_queue[K1_WARPS][TILES * 32 + 2];  // vectors of one super-tile that hold candidates (+ a zero sentinel)
+  __shared__ K1Warp s_w[K1_WARPS];
   const int grow = blockIdx.x * K1_WARPS + warp_id();
   if (grow >= p.nrows) return;                 // no block-level sync in this kernel
   const int lane = lane_id();
-  uint32_t* cand = s_cand[warp_id()];
-  uint32_t* sel = s_sel[warp_id()];
-  uint32_t* outk = s_out[warp_id()];
+  K1Warp& W = s_w[warp_id()];
+  uint32_t* cand = W.cand;
+  uint32_t* sel = W.sel;
+  uint32_t* outk = W.out;
+  uint32_t wb = (uint32_t)__cvta_generic_to_shared(&W);
+  asm volatile("mov.u32 %0, %0;" : "+r"(wb));   // opaque: keep the base in a register instead of recomputing it at every use
 
   const int R = p.R, k = p.k;
   const uint8_t* row = p.polar + (size_t)grow * R;
-  const int off = (int)((uintptr_t)row & 15);
+  const int off = ALIGNED ? 0 : (int)((uintptr_t)row & 15);
   const uint8_t* base = row - off;
   const int nvec = (off + R + 15) >> 4;
   const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
   const bool edge_row = grow == 0 || grow == p.nrows - 1;      // warp-uniform
 
   // ---- pass 1: stream the row, collect the candidates ---------------------------------------------
-  // Candidates are sparse (a few vectors per row hold any), so they are emitted cooperatively: every lane whose vector
-  // has flags pushes (flags, first range bin) onto a per-warp queue (one ballot per 32 vectors), then the warp drains
-  // the queue two vectors at a time with lane l handling byte (l & 15) of the first (l < 16) or second (l >= 16).
-  // Only range bins are emitted here; the intensities are re-read (L2) once the list is complete.
-  const int jb = lane & 15, jw = jb >> 2;
-  const uint32_t mybit = 1u << (8 * (jb & 3) + 7 - jw);                          // flag bit of byte jb (see ge_flags16)
-  const uint32_t lowmask = 0x01010101u * (0x100u - (0x100u >> jw)) |             // flag bits of the bytes before jb
-                           ((0x80808080u >> jw) & ((1u << (8 * (jb & 3))) - 1u));
+  // Candidates are sparse (a few vectors per row hold any).  The streaming part only decides, per 16-byte vector,
+  // whether it MAY hold one (any_maybe_ge); such vectors go, as they are, onto a per-warp shared-memory queue (one
+  // ballot per 32 vectors) and the queue is drained cooperatively with one lane per byte (k1_drain), which is where the
+  // exact test, the row head / tail of unaligned rows and the keys are done.
   const uint32_t lanes_below = (1u << lane) - 1u;
-  uint2* q = s_queue[warp_id()];
-  const bool hi = lane >= 16;
   int C = 0;                                   // warp-uniform candidate count
-  for (int v0 = 0; v0 < nvec; v0 += 32 * TILES) {
-    uint32_t g[TILES];
-    {
-      uint4 d[TILES];
-#pragma unroll
-      for (int i = 0; i < TILES; ++i) {
-        const int v = v0 + i * 32 + lane;
-        // only the first vector of the first row and the last vector of the last row can reach outside the buffer;
-        // tiles that lie entirely inside the row (warp-uniform test) load without a per-lane predicate
-        if (ALIGNED || !edge_row) {
-          if (ALIGNED && v0 + i * 32 + 32 <= nvec) d[i] = ld_stream16(base + 16 * (size_t)v);
-          else d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
-        } else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int i = 0; i < TILES; ++i) {
-        // a super-tile past the end of the row (3768-bin Oxford rows need 236 vectors: one full super-tile of 224 and 12
-        // more) skips the flag arithmetic of its empty tiles (warp-uniform test)
-        if (!ALIGNED && v0 + i * 32 >= nvec) { g[i] = 0; continue; }
-        const int v = v0 + i * 32 + lane;
-        uint32_t m = ge_flags16<ZHI>(d[i], addc);
-        const int b0 = v * 16 - off;             // range bin of byte 0 of this uint4
-        if (v >= nvec) m = 0;
-        else if (!ALIGNED && (b0 < 0 || b0 + 16 > R)) {        // row head / tail: drop bytes of neighbouring rows
-          // valid bytes j in [jlo, jhi) -> 16-bit mask -> the packed flag layout (byte b of word w at bit 8b + 7 - w):
-          // a nibble's bits go to the four byte lanes by one multiply (n * 0x00204081 puts bit b at 8b)
-          const int jlo = max(0, -b0), jhi = min(16, R - b0);
-          const uint32_t jm = (jhi > jlo) ? ((0xffffu >> (16 - jhi)) & (0xffffu << jlo)) : 0u;
-          uint32_t keep = 0;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) keep |= ((((jm >> (4 * w)) & 0xfu) * 0x00204081u) & 0x01010101u) << (7 - w);
-          m &= keep;
-        }
-        g[i] = m;
-      }
+  if (p.zmin == 0) {
+    C = R;                                     // every byte is a candidate: the selection below reads the row itself
+    if (R <= K1_CAP) {                         // ... unless the row is short enough for the candidate list
+      for (int j = lane; j < R; j += 32) cand[j] = ((uint32_t)row[j] << 16) | (uint32_t)j;
+      __syncwarp();
     }
+  } else {
     int nq = 0;                                // warp-uniform queue length
+    for (int v0 = 0; v0 < nvec; v0 += 32 * TILES) {
+      uint4 d[TILES];
+      // all tiles but the last lie inside the row and nothing reaches outside the buffer (only the first vector of the
+      // first row and the last vector of the last row of an unaligned buffer can): unpredicated loads at immediate
+      // offsets, the last tile at a clamped address (its lanes past the row re-read the row's last vector and are
+      // dropped by the v < nvec test below)
+      const bool fast = (v0 + 32 * (TILES - 1) < nvec) && (ALIGNED || !edge_row);      // warp-uniform
+      if (fast) {
+        const uint8_t* pl = base + 16 * (size_t)(v0 + lane);
 #pragma unroll
-    for (int i = 0; i < TILES; ++i) {
-      const bool has = g[i] != 0;
-      const uint32_t bal = __ballot_sync(FULL, has);
-      if (bal) {                                 // warp-uniform
-        if (has) q[nq + __popc(bal & lanes_below)] = make_uint2(g[i], (uint32_t)((v0 + i * 32 + lane) * 16 - off));
-        nq += __popc(bal);
+        for (int i = 0; i < TILES - 1; ++i) d[i] = ld_stream16(pl + 512 * i);
+        d[TILES - 1] = ld_stream16(base + 16 * (size_t)min(v0 + 32 * (TILES - 1) + lane, nvec - 1));
+      } else {
+#pragma unroll
+        for (int i = 0; i < TILES; ++i) {
+          const int v = v0 + i * 32 + lane;
+          if (ALIGNED || !edge_row) d[i] = (v < nvec) ? ld_stream16(base + 16 * (size_t)v) : make_uint4(0, 0, 0, 0);
+          else d[i] = (v < nvec) ? load16_guarded(base + 16 * (size_t)v, p.polar, p.polar_end) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TILES; ++i) {
+        const int v = v0 + i * 32 + lane;
+        // vectors past the row hold zeros (never a candidate: z_min >= 1) except in the last tile of the fast path
+        const bool has = any_maybe_ge<ZHI>(d[i], addc, p.one) && (i < TILES - 1 || v < nvec);
+        const uint32_t bal = __ballot_sync(FULL, has);
+        if (bal) {                                 // warp-uniform; nq <= K1_QCAP - 32 here
+          if (has) {
+            const uint32_t slot = (uint32_t)(nq + __popc(bal & lanes_below));
+            sts128(wb + 16u * slot, d[i]);
+            sts32<K1_QBIN>(wb + 4u * slot, (uint32_t)(v * 16 - off));   // range bin of byte 0 (negative in an unaligned row's head)
+          }
+          nq += __popc(bal);
+          if (nq > K1_QCAP - 32) { k1_drain(wb, nq, C, p.zmin, R, lane, lanes_below); nq = 0; }
+        }
       }
     }
-    if (lane == 0) q[nq] = make_uint2(0u, 0u);   // sentinel: an odd queue drains its last entry beside an empty one
-    __syncwarp();
-    for (int e = 0; e < nq; e += 2) {
-      const uint2 e1 = q[e];
-      const uint2 e2 = q[e + 1];
-      const uint32_t mm = hi ? e2.x : e1.x;
-      const int c1 = __popc(e1.x);
-      if (mm & mybit) {
-        const int pos = C + (hi ? c1 : 0) + __popc(mm & lowmask);
-        if (pos < K1_CAP) cand[pos] = (hi ? e2.y : e1.y) + (uint32_t)jb;
-      }
-      C += c1 + __popc(e2.x);
-    }
-    __syncwarp();                                // the queue is rewritten by the next super-tile
+    k1_drain(wb, nq, C, p.zmin, R, lane, lanes_below);
   }
-  __syncwarp();
-  if (C <= K1_CAP) {                             // range bins -> keys (intensity << 16 | range)
-    for (int j = lane; j < C; j += 32) { const uint32_t r = cand[j]; cand[j] = ((uint32_t)row[r] << 16) | r; }
-  }
-  __syncwarp();
 
   // ---- pass 2: exact top-k of the keys -----------------------------------------------------------
   const int kk = min(k, C);
@@ -283,6 +316,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
 inline void k1_launch(const K1Params& p_in, cudaStream_t stream) {
   K1Params p = p_in;
   p.A_magic = (uint32_t)(0xffffffffull / (unsigned long long)p.A + 1ull);
+  p.one = 1u;
   const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
   const bool aligned = ((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0;
   const bool zhi = p.zmin >= 128;
