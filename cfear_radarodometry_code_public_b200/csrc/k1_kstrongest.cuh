@@ -60,12 +60,13 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t*
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Pre-test of one 16-byte vector: false only if NO byte is >= z_min (z_min >= 1; z_min == 0 is handled by the caller).
+// Test of one 16-byte vector: does ANY byte reach z_min (z_min >= 1; z_min == 0 is handled by the caller)?
 // z_min < 128: bit 7 of (x + c) | x per byte with c = 0x80 - z_min.  A byte >= 128 passes through the "| x"; below that
-// byte + c cannot overflow, so bit 7 says byte >= z_min.  The low 7 bits are NOT masked off first, so a carry out of a
-// neighbouring byte >= 128 + z_min may add one: a byte equal to z_min - 1 can pass (a false positive, sorted out by the
-// exact per-byte test of the drain), a byte >= z_min never fails.  Two instructions per word (the add goes to the FMA
-// pipe as IMAD.IADD, the three-input OR is one LOP3) instead of three plus the merges of an exact packed flag word.
+// byte + c cannot overflow, so bit 7 says byte >= z_min.  The low 7 bits are NOT masked off first, so a carry out of the
+// byte below (inside the 32-bit word) may add one and let a byte equal to z_min - 1 pass -- but a byte only carries when
+// it is >= 128 + z_min, i.e. a candidate itself, so the answer for the vector is exact; which bytes are the candidates is
+// decided by the per-byte test of the drain.  Two instructions per word (one add, one three-input OR) instead of three
+// plus the merges of an exact packed flag word.
 // ZHI (z_min >= 128): bit 7 of x & ((x & 0x7f..) + c), exact.
 template <bool ZHI>
 __device__ __forceinline__ bool any_maybe_ge(const uint4& d, uint32_t addc, uint32_t one) {

@@ -56,6 +56,44 @@ def test_kstrongest_k_and_zmin_sweep(orc, k, zmin):
     c.close()
 
 
+def pretest_stress_image(zmin, A=48, R=3360, seed=11):
+    """Rows aimed at K1's streaming any-byte test (inside a word a byte >= 128 + z_min carries into its neighbour, so a
+    neighbour equal to z_min - 1 looks like a candidate until the exact per-byte test of the drain) and at the queue of
+    flagged vectors (more than 64 flagged vectors in one row force a drain in the middle of the row, with the candidate
+    list still below its capacity)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = max(zmin - 1, 0)
+    img = rng.integers(0, max(lo, 1), (A, R), dtype=np.uint8) if lo > 0 else np.zeros((A, R), np.uint8)
+    img[0, 0::2] = 255; img[0, 1::2] = lo           # every byte pair (255, z_min - 1): saturated + false positives
+    img[1, 7::16] = 255; img[1, 8::16] = lo         # one such pair per vector: 210 candidates, 210 flagged vectors
+    img[2, 3::4] = lo; img[2, 2::128] = 255         # false positives only around a few real candidates
+    img[3, 5::32] = min(zmin + 1, 255)              # 105 flagged vectors, one candidate each
+    img[4, 15::48] = min(zmin, 255)                 # 70 flagged vectors: just past the forced-drain threshold
+    img[5, :] = lo                                  # nothing, everything one below z_min
+    img[6, ::3] = 255; img[6, 1::3] = lo            # carries into every third byte
+    for a in range(7, A):                           # sparse real candidates beside (>= 128 + z_min, z_min - 1) pairs
+        n = int(rng.integers(0, 30))
+        cols = rng.integers(1, R - 1, n)
+        img[a, cols] = rng.integers(min(zmin, 255), 256, n)
+        cols = rng.integers(1, R - 1, 40)
+        img[a, cols] = 255; img[a, cols + 1] = lo
+    return img
+
+
+@pytest.mark.parametrize("zmin", [1, 2, 60, 100, 127, 128, 129, 200, 255])
+@pytest.mark.parametrize("R", [3360, 3768])
+def test_kstrongest_carry_neighbours_and_queue_drains(orc, zmin, R):
+    A = 48
+    im = np.stack([pretest_stress_image(zmin, A, R, seed=11), pretest_stress_image(zmin, A, R, seed=12)])
+    c = capi.Context(max_batch=2, azimuths=A, range_bins=R, z_min=float(zmin), max_cellsets=2)
+    idx, cnt = c.kstrongest(im)
+    for i in range(2):
+        oi, oc = orc.kstrongest(im[i], zmin, 12)
+        assert np.array_equal(cnt[i], oc)
+        assert np.array_equal(idx[i], oi)
+    c.close()
+
+
 def test_kstrongest_odd_row_length(orc):
     # R not a multiple of 16: rows are not 16-byte aligned
     A, R = 37, 1001
