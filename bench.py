@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--batch-cache", default=None, help="npz file caching the generated workload between runs")
     ap.add_argument("--save-poses", default=None, help="experiment builds: save poses / iteration counts (npz)")
     ap.add_argument("--ref-poses", default=None, help="experiment builds: compare with the npz another build saved")
-    ap.add_argument("--inflight", type=int, default=4, help="result / slot sets the overlapped steps rotate through")
+    ap.add_argument("--inflight", type=int, default=5, help="result / slot sets the overlapped steps rotate through")
     ap.add_argument("--serial", action="store_true", help="device-resident arm through the stream-ordered cfear_odometry_step_batch_dev")
     ap.add_argument("--min-seconds", type=float, default=0.25, help="the K-step timed region is repeated until it lasts this long")
     args = ap.parse_args()

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfear_b200.so")
+# CFEAR_B200_LIB: experiment builds (profiles/ab); the shipped library otherwise
+LIB_PATH = os.environ.get("CFEAR_B200_LIB") or os.path.join(_HERE, "libcfear_b200.so")
 
 COST = {"P2P": 0, "P2L": 1, "P2D": 2}
 LOSS = {"None": 0, "Huber": 1, "Cauchy": 2, "SoftLOne": 3, "Combined": 4, "Tukey": 5}

@@ -119,7 +119,7 @@ static_assert(sizeof(cfear_cell) == sizeof(CellAoS), "cell layout");
                                        // profiles/r02m_nn_cell_ab.txt, profiles/r02v_k5_three_per_sm_ab.txt)
 #endif
 constexpr int CFEAR_MAX_TICKETS = 8;   // steps that may be in flight between submit and wait
-constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 4)
+constexpr int CFEAR_NPIPES = 8;        // most device-resident steps that may overlap (cfear_config.steps_in_flight, default 5)
 
 // Everything one step writes between K1 and K5.  Set 0 aliases the context's own buffers (every stream-ordered entry
 // point uses it on the context stream); sets 1..CFEAR_NPIPES have their own streams so that consecutive device-resident
@@ -141,6 +141,7 @@ struct cfear_ctx {
   std::vector<cudaEvent_t> chunk_ev, k1_done, ticket_ev;   // host-buffer path: H2D done / staging area read / step done
   cudaEvent_t polar_free = nullptr; bool polar_dirty = true; int next_ticket = 0;
   int64_t launches = 0;
+  int prio[3] = {0, 0, 0};          // launch priorities of K1, K3, K5 (experiment: CFEAR_PRIO="k1,k3,k5")
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
@@ -235,7 +236,8 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   cfear_ctx* c = new (std::nothrow) cfear_ctx();
   if (!c) { g_err = "out of host memory"; return CFEAR_ERR_ARG; }
   c->cfg = *cfg;
-  c->npipes = cfg->steps_in_flight > 0 ? std::min(cfg->steps_in_flight, CFEAR_NPIPES) : 4;
+  if (const char* e = getenv("CFEAR_PRIO")) sscanf(e, "%d,%d,%d", &c->prio[0], &c->prio[1], &c->prio[2]);
+  c->npipes = cfg->steps_in_flight > 0 ? std::min(cfg->steps_in_flight, CFEAR_NPIPES) : 5;
   // from here on a CUDA failure must not leak the half-built context
 #define CKC(expr)                                                                                 \
   do {                                                                                            \
@@ -399,7 +401,7 @@ static int launch_k1(cfear_ctx* c, const PipeBufs& B, const uint8_t* d_polar, in
   p.min_range_bin = (int)ceil(min_distance / range_res);                      // radar_filters.cpp:315
   p.range_res = range_res; p.cs = c->d_cs;
   p.kidx = B.d_kidx; p.kcnt = B.d_kcnt; p.rowcloud = B.d_rowcloud; p.rowcnt = B.d_rowcnt;
-  k1_launch(p, B.stream);
+  k1_launch(p, B.stream, c->prio[0]);
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;
@@ -440,7 +442,7 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  k3_surface_points<<<nscans, K3_THREADS, c->k3_smem, B.stream>>>(p);
+  CK(launch_with_priority(k3_surface_points, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;
@@ -461,9 +463,9 @@ static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, con
   p.smem_bytes = c->k5_smem;
 bool launched = false;
   switch (p.cost) {
-    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, B.stream); break;
-    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, B.stream); break;
-    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, B.stream); break;
+    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
+    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
+    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
   }
   if (!launched) { g_err = "this build has no instantiation for the requested cost / loss"; return CFEAR_ERR_ARG; }
   c->launches++;

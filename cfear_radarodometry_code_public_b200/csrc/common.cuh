@@ -7,6 +7,19 @@ namespace cfear {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Kernel launch with a per-launch scheduling priority (cudaLaunchAttributePriority; numerically lower = served first by
+// the block scheduler, 0 = the default).  With several steps in flight the registration kernel -- the long, latency-bound
+// end of every step's chain -- is given precedence over the next steps' filter kernels, which fill what it leaves.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_with_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int prio, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority; at[0].val.priority = prio;
+  cfg.attrs = at; cfg.numAttrs = prio != 0 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Device-resident cell-set pool (SoA).  Slot s occupies [s*max_cells, (s+1)*max_cells) of each array.
 // This is what MapPointNormal holds for the pose path (pointnormal.h:66-73,196-199): cells + the

@@ -10,14 +10,22 @@
 //   range bin exactly like the reference's sorted-insert / erase-front loop.
 // Algorithmic HBM bytes per row: R (read) + 4k+4 (indices) + 16k+4 (cloud row).
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 
 namespace cfear {
 
 #ifndef CFEAR_K1_MINBLOCKS
-#define CFEAR_K1_MINBLOCKS 5   // resident CTAs per SM the register budget is set for: 48 registers, no spills (6 CTAs at 40 registers spill in the streaming loop: 0.076 vs 0.072 ms)
+#define CFEAR_K1_MINBLOCKS 4   // resident CTAs per SM the register budget is set for: 64 registers (the next row's vectors stay in registers while a row is finished)
 #endif
-constexpr int K1_WARPS = 8;       // warps (rows) per CTA
+#ifndef CFEAR_K1_WARPS
+#define CFEAR_K1_WARPS 8
+#endif
+constexpr int K1_WARPS = CFEAR_K1_WARPS;       // warps per CTA
+#ifndef CFEAR_K1_RPW
+#define CFEAR_K1_RPW 8
+#endif
+constexpr int K1_RPW = CFEAR_K1_RPW;   // most rows per warp (the loads of row i+1 fly while row i is finished); k1_launch picks K1Params::rpw
 constexpr int K1_CAP = 256;       // candidate keys per warp kept in shared memory
 constexpr int K1_TILES = 7;       // uint4 per lane per super-tile (7*512 B = 3584 B >= one 3360-bin Navtech row in registers);
 constexpr int K1_TILES_WIDE = 8;  // rows of up to 4096 bytes (Oxford: 3768 bins) in one super-tile
@@ -29,6 +37,7 @@ struct K1Params {
   int nrows;                 // nscans * A
   int A, R;
   uint32_t A_magic;          // ceil(2^32 / A): row -> azimuth without a division (k1_launch fills it)
+  int rpw;                   // rows per warp, 1..K1_RPW (k1_launch fills it)
   uint32_t one;              // 1, unknown to the compiler (k1_launch fills it): x * one + c is an IMAD on the FMA pipe
   int zmin;                  // already uchar(int(z_min))
   int k;
@@ -141,13 +150,11 @@ __device__ __forceinline__ void k1_drain(uint32_t wb, int nq, int& C, int zmin, 
 
 // ALIGNED: every row starts on a 16-byte boundary and R % 16 == 0 (Navtech 3360-bin rows), so no vector straddles a row.
 #ifndef CFEAR_K1_MINBLOCKS_UNALIGNED
-#define CFEAR_K1_MINBLOCKS_UNALIGNED 5   // the 8-tile form of the 3768-bin rows needs 48 registers
+#define CFEAR_K1_MINBLOCKS_UNALIGNED 4
 #endif
 template <bool ALIGNED, bool ZHI, int TILES = K1_TILES>
 __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : CFEAR_K1_MINBLOCKS_UNALIGNED) k1_kstrongest(const K1Params p) {
   __shared__ K1Warp s_w[K1_WARPS];
-  const int grow = blockIdx.x * K1_WARPS + warp_id();
-  if (grow >= p.nrows) return;                 // no block-level sync in this kernel
   const int lane = lane_id();
   K1Warp& W = s_w[warp_id()];
   uint32_t* cand = W.cand;
@@ -157,11 +164,20 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
   asm volatile("mov.u32 %0, %0;" : "+r"(wb));   // opaque: keep the base in a register instead of recomputing it at every use
 
   const int R = p.R, k = p.k;
+  const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  // A warp takes p.rpw rows, K1_WARPS apart (the warps of a CTA read consecutive rows at every step), and requests the
+  // next row's vectors as soon as the current row's have been looked at: the drain, the selection and the outputs of a
+  // row run under the next row's loads.  No block-level synchronisation anywhere in this kernel.
+  uint4 d[TILES];
+  bool have_d = false;                         // d[] already holds the first super-tile of this row (warp-uniform)
+  for (int it = 0; it < p.rpw; ++it) {
+  const int grow = (blockIdx.x * p.rpw + it) * K1_WARPS + warp_id();
+  if (grow >= p.nrows) break;
   const uint8_t* row = p.polar + (size_t)grow * R;
   const int off = ALIGNED ? 0 : (int)((uintptr_t)row & 15);
   const uint8_t* base = row - off;
   const int nvec = (off + R + 15) >> 4;
-  const uint32_t addc = (0x80u - (uint32_t)(p.zmin & 0x7f)) * 0x01010101u;
   const bool edge_row = grow == 0 || grow == p.nrows - 1;      // warp-uniform
 
   // ---- pass 1: stream the row, collect the candidates ---------------------------------------------
@@ -169,7 +185,6 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
   // whether it MAY hold one (any_maybe_ge); such vectors go, as they are, onto a per-warp shared-memory queue (one
   // ballot per 32 vectors) and the queue is drained cooperatively with one lane per byte (k1_drain), which is where the
   // exact test, the row head / tail of unaligned rows and the keys are done.
-  const uint32_t lanes_below = (1u << lane) - 1u;
   int C = 0;                                   // warp-uniform candidate count
   if (p.zmin == 0) {
     C = R;                                     // every byte is a candidate: the selection below reads the row itself
@@ -180,13 +195,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
   } else {
     int nq = 0;                                // warp-uniform queue length
     for (int v0 = 0; v0 < nvec; v0 += 32 * TILES) {
-      uint4 d[TILES];
       // all tiles but the last lie inside the row and nothing reaches outside the buffer (only the first vector of the
       // first row and the last vector of the last row of an unaligned buffer can): unpredicated loads at immediate
       // offsets, the last tile at a clamped address (its lanes past the row re-read the row's last vector and are
       // dropped by the v < nvec test below)
       const bool fast = (v0 + 32 * (TILES - 1) < nvec) && (ALIGNED || !edge_row);      // warp-uniform
-      if (fast) {
+      if (have_d && v0 == 0) {
+        // requested while the previous row was being finished
+      } else if (fast) {
         const uint8_t* pl = base + 16 * (size_t)(v0 + lane);
 #pragma unroll
         for (int i = 0; i < TILES - 1; ++i) d[i] = ld_stream16(pl + 512 * i);
@@ -213,6 +229,24 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
           }
           nq += __popc(bal);
           if (nq > K1_QCAP - 32) { k1_drain(wb, nq, C, p.zmin, R, lane, lanes_below); nq = 0; }
+        }
+      }
+      have_d = false;
+      if (it + 1 < p.rpw && v0 + 32 * TILES >= nvec) {
+        // this row's last vectors have been looked at: request the next row's first super-tile (fast form only)
+        const int gnext = grow + K1_WARPS;
+        if (gnext < p.nrows) {
+          const uint8_t* rown = row + (size_t)K1_WARPS * R;
+          const int offn = ALIGNED ? 0 : (int)((uintptr_t)rown & 15);
+          const uint8_t* basen = rown - offn;
+          const int nvecn = (offn + R + 15) >> 4;
+          if (32 * (TILES - 1) < nvecn && (ALIGNED || gnext != p.nrows - 1)) {
+            const uint8_t* pl = basen + 16 * (size_t)lane;
+#pragma unroll
+            for (int i = 0; i < TILES - 1; ++i) d[i] = ld_stream16(pl + 512 * i);
+            d[TILES - 1] = ld_stream16(basen + 16 * (size_t)min(32 * (TILES - 1) + lane, nvecn - 1));
+            have_d = true;
+          }
         }
       }
     }
@@ -310,21 +344,26 @@ __global__ void __launch_bounds__(K1_WARPS * 32, ALIGNED ? CFEAR_K1_MINBLOCKS : 
     ncloud += __popc(bal);
   }
   if (lane == 0) { p.kcnt[grow] = kk; p.rowcnt[grow] = ncloud; }
+  __syncwarp();                                // the lists are rewritten by the next row
+  }
 }
 
 // Launch with the instantiation the data allows: aligned rows (every row on a 16-byte boundary, no vector straddles a
 // row) and the z_min half (>= 128 or not) are compile-time.
-inline void k1_launch(const K1Params& p_in, cudaStream_t stream) {
+inline void k1_launch(const K1Params& p_in, cudaStream_t stream, int prio = 0) {
   K1Params p = p_in;
   p.A_magic = (uint32_t)(0xffffffffull / (unsigned long long)p.A + 1ull);
   p.one = 1u;
-  const int grid = (p.nrows + K1_WARPS - 1) / K1_WARPS;
+  // rows per warp: as many as leave about two waves of CTAs on a B200 (148 SMs x 4 CTAs); small launches (one scan: 400
+  // rows) keep one row per warp, where latency is what counts
+  p.rpw = std::max(1, std::min(K1_RPW, p.nrows / (K1_WARPS * 148 * 4 * 2)));
+  const int grid = (p.nrows + K1_WARPS * p.rpw - 1) / (K1_WARPS * p.rpw);
   const bool aligned = ((uintptr_t)p.polar & 15) == 0 && (p.R & 15) == 0;
   const bool zhi = p.zmin >= 128;
   const bool wide = ((15 + p.R + 15) >> 4) > 32 * K1_TILES;      // a row (plus its alignment slack) exceeds one 7-tile super-tile
-  if (aligned) { if (zhi) k1_kstrongest<true, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<true, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
-  else if (wide) { if (zhi) k1_kstrongest<false, true, K1_TILES_WIDE><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<false, false, K1_TILES_WIDE><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
-  else { if (zhi) k1_kstrongest<false, true><<<grid, K1_WARPS * 32, 0, stream>>>(p); else k1_kstrongest<false, false><<<grid, K1_WARPS * 32, 0, stream>>>(p); }
+  if (aligned) { if (zhi) launch_with_priority(k1_kstrongest<true, true>, grid, K1_WARPS * 32, 0, stream, prio, p); else launch_with_priority(k1_kstrongest<true, false>, grid, K1_WARPS * 32, 0, stream, prio, p); }
+  else if (wide) { if (zhi) launch_with_priority(k1_kstrongest<false, true, K1_TILES_WIDE>, grid, K1_WARPS * 32, 0, stream, prio, p); else launch_with_priority(k1_kstrongest<false, false, K1_TILES_WIDE>, grid, K1_WARPS * 32, 0, stream, prio, p); }
+  else { if (zhi) launch_with_priority(k1_kstrongest<false, true>, grid, K1_WARPS * 32, 0, stream, prio, p); else launch_with_priority(k1_kstrongest<false, false>, grid, K1_WARPS * 32, 0, stream, prio, p); }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,14 +22,14 @@ cudaError_t K5_CAT(k5_set_smem_cost, CFEAR_K5_TU_COST)(int bytes) {
   return e;
 }
 
-bool K5_CAT(k5_launch_cost, CFEAR_K5_TU_COST)(const RegParams& p, int nprob, int smem, cudaStream_t stream) {
+bool K5_CAT(k5_launch_cost, CFEAR_K5_TU_COST)(const RegParams& p, int nprob, int smem, cudaStream_t stream, int prio) {
   // gn_fixed / cost only, and the ceres_lm loop with association outputs or the soft prior: the AUX instantiations
   const bool aux = p.solver_mode != 0 || p.assoc != nullptr || p.assoc_sim != nullptr || p.soft_L != nullptr;
   switch (p.loss) {
 #define K5_CASE(LO)                                                                                       \
   case LO:                                                                                                \
-    if (aux) k5_register<CFEAR_K5_TU_COST, LO, true><<<nprob, K5_THREADS, smem, stream>>>(p);             \
-    else k5_register<CFEAR_K5_TU_COST, LO, false><<<nprob, K5_THREADS, smem, stream>>>(p);                \
+    if (aux) launch_with_priority(k5_register<CFEAR_K5_TU_COST, LO, true>, nprob, K5_THREADS, smem, stream, prio, p);   \
+    else launch_with_priority(k5_register<CFEAR_K5_TU_COST, LO, false>, nprob, K5_THREADS, smem, stream, prio, p);      \
     return true;
     K5_FOR_EACH_LOSS(K5_CASE)
 #undef K5_CASE

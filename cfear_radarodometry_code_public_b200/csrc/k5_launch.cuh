@@ -10,8 +10,8 @@ cudaError_t k5_set_smem_cost0(int bytes);
 cudaError_t k5_set_smem_cost1(int bytes);
 cudaError_t k5_set_smem_cost2(int bytes);
 // launch k5_register<COST, p.loss, p.solver_mode != ceres_lm> on `stream`; false if p.loss is not instantiated
-bool k5_launch_cost0(const RegParams& p, int nprob, int smem, cudaStream_t stream);
-bool k5_launch_cost1(const RegParams& p, int nprob, int smem, cudaStream_t stream);
-bool k5_launch_cost2(const RegParams& p, int nprob, int smem, cudaStream_t stream);
+bool k5_launch_cost0(const RegParams& p, int nprob, int smem, cudaStream_t stream, int prio = 0);
+bool k5_launch_cost1(const RegParams& p, int nprob, int smem, cudaStream_t stream, int prio = 0);
+bool k5_launch_cost2(const RegParams& p, int nprob, int smem, cudaStream_t stream, int prio = 0);
 
 }  // namespace cfear

@@ -880,7 +880,12 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
     s_pose[5 * tid + 0] = poses[3 * tid + 0]; s_pose[5 * tid + 1] = poses[3 * tid + 1];
     s_pose[5 * tid + 2] = yaw; s_pose[5 * tid + 3] = c; s_pose[5 * tid + 4] = s;
   }
-  if (tid == 0) mbar_init(&s_bar, 1);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    // the soft prior is only set up by the ceres_lm branch; gn_fixed's covariance round (eval_round<.., AUX>) must not see
+    // whatever the previous CTA left in this shared-memory word
+    if constexpr (AUX) s_lm.soft = 0;
+  }
   __syncthreads();
 
   // Shared-memory plan:  [ tables | s_nn | s_list | source means, normals | U ]  with U = the rest of the dynamic allocation.

@@ -83,7 +83,7 @@ typedef struct cfear_config {
   int32_t max_keyframes;     /* K max = submap_scan_size */
   int32_t max_cellsets;      /* number of device-resident cell-set slots */
   int32_t max_cells;         /* capacity of one cell set; 0 -> azimuths*k_strongest */
-  int32_t steps_in_flight;   /* cfear_odometry_step_batch_dev_submit: internal streams / scratch sets to rotate through (0 -> 4, max 8) */
+  int32_t steps_in_flight;   /* cfear_odometry_step_batch_dev_submit: internal streams / scratch sets to rotate through (0 -> 5, max 8) */
 } cfear_config;
 
 /* pcl::PointXYZI as written by getPeaksFilteredPointCloud (radar_filters.cpp:328-333) */
