@@ -169,6 +169,13 @@ struct cfear_ctx {
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) { g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CFEAR_ERR_CUDA; }
     allocs.push_back(q);
+    // every buffer starts zeroed: the padded tails of row-padded outputs (k-strongest rows with fewer than k candidates,
+    // cell arrays beyond ncells) are copied and staged as whole blocks, and should not carry another context's bytes
+    // (allocation happens at creation and on the first use of a feature; the context's streams are non-blocking, i.e. not
+    // ordered against the legacy stream the memset runs on, hence the synchronisation)
+    e = cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { g_err = std::string("cudaMemset: ") + cudaGetErrorString(e); return CFEAR_ERR_CUDA; }
     *p = reinterpret_cast<T*>(q);
     return CFEAR_OK;
   }
