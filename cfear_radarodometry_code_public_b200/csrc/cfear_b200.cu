@@ -274,7 +274,8 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   c->pts_in_smem = (full + 2048 <= (size_t)max_optin) ? 1 : 0;
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
   c->k4_smem = hist_bytes;
-  CKC(cudaFuncSetAttribute(k3_surface_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+  if (c->pts_in_smem) CKC(cudaFuncSetAttribute(k3_surface_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+  else CKC(cudaFuncSetAttribute(k3_surface_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   // (the CA-CFAR kernel's shared-memory attribute is set by cfear_cfar_filter, which is the only place that needs it)
   {   // K5: K5_MINBLOCKS CTAs per SM, each with 1 KB reserved by the system and ~1 KB of static shared memory
@@ -449,7 +450,8 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  CK(launch_with_priority(k3_surface_points, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
+  if (c->pts_in_smem) CK(launch_with_priority(k3_surface_points<true>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
+  else CK(launch_with_priority(k3_surface_points<false>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   c->launches++;
   CK(cudaGetLastError());
   return CFEAR_OK;

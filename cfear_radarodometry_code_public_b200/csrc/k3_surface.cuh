@@ -19,6 +19,7 @@
 //   mean / covariance / closed-form 2x2 eigen -> validity -> ordered compaction into the cell slot
 //   fp32 means -> bucket grid (counting sort through hist) -> gstart / gxy / gidx of the slot
 #pragma once
+#include <type_traits>
 #include <cstdio>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -235,6 +236,9 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
 #define K3P(i)
 #endif
 
+// PTS_SMEM (= K3Params::pts_in_smem, fixed per context): a compile-time fact, so that every access to the point buffer and to
+// the shared-memory histogram is a shared-memory instruction (LDS / ATOMS) instead of a generic one.
+template <bool PTS_SMEM>
 __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_points(const K3Params p) {
 #ifdef CFEAR_K3_PROFILE
   long long k3t[16];
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
   // bufB (scatter target of the voxel sort, then the centroid / cell-mean lists: touched a few times per element) is
   // global scratch that stays in L2.  With the 16-bit histogram that is 109 KB per CTA: two CTAs per SM.
   float4* bufA; float4* bufB = p.g_bufB + (size_t)scan * cap; int* s_hist;
-  if (p.pts_in_smem) {
+  if constexpr (PTS_SMEM) {
     bufA = reinterpret_cast<float4*>(dyn_smem);
     s_hist = reinterpret_cast<int*>(bufA + cap);
   } else {
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
   if (p.mode == 0) {
     const int nslots = p.A * p.k;
     const float4* src = p.rowcloud + (size_t)scan * nslots;
-    if (p.pts_in_smem) {
+    if constexpr (PTS_SMEM) {
       if (tid == 0) mbar_init(&s_bar, 1);
       __syncthreads();
       if (tid == 0) {
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
     for (int a = tid; a < p.A; a += T) s_hist[a] = rc[a];
     __syncthreads();
     n = block_array_excl_scan(s_hist, p.A, s_warp);
-    if (p.pts_in_smem) mbar_wait(&s_bar, 0);
+    if constexpr (PTS_SMEM) mbar_wait(&s_bar, 0);
     // in-place left compaction, chunk by chunk (dest index <= source index), + Compensate
     const double* mot = p.mot ? p.mot + 3 * (size_t)scan : nullptr;
     const double m0 = mot ? mot[0] : 0.0, m1 = mot ? mot[1] : 0.0, m2 = mot ? mot[2] : 0.0;
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
         const int cnt = ((a + 1 < p.A) ? s_hist[a + 1] : n) - start;
         if (j < cnt) {
           have = true; dst = start + j;
-          pt = p.pts_in_smem ? bufA[s] : src[s];
+          if constexpr (PTS_SMEM) pt = bufA[s]; else pt = src[s];
           if (mot) {                                       // utils.cpp:96-113
             const double x = (double)pt.x, y = (double)pt.y;
 #ifdef CFEAR_K3_ATAN2
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
   } else {
     n = p.npts[scan];
     const float4* src = p.cloud + (size_t)scan * cap;
-    if (p.pts_in_smem) {
+    if constexpr (PTS_SMEM) {
       if (tid == 0) mbar_init(&s_bar, 1);
       __syncthreads();
       if (n > 0) {
@@ -362,14 +366,17 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
   const int minby = (int)floorf(mny * inv), maxby = (int)floorf(mxy * inv);
   const int divx = maxbx - minbx + 1, divy = maxby - minby + 1;
   const long long nbins_ll = (long long)divx * divy;
-  Hist16 hist; hist.w = reinterpret_cast<uint32_t*>(s_hist);
-  if (nbins_ll + 1 > K3_HIST_CAP) {
-    if (nbins_ll + 1 > p.g_hist_cap) {
-      if (tid == 0) { p.status[scan] = 1; p.pool.ncells[slot] = 0; }
-      return;
-    }
-    hist.w = reinterpret_cast<uint32_t*>(p.g_hist + (size_t)scan * (p.g_hist_cap + 1));
+  const bool hist_global = nbins_ll + 1 > K3_HIST_CAP;         // block-uniform; very sparse scans only
+  if (hist_global && nbins_ll + 1 > p.g_hist_cap) {
+    if (tid == 0) { p.status[scan] = 1; p.pool.ncells[slot] = 0; }
+    return;
   }
+  // The rest of the kernel exists twice, once per home of the voxel histogram, so that in the usual case the compiler
+  // knows it is shared memory (LDS / ATOMS instead of generic loads and atomics in the sort and the neighbourhood pass).
+  auto rest = [&](auto HG) {
+  Hist16 hist;
+  if constexpr (decltype(HG)::value) hist.w = reinterpret_cast<uint32_t*>(p.g_hist + (size_t)scan * (p.g_hist_cap + 1));
+  else hist.w = reinterpret_cast<uint32_t*>(s_hist);
   const int nbins = (int)nbins_ll;
   hist.zero(nbins + 1);
   __syncthreads();
@@ -566,6 +573,8 @@ __global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_poi
            scan, n, nvox, ncells, nbins, k3t[1] - k3t[0], k3t[2] - k3t[1], k3t[3] - k3t[2], k3t[4] - k3t[3], k3t[5] - k3t[4], k3t[6] - k3t[5],
            k3t[7] - k3t[6], k3t[8] - k3t[7], k3t[9] - k3t[8], k3t[10] - k3t[9], k3t[11] - k3t[10], k3t[11] - k3t[0]);
 #endif
+  };
+  if (hist_global) rest(std::true_type{}); else rest(std::false_type{});
 }
 
 // NN index for an uploaded cell set (cfear_cells_upload): one CTA per slot.
