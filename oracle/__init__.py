@@ -120,6 +120,11 @@ def nearest(means, queries, radius):
     return out
 
 
+def set_nn_tie_largest(on: bool):
+    """Test knob: NN ties between cells with identical fp32 means go to the largest index instead of the smallest."""
+    lib().orc_set_nn_tie_largest(int(bool(on)))
+
+
 def reg_cfg(cost="P2L", loss="Huber", loss_limit=0.1, weight_opt=0, cov_scale=1.0, regularization=1.0,
             radius=2.0, max_outer=8, min_outer=3, max_inner=20, solver_mode=0, gn_iters=10):
     ci = np.array([COST[cost] if isinstance(cost, str) else cost, LOSS[loss] if isinstance(loss, str) else loss,

@@ -248,7 +248,10 @@ void radius_search(const BucketGrid& G, float qx, float qy, float r, std::vector
 }
 
 // pointnormal.cpp:238-254  GetClosestIdx: exact fp32 1-NN, accepted iff d2 < d*d.
-// Ties: smallest index.
+// Ties (cells whose fp32 means coincide -- CFEAR's cell sets hold such duplicates): smallest index.  Which copy the
+// reference returns is decided by FLANN's tree walk; g_nn_tie_largest flips the choice to the largest index so that
+// tests can bound what that freedom does to a registration (tests/test_flann_pin.py).
+static int g_nn_tie_largest = 0;
 int nearest_within(const BucketGrid& G, double pxd, double pyd, double radius) {
   const float qx = (float)pxd, qy = (float)pyd;     // :241-242
   const int span = (int)std::ceil(radius / G.g) + 1;
@@ -261,7 +264,7 @@ int nearest_within(const BucketGrid& G, double pxd, double pyd, double radius) {
         const int i = G.items[s];
         const float dx = qx - G.px[i], dy = qy - G.py[i];
         float d2 = dx * dx; d2 += dy * dy;
-        if (d2 < best || (d2 == best && i < besti)) { best = d2; besti = i; }
+        if (d2 < best || (d2 == best && (g_nn_tie_largest ? i > besti : i < besti))) { best = d2; besti = i; }
       }
     }
   if (besti >= 0 && (double)best < radius * radius) return besti;   // :250
@@ -864,6 +867,8 @@ int orc_surface_points(const float* xyzi, int n, float radius, double downsample
 }
 
 // pointnormal.cpp:238-254 on a set of cell means.
+void orc_set_nn_tie_largest(int on) { g_nn_tie_largest = on; }
+
 void orc_nearest(const double* means, int n, const double* queries, int nq, double radius, int32_t* out) {
   CellSet cs; cs.n = n; cs.mean = means; cs.build_index();
   for (int q = 0; q < nq; ++q) out[q] = nearest_within(cs.grid, queries[2 * q], queries[2 * q + 1], radius);
