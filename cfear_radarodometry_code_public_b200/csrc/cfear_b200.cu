@@ -145,7 +145,7 @@ struct cfear_ctx {
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
-  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0, k5_smem_wide = 0, num_sms = 0;
   int g_hist_cap = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -283,8 +283,14 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
     CKC(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     const int fit = per_sm / K5_MINBLOCKS - 2048;
     c->k5_smem = std::min(K5_SMEM_BYTES > 0 ? K5_SMEM_BYTES : fit, max_optin - 1024);
+    // the wide form (one 384-thread CTA per SM, batches of at most one problem per SM) takes what one CTA may have;
+    // CFEAR_K5_WIDE=0 in the environment keeps every launch on the 128-thread form (A/B runs)
+    CKC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    const char* w = getenv("CFEAR_K5_WIDE");
+    c->k5_smem_wide = (w && w[0] == '0') ? 0 : max_optin - 2048;
   }
-  CKC(k5_set_smem_cost0(c->k5_smem)); CKC(k5_set_smem_cost1(c->k5_smem)); CKC(k5_set_smem_cost2(c->k5_smem));
+  CKC(k5_set_smem_cost0(c->k5_smem, c->k5_smem_wide)); CKC(k5_set_smem_cost1(c->k5_smem, c->k5_smem_wide));
+  CKC(k5_set_smem_cost2(c->k5_smem, c->k5_smem_wide));
 
   const size_t rows = (size_t)B * A;
   AL(c->d_polar, rows * R);
@@ -470,11 +476,12 @@ static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, con
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-bool launched = false;
+  const int wide = (nprob <= c->num_sms) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
+  bool launched = false;
   switch (p.cost) {
-    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
-    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
-    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, B.stream, c->prio[2]); break;
+    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
+    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
+    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
   }
   if (!launched) { g_err = "this build has no instantiation for the requested cost / loss"; return CFEAR_ERR_ARG; }
   c->launches++;

@@ -29,7 +29,11 @@ constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, THREE pro
                                                // A CTA alone is slower than the 2-per-SM forms (0.381 ms / 256 problems vs 0.343 for 192 threads,
                                                // 0.347 for 128 threads with 202 registers), but with four steps in flight the step takes 0.337 ms
                                                // instead of 0.370 / 0.356 (profiles/r02q_k5_threads_ab.txt, profiles/r02v_k5_three_per_sm_ab.txt)
-constexpr int K5_WARPS = K5_THREADS / 32;
+// The WIDE form: the same kernel with one 384-thread CTA per SM, launched when a batch has no more problems than the GPU
+// has SMs (sequence replay with few sequences, the drop-in classes' one-scan-at-a-time calls).  There the SM would hold one
+// 128-thread CTA and the step lasts as long as one problem does; twelve warps cut the association and evaluation passes
+// to a third (the register budget is the same 65536 / 384 = 170 per thread).  Only the product instantiations (AUX = false).
+constexpr int K5_THREADS_WIDE = 384;
 #ifndef CFEAR_K5_MINBLOCKS
 #define CFEAR_K5_MINBLOCKS (CFEAR_K5_THREADS > 256 ? 1 : (CFEAR_K5_THREADS > 128 ? 2 : 3))
 #endif
@@ -239,8 +243,8 @@ struct LMShared {
 // that all warps run): round 1 used a producer / consumer form in which warp 0 and the serving warps reached the same
 // named barrier from different code locations -- legal PTX, but compute-sanitizer's synccheck reports it as "divergent
 // thread(s) in block".  With the shared loop all three sanitizer tools are clean.
-__device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(K5_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(K5_THREADS) : "memory"); }
+template <int NT> __device__ __forceinline__ void bar_a() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+template <int NT> __device__ __forceinline__ void bar_b() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); }
 
 // Warp reduction of the 10 sums by recursive halving: at each step a lane hands the half of its values its partner
 // keeps to that partner, so 5+3+2+1+1 = 12 exchanges replace the 50 of ten separate butterflies.  Ends with sum i in the
@@ -263,7 +267,7 @@ __device__ __forceinline__ void warp_reduce10(const double acc[10], double* s_pa
 }
 
 // every warp: this thread's share of the list at (x, cs, sn) -> per-warp partial sums in s_part[warp][10]
-template <int COST, int LOSS>
+template <int COST, int LOSS, int NT>
 __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& res, int nres, const double x[3], double cs,
                                              double sn, double* s_part) {
   double acc[10];
@@ -273,8 +277,8 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
   if (nres <= res.cap_s) {                   // the whole list is in shared memory (the normal case): no per-load path select
     const double2* f1 = res.s, * f2 = res.s + res.cap_s, * f3 = res.s + 2 * res.cap_s;
     const uint16_t* fj = res.sj; const double2* sm = res.src_mean;
-    for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
-      const int r2 = r + K5_THREADS;
+    for (; r + NT < nres; r += 2 * NT) {
+      const int r2 = r + NT;
       const int j0 = fj[r], j1 = fj[r2];
       const double2 q0 = f1[r], ab0 = f2[r], cw0 = f3[r];
       const double2 q1 = f1[r2], ab1 = f2[r2], cw1 = f3[r2];
@@ -284,8 +288,8 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
     }
     if (r < nres) accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, sm[fj[r]], f1[r], f2[r], f3[r], acc);
   } else {
-    for (; r + K5_THREADS < nres; r += 2 * K5_THREADS) {
-      const int r2 = r + K5_THREADS;
+    for (; r + NT < nres; r += 2 * NT) {
+      const int r2 = r + NT;
       const double2 p0 = res.ldp(r), q0 = res.ld(0, r), ab0 = res.ld(1, r), cw0 = res.ld(2, r);
       const double2 p1 = res.ldp(r2), q1 = res.ld(0, r2), ab1 = res.ld(1, r2), cw1 = res.ld(2, r2);
       accumulate<COST, LOSS, true>(loss_limit, cs, sn, x, p0, q0, ab0, cw0, acc);
@@ -300,7 +304,7 @@ __device__ __forceinline__ void eval_contrib(double loss_limit, const ResList& r
 // decision to stop; it publishes either in shared memory, barrier A, every warp accumulates its share of the residual
 // list and stores its 10 partial sums, barrier B, warp 0 adds the K5_WARPS partials in fixed order (bit-reproducible) and,
 // in the AUX instantiations, the soft prior's block.  Returns false (block-uniform) on the stop mark; `ev` is valid in warp 0.
-template <int COST, int LOSS, bool AUX>
+template <int COST, int LOSS, bool AUX, int NT>
 __device__ __forceinline__ bool eval_round(double loss_limit, const ResList& res, int nres, bool w0, bool stop, const double y[3],
                                            EvalOut& ev, LMShared* sh, double* s_part PROF_PARAM) {
   PROF_T(te0);
@@ -310,12 +314,12 @@ __device__ __forceinline__ bool eval_round(double loss_limit, const ResList& res
     if (lane_id() == 0) { sh->bc[0] = yy[0]; sh->bc[1] = yy[1]; sh->bc[2] = yy[2]; sh->bc[3] = cs; sh->bc[4] = sn; sh->ctl = stop ? 0 : 1; }
   }
   PROF_T(te1);
-  bar_a();
+  bar_a<NT>();
   if (sh->ctl == 0) return false;
   if (!w0) { yy[0] = sh->bc[0]; yy[1] = sh->bc[1]; yy[2] = sh->bc[2]; cs = sh->bc[3]; sn = sh->bc[4]; }
-  eval_contrib<COST, LOSS>(loss_limit, res, nres, yy, cs, sn, s_part);
+  eval_contrib<COST, LOSS, NT>(loss_limit, res, nres, yy, cs, sn, s_part);
   PROF_T(te2);
-  bar_b();
+  bar_b<NT>();
   PROF_T(te3);
   PROF_ADD(prof[4], te0, te1); PROF_ADD(prof[5], te1, te2); PROF_ADD(prof[6], te2, te3); PROF_ADD(prof[7], 0, 1);
   if (w0) {
@@ -324,7 +328,7 @@ __device__ __forceinline__ bool eval_round(double loss_limit, const ResList& res
 #pragma unroll
     for (int i = 0; i < 10; ++i) tot[i] = s_part[i];
 #pragma unroll
-    for (int w = 1; w < K5_WARPS; ++w) {
+    for (int w = 1; w < NT / 32; ++w) {
 #pragma unroll
       for (int i = 0; i < 10; ++i) tot[i] += s_part[w * 10 + i];
     }
@@ -409,7 +413,7 @@ __device__ __forceinline__ void store_accepted(LMShared* sh, const EvalOut& e) {
 // evaluated with its Jacobian in the same pass, so an accepted step needs no second pass over the residuals.  x and sum
 // are valid in warp 0; LMShared::acc_H is left holding J^T J (loss-corrected, unscaled) at the returned x, which is what
 // GetCovariance needs.
-template <int COST, int LOSS, bool AUX>
+template <int COST, int LOSS, bool AUX, int NT>
 __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res, int nres, bool w0, double x[3], SolveSum& sum,
                                          LMShared* sh, double* s_part PROF_PARAM) {
   const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8;
@@ -427,7 +431,7 @@ __device__ __forceinline__ void lm_solve(const RegParams& P, const ResList& res,
   double xc[3] = {x[0], x[1], x[2]}, delta[3] = {0, 0, 0};              // the first round evaluates x itself
   for (;;) {
     EvalOut evc;                                                        // (dead across the round: not loop-carried)
-    if (!eval_round<COST, LOSS, AUX>(P.loss_limit, res, nres, w0, stop, xc, evc, sh, s_part PROF_ARG)) break;
+    if (!eval_round<COST, LOSS, AUX, NT>(P.loss_limit, res, nres, w0, stop, xc, evc, sh, s_part PROF_ARG)) break;
     if (!w0) continue;
     if (first) {                                                        // iteration 0: cost, gradient, Jacobi scaling at x
       first = false;
@@ -668,10 +672,10 @@ __device__ __forceinline__ void make_record(const RegParams& P, const RelT& T, d
 //   2. one block scan gives every accepted pair its position, in (keyframe, cell) order; the residual records are then
 //      built position by position (two in flight per thread) and stored straight into the residual list.
 // Returns the number of residual blocks (block-uniform).
-template <int COST, bool AUX>
+template <int COST, bool AUX, int NT>
 __device__ __forceinline__ int build_problem(const RegParams& P, const AssocCtx& C, const ResList& res, int32_t* assoc, double* assoc_sim,
                                              int* s_warp, uint16_t* s_nn, uint16_t* s_list, int tile PROF_PARAM) {
-  const int T = K5_THREADS, tid = threadIdx.x;
+  const int T = NT, tid = threadIdx.x;
   const int n_src = C.n_src, npairs = C.K * n_src;
   const double angle_outlier = cos(M_PI / 6.0);
   const int cap = res.cap_g;
@@ -841,11 +845,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // AUX = false: the ceres_lm solver only (the product path).  AUX = true: the two auxiliary modes -- gn_fixed and cost
 // only -- which live in their own instantiation so that their code does not cost the main kernel registers.
-template <int COST, int LOSS, bool AUX>
-__global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(const RegParams P) {
+template <int COST, int LOSS, bool AUX, int NT = K5_THREADS>
+__global__ void __launch_bounds__(NT, NT == K5_THREADS ? CFEAR_K5_MINBLOCKS : 1) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
-  __shared__ double s_part[K5_WARPS * 10];
+  __shared__ double s_part[(NT / 32) * 10];
   __shared__ LMShared s_lm;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_grid_bytes;
@@ -912,7 +916,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
   if ((uint32_t)C.n_src * 32u <= (uint32_t)P.smem_bytes / 4) {
     double2* sm = reinterpret_cast<double2*>(dyn_smem + u_off);
     double2* sn = sm + C.n_src;
-    for (int j = tid; j < C.n_src; j += K5_THREADS) { sm[j] = C.src_mean[j]; sn[j] = C.src_normal[j]; }
+    for (int j = tid; j < C.n_src; j += NT) { sm[j] = C.src_mean[j]; sn[j] = C.src_normal[j]; }
     C.src_mean = sm; C.src_normal = sn;
     u_off += (uint32_t)((C.n_src * 32 + 127) & ~127);
   }
@@ -961,7 +965,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
     sincos(x[2], &C.sn_s, &C.cs_s);
     C.radius = (itr == 1) ? 2 * P.radius : P.radius;
     C.nnr = nn_radius(C.radius);
-    const int n = build_problem<COST, AUX>(P, C, res, assoc, assoc_sim, s_warp, s_nn, s_list, tile PROF_ARG);
+    const int n = build_problem<COST, AUX, NT>(P, C, res, assoc, assoc_sim, s_warp, s_nn, s_list, tile PROF_ARG);
     if (overlay) grids_resident = false;
     PROF_T(ta2);
     PROF_ADD(prof[2], ta0, ta1); PROF_ADD(prof[0], ta1, ta2);
@@ -981,7 +985,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
     if (nres * per_block <= 1) success = false;                                 // :205-208
     else {
       EvalOut ev;
-      eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+      eval_round<COST, LOSS, false, NT>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
       if (tid == 0) sh->out_final_cost = ev.cost;
       __syncthreads();
       sum.final_cost = sh->out_final_cost;
@@ -995,7 +999,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
       if (nres * per_block <= 1) { success = false; break; }
       {
         EvalOut ev;
-        eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+        eval_round<COST, LOSS, false, NT>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
         if (w0) {
           double y[3]; const double nb[3] = {-ev.g[0], -ev.g[1], -ev.g[2]};
           const bool okw = chol3_solve(ev.H, nb, y);
@@ -1017,7 +1021,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
     outer = it;
     if (success) {
       EvalOut ev;
-      eval_round<COST, LOSS, false>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+      eval_round<COST, LOSS, false, NT>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
       if (tid == 0) sh->out_final_cost = ev.cost;
       __syncthreads();
       sum.final_cost = sh->out_final_cost;
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
       if (nres * per_block <= 1) { success = false; break; }                    // :370, :114
       PROF_T(ts0);
       const double x_in[3] = {x[0], x[1], x[2]};
-      lm_solve<COST, LOSS, AUX>(P, res, nres, w0, x, sum, sh, s_part PROF_ARG);          // :117
+      lm_solve<COST, LOSS, AUX, NT>(P, res, nres, w0, x, sum, sh, s_part PROF_ARG);          // :117
       if (tid == 0) {
         sh->out_x[0] = x[0]; sh->out_x[1] = x[1]; sh->out_x[2] = x[2];
         sh->out_final_cost = sum.final_cost; sh->out_last_rel = sum.last_rel;
@@ -1101,7 +1105,7 @@ __global__ void __launch_bounds__(K5_THREADS, CFEAR_K5_MINBLOCKS) k5_register(co
 #pragma unroll
       for (int i = 0; i < 6; ++i) ev.H[i] = sh->acc_H[i];
     } else {                                   // (block-uniform) one more round at the restored pose
-      eval_round<COST, LOSS, AUX>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
+      eval_round<COST, LOSS, AUX, NT>(P.loss_limit, res, nres, w0, false, x, ev, sh, s_part PROF_ARG);
     }
     if (w0) {
       double inv[9]; bool ok = true;
