@@ -145,7 +145,7 @@ struct cfear_ctx {
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
-  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0, k5_smem_wide = 0, num_sms = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0, k5_smem_wide = 0, num_sms = 0, k3_wide = 0;
   int g_hist_cap = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -274,7 +274,12 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   c->pts_in_smem = (full + 2048 <= (size_t)max_optin) ? 1 : 0;
   c->k3_smem = c->pts_in_smem ? full : hist_bytes;
   c->k4_smem = hist_bytes;
-  if (c->pts_in_smem) CKC(cudaFuncSetAttribute(k3_surface_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+  if (c->pts_in_smem) {
+    CKC(cudaFuncSetAttribute(k3_surface_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+    CKC(cudaFuncSetAttribute(k3_surface_points<true, K3_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
+    const char* w3 = getenv("CFEAR_K3_WIDE");                        // CFEAR_K3_WIDE=0: every launch on the 512-thread form (A/B runs)
+    c->k3_wide = (w3 && w3[0] == '0') ? 0 : 1;
+  }
   else CKC(cudaFuncSetAttribute(k3_surface_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
   // (the CA-CFAR kernel's shared-memory attribute is set by cfear_cfar_filter, which is the only place that needs it)
@@ -456,7 +461,9 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  if (c->pts_in_smem) CK(launch_with_priority(k3_surface_points<true>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
+  if (c->pts_in_smem && c->k3_wide && nscans <= c->num_sms)          // at most one scan per SM: one 1024-thread CTA each
+    CK(launch_with_priority(k3_surface_points<true, K3_THREADS_WIDE>, nscans, K3_THREADS_WIDE, c->k3_smem, B.stream, c->prio[1], p));
+  else if (c->pts_in_smem) CK(launch_with_priority(k3_surface_points<true>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   else CK(launch_with_priority(k3_surface_points<false>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   c->launches++;
   CK(cudaGetLastError());

@@ -36,6 +36,10 @@ namespace cfear {
 #define CFEAR_K3_MINBLOCKS 2
 #endif
 constexpr int K3_THREADS = CFEAR_K3_THREADS;
+#ifndef CFEAR_K3_THREADS_WIDE
+#define CFEAR_K3_THREADS_WIDE 1024
+#endif
+constexpr int K3_THREADS_WIDE = CFEAR_K3_THREADS_WIDE;
 #ifndef CFEAR_K3_LPC
 #define CFEAR_K3_LPC 2
 #endif
@@ -238,8 +242,11 @@ __device__ inline void build_nn_grid(const CellPool& pool, int slot, const float
 
 // PTS_SMEM (= K3Params::pts_in_smem, fixed per context): a compile-time fact, so that every access to the point buffer and to
 // the shared-memory histogram is a shared-memory instruction (LDS / ATOMS) instead of a generic one.
-template <bool PTS_SMEM>
-__global__ void __launch_bounds__(K3_THREADS, CFEAR_K3_MINBLOCKS) k3_surface_points(const K3Params p) {
+// NT = K3_THREADS_WIDE: the same kernel as one 1024-thread CTA per SM, launched for batches of at most one scan per SM
+// (sequence replay with few sequences, the drop-in classes' single-scan calls), where a scan's latency is the step.
+// Every loop strides by blockDim.x and no sum depends on the thread count, so the cells are bit-identical.
+template <bool PTS_SMEM, int NT = K3_THREADS>
+__global__ void __launch_bounds__(NT, NT == K3_THREADS ? CFEAR_K3_MINBLOCKS : 1) k3_surface_points(const K3Params p) {
 #ifdef CFEAR_K3_PROFILE
   long long k3t[16];
 #endif
