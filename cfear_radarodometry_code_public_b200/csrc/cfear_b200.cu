@@ -277,8 +277,7 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
   if (c->pts_in_smem) {
     CKC(cudaFuncSetAttribute(k3_surface_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
     CKC(cudaFuncSetAttribute(k3_surface_points<true, K3_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
-    const char* w3 = getenv("CFEAR_K3_WIDE");                        // CFEAR_K3_WIDE=0: every launch on the 512-thread form (A/B runs)
-    c->k3_wide = (w3 && w3[0] == '0') ? 0 : 1;
+    c->k3_wide = 1;
   }
   else CKC(cudaFuncSetAttribute(k3_surface_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k3_smem));
   CKC(cudaFuncSetAttribute(k4_build_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
@@ -288,11 +287,9 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
     CKC(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     const int fit = per_sm / K5_MINBLOCKS - 2048;
     c->k5_smem = std::min(K5_SMEM_BYTES > 0 ? K5_SMEM_BYTES : fit, max_optin - 1024);
-    // the wide form (one 384-thread CTA per SM, batches of at most one problem per SM) takes what one CTA may have;
-    // CFEAR_K5_WIDE=0 in the environment keeps every launch on the 128-thread form (A/B runs)
+    // the wide form (one 384-thread CTA per SM, batches of at most one problem per SM) takes what one CTA may have
     CKC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    const char* w = getenv("CFEAR_K5_WIDE");
-    c->k5_smem_wide = (w && w[0] == '0') ? 0 : max_optin - 2048;
+    c->k5_smem_wide = max_optin - 2048;
   }
   CKC(k5_set_smem_cost0(c->k5_smem, c->k5_smem_wide)); CKC(k5_set_smem_cost1(c->k5_smem, c->k5_smem_wide));
   CKC(k5_set_smem_cost2(c->k5_smem, c->k5_smem_wide));
@@ -440,6 +437,14 @@ static int launch_peaks(cfear_ctx* c, const uint8_t* d_polar, int nscans) {
   return CFEAR_OK;
 }
 
+// CFEAR_K3_WIDE=0 / CFEAR_K5_WIDE=0 in the environment keep small batches on the batch-sized forms of K3 / K5 (512 / 128
+// threads).  Read at every launch so that the tests can run one context both ways; the choice never changes K3's results
+// and moves K5's sums by rounding only.
+static bool wide_allowed(const char* name) {
+  const char* v = getenv(name);
+  return !(v && v[0] == '0');
+}
+
 static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud, int off = 0) {
   K3Params p;
   p.mode = mode; p.A = c->cfg.azimuths; p.k = c->cfg.k_strongest;
@@ -461,7 +466,7 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  if (c->pts_in_smem && c->k3_wide && nscans <= c->num_sms)          // at most one scan per SM: one 1024-thread CTA each
+  if (c->pts_in_smem && c->k3_wide && nscans <= c->num_sms && wide_allowed("CFEAR_K3_WIDE"))          // at most one scan per SM: one 1024-thread CTA each
     CK(launch_with_priority(k3_surface_points<true, K3_THREADS_WIDE>, nscans, K3_THREADS_WIDE, c->k3_smem, B.stream, c->prio[1], p));
   else if (c->pts_in_smem) CK(launch_with_priority(k3_surface_points<true>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   else CK(launch_with_priority(k3_surface_points<false>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
@@ -483,7 +488,7 @@ static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, con
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-  const int wide = (nprob <= c->num_sms) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
+  const int wide = (nprob <= c->num_sms && wide_allowed("CFEAR_K5_WIDE")) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
   bool launched = false;
   switch (p.cost) {
     case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;

@@ -7,7 +7,7 @@ import pytest
 
 from cfear_radarodometry_code_public_b200 import capi, synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_form")]
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

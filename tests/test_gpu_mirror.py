@@ -10,7 +10,7 @@ import pytest
 import helpers
 from cfear_radarodometry_code_public_b200.synth import se2_inv, se2_mul
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_form")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "cfear_radarodometry_code_public_b200")
 

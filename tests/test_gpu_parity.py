@@ -10,7 +10,7 @@ import pytest
 from cfear_radarodometry_code_public_b200 import capi
 import helpers
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_form")]
 
 POS_TOL, ROT_TOL = 1e-4, 1e-5
 
