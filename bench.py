@@ -321,7 +321,10 @@ def main():
                                     t_poses[0].data_ptr(), t_cov[0].data_ptr(), t_stats[0].data_ptr())
     ctx.sync()
     nser, stage_ser = ctx.stage_timing(False)
-    assert np.array_equal(t_poses[0].cpu().numpy(), poses_dev), "overlapped and stream-ordered steps disagree"
+    # bit-identical at the benchmark's batch size (both arms launch the batch-sized kernels); a small --nprob may put the
+    # stream-ordered arm on K5's wide form, whose sums are formed in another order: rounding only
+    dser = np.abs(t_poses[0].cpu().numpy() - poses_dev).max()
+    assert dser == 0.0 if nprob > 148 else dser < 1e-11, "overlapped and stream-ordered steps disagree (%g)" % dser
 
     # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8(d), per-kernel split in DESIGN.md) ----
     hbm_peak, peak_src = peaks()

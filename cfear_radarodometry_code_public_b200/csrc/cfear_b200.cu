@@ -162,6 +162,7 @@ struct cfear_ctx {
   PipeBufs pb[CFEAR_NPIPES + 1];    // [0] aliases the buffers above on the context stream; [1..] the overlapped steps' sets
   bool pipes_ready = false, inflight = false;
   int npipes = 4, next_pipe = 0, last_pipe = 0;
+  int launch_conc = 1;              // steps this launch shares the GPU with (cfear_odometry_step_batch_dev_submit: steps_in_flight)
   int pipe_user = 0;                // who enqueued on the internal streams last: 1 = overlapped batch steps, 2 = sequence replay
 
   template <typename T> int alloc(T** p, size_t count) {
@@ -444,6 +445,12 @@ static bool wide_allowed(const char* name) {
   const char* v = getenv(name);
   return !(v && v[0] == '0');
 }
+// One wide CTA per SM pays when every scan / problem in flight can have an SM of its own: a stream-ordered launch of at
+// most num_sms of them, or overlapped steps whose sum stays near that (measured, five steps in flight: 32-problem steps
+// 428 k scans/s wide vs 338 k batch-sized, 64-problem steps 549 k vs 572 k, 128: 550 k vs 767 k; profiles/r04g_*.txt).
+static bool wide_batch(const cfear_ctx* c, int n) {
+  return c->launch_conc <= 1 ? n <= c->num_sms : 2 * n * c->launch_conc <= 3 * c->num_sms;
+}
 
 static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, const double* d_mot, const int32_t* d_slots, bool write_cloud, int off = 0) {
   K3Params p;
@@ -466,7 +473,7 @@ static int launch_k3(cfear_ctx* c, const PipeBufs& B, int mode, int nscans, cons
     p.g_bufB += o * p.cap_pts;
     p.g_hist += o * (p.g_hist_cap + 1);
   }
-  if (c->pts_in_smem && c->k3_wide && nscans <= c->num_sms && wide_allowed("CFEAR_K3_WIDE"))          // at most one scan per SM: one 1024-thread CTA each
+  if (c->pts_in_smem && c->k3_wide && wide_batch(c, nscans) && wide_allowed("CFEAR_K3_WIDE"))          // at most one scan per SM: one 1024-thread CTA each
     CK(launch_with_priority(k3_surface_points<true, K3_THREADS_WIDE>, nscans, K3_THREADS_WIDE, c->k3_smem, B.stream, c->prio[1], p));
   else if (c->pts_in_smem) CK(launch_with_priority(k3_surface_points<true>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
   else CK(launch_with_priority(k3_surface_points<false>, nscans, K3_THREADS, c->k3_smem, B.stream, c->prio[1], p));
@@ -488,7 +495,7 @@ static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, con
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-  const int wide = (nprob <= c->num_sms && wide_allowed("CFEAR_K5_WIDE")) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
+  const int wide = (wide_batch(c, nprob) && wide_allowed("CFEAR_K5_WIDE")) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
   bool launched = false;
   switch (p.cost) {
     case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
@@ -871,7 +878,12 @@ int cfear_odometry_step_batch_dev_submit(cfear_ctx* c, int nprob, const uint8_t*
   PipeBufs& B = c->pb[pi];
   CK(cudaEventRecord(B.in, c->stream));
   CK(cudaStreamWaitEvent(B.stream, B.in, 0));
-  if (nprob > 0) RC(step_dev(c, B, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats));
+  if (nprob > 0) {
+    c->launch_conc = c->npipes;                          // this step shares the GPU with the other steps in flight
+    const int rc = step_dev(c, B, nprob, d_polar, d_mot, d_kf_slots, K, d_cur_slots, d_poses, d_cov36, d_stats);
+    c->launch_conc = 1;
+    if (rc != CFEAR_OK) return rc;
+  }
   CK(cudaEventRecord(B.done, B.stream));
   CK(cudaEventRecord(c->ticket_ev[ticket], B.stream));
   c->inflight = true; c->last_pipe = pi;
