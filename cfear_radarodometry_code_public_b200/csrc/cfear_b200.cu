@@ -145,7 +145,7 @@ struct cfear_ctx {
   int timing = 0;
   float stage_ms[3] = {0, 0, 0};
   int cap_pts = 0, max_cells = 0, grid_cap = 0, res_cap = 0;
-  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0, k5_smem_wide = 0, num_sms = 0, k3_wide = 0;
+  int pts_in_smem = 0; size_t k3_smem = 0, k4_smem = 0; int k5_smem = 0, k5_smem_mid = 0, k5_smem_wide = 0, num_sms = 0, k3_wide = 0;
   int g_hist_cap = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -291,9 +291,10 @@ int cfear_create(const cfear_config* cfg, cfear_ctx** out) {
     // the wide form (one 384-thread CTA per SM, batches of at most one problem per SM) takes what one CTA may have
     CKC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     c->k5_smem_wide = max_optin - 2048;
+    c->k5_smem_mid = std::min(per_sm / 2 - 2048, max_optin - 2048);     // two 192-thread CTAs per SM
   }
-  CKC(k5_set_smem_cost0(c->k5_smem, c->k5_smem_wide)); CKC(k5_set_smem_cost1(c->k5_smem, c->k5_smem_wide));
-  CKC(k5_set_smem_cost2(c->k5_smem, c->k5_smem_wide));
+  CKC(k5_set_smem_cost0(c->k5_smem, c->k5_smem_mid, c->k5_smem_wide)); CKC(k5_set_smem_cost1(c->k5_smem, c->k5_smem_mid, c->k5_smem_wide));
+  CKC(k5_set_smem_cost2(c->k5_smem, c->k5_smem_mid, c->k5_smem_wide));
 
   const size_t rows = (size_t)B * A;
   AL(c->d_polar, rows * R);
@@ -495,12 +496,20 @@ static int launch_k5(cfear_ctx* c, const PipeBufs& B, int nprob, int nscans, con
   if (solver_mode_override >= 0) p.solver_mode = solver_mode_override;
   if (p.cost < 0 || p.cost > 2 || p.loss < 0 || p.loss > 5) { g_err = "unknown cost / loss type"; return CFEAR_ERR_ARG; }
   p.smem_bytes = c->k5_smem;
-  const int wide = (wide_batch(c, nprob) && wide_allowed("CFEAR_K5_WIDE")) ? c->k5_smem_wide : 0;      // at most one problem per SM: one 384-thread CTA each
+  // launch form: 2 = one 384-thread CTA per SM (at most one problem per SM), 1 = two 192-thread CTAs per SM (a stream-ordered
+  // launch of at most two problems per SM), 0 = three 128-thread CTAs per SM.  CFEAR_K5_FORM=0|1|2 forces one (tests, A/B runs).
+  int form = 0;
+  if (wide_allowed("CFEAR_K5_WIDE")) {
+    if (wide_batch(c, nprob)) form = 2;
+    else if (c->launch_conc <= 1 && nprob <= 2 * c->num_sms) form = 1;
+  }
+  if (const char* f = getenv("CFEAR_K5_FORM")) { if (f[0] >= '0' && f[0] <= '2') form = f[0] - '0'; }
+  const int smem_form = form == 2 ? c->k5_smem_wide : c->k5_smem_mid;
   bool launched = false;
   switch (p.cost) {
-    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
-    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
-    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, wide, B.stream, c->prio[2]); break;
+    case 0: launched = k5_launch_cost0(p, nprob, c->k5_smem, form, smem_form, B.stream, c->prio[2]); break;
+    case 1: launched = k5_launch_cost1(p, nprob, c->k5_smem, form, smem_form, B.stream, c->prio[2]); break;
+    case 2: launched = k5_launch_cost2(p, nprob, c->k5_smem, form, smem_form, B.stream, c->prio[2]); break;
   }
   if (!launched) { g_err = "this build has no instantiation for the requested cost / loss"; return CFEAR_ERR_ARG; }
   c->launches++;

@@ -34,6 +34,9 @@ constexpr int K5_THREADS = CFEAR_K5_THREADS;   // 4 warps per problem, THREE pro
 // 128-thread CTA and the step lasts as long as one problem does; twelve warps cut the association and evaluation passes
 // to a third (the register budget is the same 65536 / 384 = 170 per thread).  Only the product instantiations (AUX = false).
 constexpr int K5_THREADS_WIDE = 384;
+// The MID form: 192 threads, two CTAs per SM, for a stream-ordered launch of more problems than SMs but at most two per
+// SM (bench.py's 256-problem step when nothing overlaps it): the third 128-thread slot would stay empty there.
+constexpr int K5_THREADS_MID = 192;
 #ifndef CFEAR_K5_MINBLOCKS
 #define CFEAR_K5_MINBLOCKS (CFEAR_K5_THREADS > 256 ? 1 : (CFEAR_K5_THREADS > 128 ? 2 : 3))
 #endif
@@ -846,7 +849,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // AUX = false: the ceres_lm solver only (the product path).  AUX = true: the two auxiliary modes -- gn_fixed and cost
 // only -- which live in their own instantiation so that their code does not cost the main kernel registers.
 template <int COST, int LOSS, bool AUX, int NT = K5_THREADS>
-__global__ void __launch_bounds__(NT, NT == K5_THREADS ? CFEAR_K5_MINBLOCKS : 1) k5_register(const RegParams P) {
+__global__ void __launch_bounds__(NT, NT == K5_THREADS ? CFEAR_K5_MINBLOCKS : (NT == K5_THREADS_MID ? 2 : 1)) k5_register(const RegParams P) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int s_warp[33];
   __shared__ double s_part[(NT / 32) * 10];
