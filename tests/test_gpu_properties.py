@@ -94,3 +94,35 @@ def test_registration_is_se2_equivariant(full):
             check(np.array([37.5, -12.25, 0.7]))
     finally:
         c.update_config(cost="P2D")
+
+
+@pytest.mark.parametrize("nprob", [148, 149, 296, 297])
+def test_k5_launch_form_follows_the_batch_size(monkeypatch, nprob):
+    """cfear_register_batch picks K5's launch form from the batch size (one 384-thread CTA per SM up to one problem per
+    SM, 192 x 2 up to two, 128 x 3 beyond; csrc/cfear_b200.cu launch_k5).  The same eight problems replicated to a batch
+    on either side of each boundary give the poses of the forced 128-thread form to rounding, with equal iteration
+    counts, and every copy of a problem gives the same bits."""
+    for v in ("CFEAR_K3_WIDE", "CFEAR_K5_WIDE", "CFEAR_K5_FORM"):
+        monkeypatch.delenv(v, raising=False)
+    base = 8
+    c = capi.Context(max_batch=nprob, max_cellsets=2 * base, max_keyframes=1, cost="P2D", loss="Huber", weight_opt=4,
+                     regularization=0.1)
+    P = np.zeros((nprob, 2, 3))
+    slots = np.zeros((nprob, 2), np.int32)
+    for b in range(base):
+        sets, _, _ = workload.make_cellset_pair(400, seed=40 + b, delta=(0.3 + 0.02 * b, -0.2, np.deg2rad(1.0 + 0.1 * b)))
+        c.cells_upload(2 * b, sets[0]); c.cells_upload(2 * b + 1, sets[1])
+    for i in range(nprob):
+        slots[i] = (2 * (i % base), 2 * (i % base) + 1)
+    gp, _gcov, gst, _ = c.register_batch(slots, P)
+    monkeypatch.setenv("CFEAR_K5_FORM", "0")
+    rp, _rcov, rst, _ = c.register_batch(slots[:base], P[:base])
+    c.close()
+    assert gst["success"].all() and rst["success"].all()
+    for i in range(nprob):
+        assert np.array_equal(gp[i], gp[i % base])
+    d = gp[:base, 1] - rp[:, 1]
+    assert np.hypot(d[:, 0], d[:, 1]).max() < 1e-11 and np.abs(d[:, 2]).max() < 1e-12
+    assert np.array_equal(gst["outer_iterations"][:base], rst["outer_iterations"])
+    assert np.array_equal(gst["inner_iterations"][:base], rst["inner_iterations"])
+    assert np.array_equal(gst["num_residuals"][:base], rst["num_residuals"])
