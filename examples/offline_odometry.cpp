@@ -112,13 +112,19 @@ static int run(int argc, char** argv) {
   radarDriver driver(rad_pars, true);
   OdometryKeyframeFuser fuser(odom_pars, true);
   EvalTrajectory eval;
-  std::vector<uint8_t> img((size_t)A * R);
+  // the frame buffer is this program's own, so it is page-locked: the image then goes to the device as one DMA at link
+  // rate instead of being staged by the driver (0.1 ms of a 0.6 ms frame); pageable memory works as well
+  const size_t img_bytes = (size_t)A * R;
+  std::vector<uint8_t> img_pageable;
+  uint8_t* img_data = static_cast<uint8_t*>(cfear_alloc_pinned(img_bytes));
+  const bool img_pinned = img_data != nullptr;
+  if (!img_pinned) { img_pageable.resize(img_bytes); img_data = img_pageable.data(); }
   double tot = 0;
   for (int frame = 0; frame < n; ++frame) {
     uint64_t stamp = 0;
-    if (fread(&stamp, 8, 1, f) != 1 || fread(img.data(), 1, img.size(), f) != img.size()) { std::cerr << "truncated frame file" << std::endl; return 4; }
+    if (fread(&stamp, 8, 1, f) != 1 || fread(img_data, 1, img_bytes, f) != img_bytes) { std::cerr << "truncated frame file" << std::endl; return 4; }
     const auto t0 = std::chrono::steady_clock::now();
-    PolarImage pim; pim.rows = A; pim.cols = R; pim.data = img.data(); pim.stamp = stamp;
+    PolarImage pim; pim.rows = A; pim.cols = R; pim.data = img_data; pim.stamp = stamp;
     CloudPtr cloud_filtered, cloud_filtered_peaks;
     driver.CallbackOffline(pim, cloud_filtered, cloud_filtered_peaks);                                   // offline_odometry.cpp:103
     Affine3d Tcurrent; Matrix6d cov_current;
@@ -129,6 +135,7 @@ static int run(int argc, char** argv) {
     std::cout << "Frame: " << frame << ", dur: " << d << ", avg: " << (frame + 1) / tot << std::endl;          // :124
   }
   fclose(f);
+  if (img_pinned) cfear_free_pinned(img_data);
   // EvalTrajectory::Save (eval_trajectory.cpp:145-167): <est_directory>/<NN>.txt with NN from the sequence name
   const std::string nn = EvalTrajectory::SequenceToFileName(sequence);
   EvalTrajectory::Write(est_dir + "/" + nn + ".txt", eval.est_vek);
