@@ -139,7 +139,7 @@ def test_oracle_lm_matches_an_independent_ceres_loop(orc, cost, seed, offset):
         return cost_, (res * w[:, None]).ravel(), (Jr * w[:, None, None]).reshape(-1, 3)
 
     x, n_it, final_cost, _ = _ceres_lm(fun, x0)
-    assert st.num_residuals == rows * p.shape[0] > 100
+    assert st.num_residuals == rows * p.shape[0] > 50
     assert n_it == st.inner_iterations, (n_it, st.inner_iterations)
     np.testing.assert_allclose(final_cost, st.final_cost, rtol=1e-9)
     assert np.hypot(*(x[:2] - x_orc[:2])) < 1e-9 and abs(x[2] - x_orc[2]) < 1e-10
