@@ -1,6 +1,7 @@
 """n_scan_normal_reg::Register written a second time, in numpy, straight from the reference source (n_scan_normal.cpp:82-187
 outer loop, :215-326 AddScanPairCost, registration.cpp:67-76 weights) with the Ceres loop of test_lm_independent.py, and
-compared with the oracle on the same cell sets: outer and inner iteration counts, residual count, final cost, pose.
+compared with the oracle on the same cell sets: outer and inner iteration counts, residual count, final cost, pose and the
+covariance of GetCovariance (:392-433).
 CPU only.  What is shared with the oracle is the input (cell sets from the oracle's surface-point stage) and nothing else:
 the nearest neighbour is a brute-force float32 search, the P2D factor comes from numpy.linalg, the solve is the QR-based loop.
 """
@@ -94,7 +95,13 @@ def register_py(sets, poses, cost, weight_opt, reg=1.0, cov_scale=1.0, radius=2.
                 break
         prev_score, prev_par = final_cost, x.copy()
         itr += 1
-    return success, x, itr, inner_total, nres, final_cost
+    cov = None
+    if success and nres - 3 != 0:                                                   # GetCovariance              :392-433
+        _, _, Jc = fun(x, True)                                                     # the LAST problem, loss applied, at the final x
+        cmat = 30 * (final_cost / (nres - 3)) * np.linalg.inv(Jc.T @ Jc)             #                            :418
+        cov = np.eye(6)
+        cov[:2, :2] = cmat[:2, :2]; cov[5, 5] = cmat[2, 2]; cov[0, 5] = cmat[0, 2]; cov[5, 0] = cmat[2, 0]   # (1,5) / (5,1) stay 0  :426-430
+    return success, x, itr, inner_total, nres, final_cost, cov
 
 
 @pytest.mark.parametrize("cost,wopt,reg", [("P2L", 0, 1.0), ("P2D", 4, 0.1), ("P2D", 0, 1.0), ("P2P", 2, 1.0), ("P2L", 3, 1.0)])
@@ -104,10 +111,12 @@ def test_oracle_register_matches_an_independent_numpy_register(orc, cost, wopt, 
     sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(K + 1)]
     P = tp[:K + 1].copy(); P[K] = tp[K] + np.asarray(offset)
     cfg = orc.reg_cfg(cost=cost, loss="Huber", loss_limit=0.1, weight_opt=wopt, regularization=reg, cov_scale=1.0)
-    ok, op, _, st, _ = orc.register(sets, P, cfg)
-    okp, x, itr, inner, nres, fc = register_py(sets, P, cost, wopt, reg=reg)
+    ok, op, ocov, st, _ = orc.register(sets, P, cfg)
+    okp, x, itr, inner, nres, fc, cov = register_py(sets, P, cost, wopt, reg=reg)
     assert ok and okp
     assert (itr, inner, nres) == (st.outer_iterations, st.inner_iterations, st.num_residuals), \
         ((itr, inner, nres), (st.outer_iterations, st.inner_iterations, st.num_residuals))
     np.testing.assert_allclose(fc, st.final_cost, rtol=1e-9)
     assert np.hypot(*(x[:2] - op[K, :2])) < 1e-9 and abs(x[2] - op[K, 2]) < 1e-10
+    np.testing.assert_allclose(ocov, cov, rtol=1e-6, atol=1e-15)
+    assert ocov[1, 5] == 0.0 and ocov[5, 1] == 0.0 and ocov[0, 5] != 0.0
