@@ -87,6 +87,30 @@ def _huber(s, a):
     return rho, rho1
 
 
+def _loss(name, s, a):
+    """(rho, rho') of the Ceres loss functions Registration::GetLoss hands out (registration.cpp:78-97; loss_function.cc).  All
+    have rho'' <= 0, so Ceres' Corrector only scales rows by sqrt(rho')."""
+    tiny = np.finfo(np.float64).tiny
+    if name == "Huber":
+        return _huber(s, a)
+    if name == "Cauchy":
+        b = a * a
+        return b * np.log1p(s / b), np.maximum(tiny, 1.0 / (1.0 + s / b))
+    if name == "SoftLOne":
+        b = a * a
+        t = np.sqrt(1.0 + s / b)
+        return 2 * b * (t - 1.0), np.maximum(tiny, 1.0 / t)
+    if name == "Tukey":
+        b = a * a
+        v = 1.0 - s / b
+        return np.where(s <= b, b / 3.0 * (1.0 - v ** 3), b / 3.0), np.where(s <= b, v * v, 0.0)
+    if name == "Combined":                                                # ComposedLoss(HuberLoss(1), CauchyLoss(1))
+        g, g1 = _loss("Cauchy", s, 1.0)
+        f, f1 = _loss("Huber", g, 1.0)
+        return f, f1 * g1
+    return s, np.ones_like(s)                                             # None: ScaledLoss(nullptr, w)
+
+
 def _problem(orc, cost, seed, offset):
     """One outer iteration's residual blocks exactly as the reference builds them (n_scan_normal.cpp:215-326), from the
     oracle's association table: (p, q, A) per block with r = A (R(psi) p + t - q)."""

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import helpers
-from test_lm_independent import _ceres_lm, _huber
+from test_lm_independent import _ceres_lm, _loss
 
 
 def _se2(v):
@@ -53,7 +53,7 @@ def _associate(tar, src, Ttar, Tsrc, radius, cost, weight_opt, reg, cov_scale):
 
 
 def register_py(sets, poses, cost, weight_opt, reg=1.0, cov_scale=1.0, radius=2.0, max_outer=8, min_outer=3, max_inner=20,
-                loss_limit=0.1):
+                loss_limit=0.1, loss="Huber"):
     K = len(sets) - 1
     rows = 1 if cost == "P2L" else 2
     x = np.array(poses[K], dtype=np.float64)
@@ -72,8 +72,8 @@ def register_py(sets, poses, cost, weight_opt, reg=1.0, cov_scale=1.0, radius=2.
             c, s = np.cos(y[2]), np.sin(y[2])
             Rp = np.stack([c * p[:, 0] - s * p[:, 1], s * p[:, 0] + c * p[:, 1]], 1)
             res = np.einsum("nij,nj->ni", A, Rp + y[:2] - q)[:, :rows]
-            rho, rho1 = _huber((res * res).sum(1), loss_limit)
-            c_ = 0.5 * (w * rho).sum()                                              # ScaledLoss(Huber, w)       :277
+            rho, rho1 = _loss(loss, (res * res).sum(1), loss_limit)
+            c_ = 0.5 * (w * rho).sum()                                              # ScaledLoss(loss, w)        :277
             if not want_jac:
                 return c_, None, None
             Je = np.zeros((p.shape[0], 2, 3)); Je[:, 0, 0] = 1; Je[:, 1, 1] = 1
@@ -120,3 +120,22 @@ def test_oracle_register_matches_an_independent_numpy_register(orc, cost, wopt, 
     assert np.hypot(*(x[:2] - op[K, :2])) < 1e-9 and abs(x[2] - op[K, 2]) < 1e-10
     np.testing.assert_allclose(ocov, cov, rtol=1e-6, atol=1e-15)
     assert ocov[1, 5] == 0.0 and ocov[5, 1] == 0.0 and ocov[0, 5] != 0.0
+
+
+@pytest.mark.parametrize("loss", ["Cauchy", "SoftLOne", "Tukey", "Combined", "None"])
+@pytest.mark.parametrize("cost,wopt,reg,seed,K,offset", [("P2D", 4, 0.1, 6, 2, (-0.8, 0.5, -0.03)), ("P2L", 1, 1.0, 9, 3, (0.5, 0.4, 0.02))])
+def test_oracle_register_matches_the_numpy_register_for_every_loss(orc, loss, cost, wopt, reg, seed, K, offset):
+    """Registration::GetLoss (registration.cpp:78-97): Cauchy, SoftLOne, Tukey, Huber(1) o Cauchy(1), and no loss."""
+    im, tp = helpers.scan_images(seed, K)
+    sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(K + 1)]
+    P = tp[:K + 1].copy(); P[K] = tp[K] + np.asarray(offset)
+    cfg = orc.reg_cfg(cost=cost, loss=loss, loss_limit=0.1, weight_opt=wopt, regularization=reg, cov_scale=1.0)
+    ok, op, ocov, st, _ = orc.register(sets, P, cfg)
+    okp, x, itr, inner, nres, fc, cov = register_py(sets, P, cost, wopt, reg=reg, loss=loss)
+    assert ok == okp
+    assert (itr, inner, nres) == (st.outer_iterations, st.inner_iterations, st.num_residuals), \
+        ((itr, inner, nres), (st.outer_iterations, st.inner_iterations, st.num_residuals))
+    np.testing.assert_allclose(fc, st.final_cost, rtol=1e-9)
+    assert np.hypot(*(x[:2] - op[K, :2])) < 1e-9 and abs(x[2] - op[K, 2]) < 1e-10
+    if ok:
+        np.testing.assert_allclose(ocov, cov, rtol=1e-6, atol=1e-15)
