@@ -139,3 +139,40 @@ def test_oracle_register_matches_the_numpy_register_for_every_loss(orc, loss, co
     assert np.hypot(*(x[:2] - op[K, :2])) < 1e-9 and abs(x[2] - op[K, 2]) < 1e-10
     if ok:
         np.testing.assert_allclose(ocov, cov, rtol=1e-6, atol=1e-15)
+
+
+def get_cost_py(sets, poses, cost, weight_opt, reg=1.0, cov_scale=1.0, radius=2.0, loss_limit=0.1, loss="Huber"):
+    """n_scan_normal_reg::GetCost (n_scan_normal.cpp:187-213) after a Register (itr_ > 1: the association radius is not doubled):
+    one association at the given poses and 1/2 sum w rho(s)."""
+    K = len(sets) - 1
+    rows = 1 if cost == "P2L" else 2
+    x = np.asarray(poses[K], dtype=np.float64)
+    parts = [_associate(sets[i], sets[K], _se2(poses[i]), _se2(x), radius, cost, weight_opt, reg, cov_scale) for i in range(K)]
+    p, q, A, w = (np.concatenate([pt[k] for pt in parts]) for k in range(4))
+    c, s = np.cos(x[2]), np.sin(x[2])
+    Rp = np.stack([c * p[:, 0] - s * p[:, 1], s * p[:, 0] + c * p[:, 1]], 1)
+    res = np.einsum("nij,nj->ni", A, Rp + x[:2] - q)[:, :rows]
+    rho, _ = _loss(loss, (res * res).sum(1), loss_limit)
+    return rows * p.shape[0] > 1, 0.5 * (w * rho).sum(), rows * p.shape[0]
+
+
+@pytest.mark.parametrize("cost,wopt,reg", [("P2D", 4, 0.1), ("P2L", 0, 1.0)])
+def test_oracle_get_cost_matches_the_numpy_get_cost_on_the_sampling_grid(orc, cost, wopt, reg):
+    """The 27 GetCost evaluations of approximateCovarianceBySampling (odometrykeyframefuser.cpp:261-380: +-0.2 m, +-0.00218 rad,
+    three per axis) around a registered pose: every sample re-associates (n_scan_normal.cpp:199-202)."""
+    K = 2
+    im, tp = helpers.scan_images(12, K)
+    sets = [helpers.oracle_cells(orc, im[i], radius=3.0)[1] for i in range(K + 1)]
+    cfg = orc.reg_cfg(cost=cost, loss="Huber", loss_limit=0.1, weight_opt=wopt, regularization=reg, cov_scale=1.0)
+    P = tp[:K + 1].copy()
+    n = 0
+    for t in np.linspace(-0.00218125, 0.00218125, 3):
+        for dx in np.linspace(-0.2, 0.2, 3):
+            for dy in np.linspace(-0.2, 0.2, 3):
+                Q = P.copy(); Q[K] = P[K] + [dx, dy, t]
+                ok, c, nres = orc.get_cost(sets, Q, cfg)
+                okp, cp, nresp = get_cost_py(sets, Q, cost, wopt, reg=reg)
+                assert ok and okp and nres == nresp > 100
+                np.testing.assert_allclose(c, cp, rtol=1e-11)
+                n += 1
+    assert n == 27
