@@ -18,6 +18,7 @@
 #ifndef CFEAR_B200_HPP_
 #define CFEAR_B200_HPP_
 
+#include <algorithm>
 #include <array>
 #include <cassert>
 #include <cmath>
@@ -250,6 +251,24 @@ inline void Compensate(PointCloud& cloud, const Affine3d& Tmotion, bool ccw) {
   if (cloud.points.empty()) return;
   if (cfear_compensate(Backend::get().ctx(), cloud.points.data(), (int)cloud.points.size(), mot.data(), ccw ? 1 : 0) != CFEAR_OK)
     throw std::runtime_error(std::string("cfear_compensate: ") + cfear_last_error());
+}
+
+// The two clouds of a frame (filtered + peaks, odometrykeyframefuser.cpp:148-149) in ONE device round trip: the points are
+// independent, so concatenating them changes nothing but the number of copies and synchronisations per frame.
+inline void Compensate(PointCloud& cloud, PointCloud& cloud_peaks, const Affine3d& Tmotion, bool ccw) {
+  const size_t n1 = cloud.points.size(), n2 = cloud_peaks.points.size();
+  const cfear_config& g = Backend::get().cfg();
+  const size_t cap = (size_t)g.max_batch * (size_t)g.azimuths * (size_t)g.k_strongest;      // what cfear_compensate accepts
+  if (n1 == 0 || n2 == 0 || n1 + n2 > cap) { Compensate(cloud, Tmotion, ccw); Compensate(cloud_peaks, Tmotion, ccw); return; }
+  std::vector<double> mot;
+  Affine3dToVectorXYeZ(Tmotion, mot);
+  std::vector<PointXYZI> both(n1 + n2);
+  std::copy(cloud.points.begin(), cloud.points.end(), both.begin());
+  std::copy(cloud_peaks.points.begin(), cloud_peaks.points.end(), both.begin() + n1);
+  if (cfear_compensate(Backend::get().ctx(), both.data(), (int)both.size(), mot.data(), ccw ? 1 : 0) != CFEAR_OK)
+    throw std::runtime_error(std::string("cfear_compensate: ") + cfear_last_error());
+  std::copy(both.begin(), both.begin() + n1, cloud.points.begin());
+  std::copy(both.begin() + n1, both.end(), cloud_peaks.points.begin());
 }
 
 // ---- cell / MapPointNormal (pointnormal.h:45-199) -------------------------------------------------------------
@@ -759,8 +778,8 @@ class OdometryKeyframeFuser {
   void processFrame(CloudPtr& cloud, CloudPtr& cloud_peaks, const uint64_t& t) {
     const Affine3d TprevMot(Tmot);
     if (par.compensate) {
-      Compensate(*cloud, TprevMot, par.radar_ccw);
-      if (cloud_peaks) Compensate(*cloud_peaks, TprevMot, par.radar_ccw);
+      if (cloud_peaks) Compensate(*cloud, *cloud_peaks, TprevMot, par.radar_ccw);     // :148-149, one round trip for both
+      else Compensate(*cloud, TprevMot, par.radar_ccw);
     }
     std::vector<Matrix6d> cov_vek;
     std::vector<MapNormalPtr> scans_vek;
