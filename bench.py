@@ -349,7 +349,9 @@ def main():
             "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_scan": alg[names[dom]],
             "duration_ms": serial_ms[dom],
-            "duration_note": f"{names[dom]} alone: average over {nser} stream-ordered steps run right after the timed region (CUDA events on its stream)",
+            "duration_note": f"{names[dom]} alone: average over {nser} stream-ordered steps run right after the timed region (CUDA events on its stream); "
+                             "a launch with the GPU to itself takes K5 in its 192-thread x 2-per-SM form at this batch size, the overlapped steps of the "
+                             "timed region use 128 x 3 (alone: 0.38 ms; DESIGN.md section 3)",
             "stage_ms_alone": dict(zip(names, serial_ms)),
             "stage_frac_of_hbm_peak_alone": {n: (alg[n] * nprob / (t * 1e-3) / 1e9 / hbm_peak if t > 0 else None)
                                              for n, t in zip(names, serial_ms)},
