@@ -56,8 +56,8 @@ def voxel_grid_np(cloud, leaf):
     return np.array(cents, np.float32)
 
 
-def cells_np(cloud, radius, weight_intensity=True, origin=(0.0, 0.0)):
-    cents = voxel_grid_np(cloud, np.float32(radius))
+def cells_np(cloud, radius, weight_intensity=True, origin=(0.0, 0.0), downsample_factor=1.0):
+    cents = voxel_grid_np(cloud, np.float32(np.float32(radius) / downsample_factor))          # pointnormal.cpp:279
     pts3 = np.ascontiguousarray(cloud[:, :3], np.float32)                           # search::KdTree<PointXYZI>: x, y, z
     index = cv2.flann_Index(pts3, {"algorithm": 4, "leaf_max_size": 15})
     r2 = float(np.float32(radius * radius))
@@ -111,3 +111,16 @@ def test_oracle_surface_points_match_an_independent_numpy_flann_stage(orc, seed,
     np.testing.assert_allclose(got["normal"], exp["normal"], atol=1e-7)
     np.testing.assert_allclose(got["planarity"], exp["planarity"], rtol=1e-8)
     np.testing.assert_allclose(got["avg_intensity"], exp["avg_intensity"], rtol=1e-12)
+
+
+def test_oracle_surface_points_with_a_downsample_factor(orc):
+    """MapPointNormal::downsample_factor = 2 (pointnormal.cpp:5, :279): voxel leaf r / 2, four times the centroids, same radius."""
+    im, _ = helpers.scan_images(4, 0)
+    idx, cnt = orc.kstrongest(im[0], 60, 12)
+    cloud = orc.cloud(im[0], idx, cnt)
+    got = orc.surface_points(cloud, 3.0, True, downsample_factor=2.0)
+    exp = cells_np(cloud, 3.0, True, downsample_factor=2.0)
+    assert got["mean"].shape[0] == exp["mean"].shape[0] > 500
+    assert np.array_equal(got["nsamples"], exp["nsamples"])
+    np.testing.assert_allclose(got["mean"], exp["mean"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got["cov"].reshape(-1, 2, 2), exp["cov"], rtol=1e-9, atol=1e-12)
